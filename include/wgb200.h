@@ -1,0 +1,280 @@
+/*
+ * wgb200.h — C ABI of libwgebra_b200.so: the B200-native (sm_100a CUDA) backend for the
+ * wgebra dense-linear-algebra surface of wgmath.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one piece of what sits under
+ * the Rust signatures of the reference (paths relative to /root/reference/crates/):
+ *
+ *   wgb_ctx_*            <-> wgcore/src/gpu.rs:15-79          GpuInstance (device + queue)
+ *   wgb_pass_*           <-> wgcore/src/kernel.rs:7-27        CommandEncoderExt::compute_pass
+ *   wgb_submit / sync    <-> queue.submit / device.poll(wait) (wgebra/src/linalg/gemm.rs:190-192,
+ *                                                              wgcore/src/tensor.rs:304-312)
+ *   wgb_buffer_*         <-> wgcore/src/tensor.rs:65-187      TensorBuilder::build / build_init
+ *                            wgcore/src/tensor.rs:227-265     copy_from / copy_from_view
+ *                            wgcore/src/tensor.rs:300-384     read_bytes / read_to / read
+ *   wgb_view_shape       <-> wgcore/src/shapes.rs:9-21        ViewShape (byte-identical, 24 B)
+ *   wgb_gemm             <-> wgebra/src/linalg/gemm.rs:65-127 Gemm::dispatch_generic
+ *                            + gemm.wgsl:29-199 (the four kernels)
+ *   wgb_gemv             <-> wgebra/src/linalg/gemv.rs:64-137 Gemv::dispatch_generic
+ *                            + gemv.wgsl:29-154
+ *   wgb_op_assign        <-> wgebra/src/linalg/op_assign.rs:71-94 + op_assign.wgsl:14-47
+ *   wgb_reduce           <-> wgebra/src/linalg/reduce.rs:100-113  + reduce.wgsl:12-96
+ *   wgb_event_*          <-> wgcore/src/timestamps.rs:9-248   GpuTimestamps
+ *
+ * Extensions that have no reference counterpart (named by BASELINE.json north_star):
+ *   wgb_gemm_ex            bf16 operands / bf16 output, f32 compute-mode selection
+ *   wgb_dot                sum_i a[i]*b[i]   (the reference only has SqNorm = x.x)
+ *   wgb_reduce_columns     one launch for Reduce over every column of a matrix view
+ *                          (reference: one Reduce dispatch per GpuMatrix::column(j))
+ *   wgb_comm_*, wgb_gemm_row_sharded   8-GPU row-sharded GEMM + all-gather of C (NCCL / NVLink)
+ *   wgb_fill_uniform       seeded synthetic inputs generated in HBM (bench / tests)
+ *
+ * Conventions
+ *   - Plain C: opaque handles, POD structs, pointers and sizes.  No torch / C++ types.
+ *   - Every function returns a wgb_status.  The reference *panics* on a dimension
+ *     mismatch (assert_eq! at gemm.rs:91-95, gemv.rs:89-90,122, op_assign.rs:82-86);
+ *     here that is WGB_ERR_DIM_MISMATCH and the host shim turns it back into a panic /
+ *     exception.  The reference silently *skips* a dispatch whose grid is empty or that
+ *     binds a zero-sized buffer (kernel.rs:111-113,121-123,144); here that is WGB_OK
+ *     with nothing enqueued.
+ *   - Matrices are column-major; all shape fields are u32 *element* counts exactly as in
+ *     ViewShape.  Kernels widen to 64-bit internally.
+ *   - Work is enqueued asynchronously on the pass's CUDA stream, in order (wgpu executes
+ *     the dispatches of a pass in order with storage hazards resolved, so one pass / one
+ *     encoder <-> one stream).  Nothing is guaranteed complete until wgb_ctx_sync,
+ *     wgb_buffer_read or wgb_event_elapsed_ms.
+ *   - There is no CPU fallback: every entry point fails with WGB_ERR_CUDA /
+ *     WGB_ERR_NO_DEVICE when no sm_100 device is usable.
+ *   - Superset rule: the reference kernels are undefined unless every dimension, stride
+ *     and offset is a multiple of 4 (shape.wgsl:64-66) and K is a multiple of 256 / 128
+ *     for the *_fast variants (gemm.wgsl:40-41, gemv.wgsl:39-40).  This library computes
+ *     the mathematically defined result for every well-formed view, and never touches
+ *     memory outside the view.
+ */
+#ifndef WGB200_H
+#define WGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WGB200_ABI_VERSION 1
+
+typedef struct wgb_ctx wgb_ctx;       /* device + in-order queue  (GpuInstance)            */
+typedef struct wgb_pass wgb_pass;     /* command encoder + compute pass => a CUDA stream  */
+typedef struct wgb_buffer wgb_buffer; /* wgpu::Buffer                                      */
+typedef struct wgb_event wgb_event;   /* one GPU timestamp                                 */
+
+typedef enum wgb_status {
+    WGB_OK = 0,
+    WGB_ERR_INVALID = 1,       /* null handle, unknown enum value, misuse                      */
+    WGB_ERR_DIM_MISMATCH = 2,  /* the reference's assert_eq! "dimension mismatch" panics       */
+    WGB_ERR_CUDA = 3,          /* a CUDA runtime / driver call failed                          */
+    WGB_ERR_UNSUPPORTED = 4,   /* dtype / variant combination not implemented                  */
+    WGB_ERR_OOM = 5,           /* device or pinned-host allocation failed                      */
+    WGB_ERR_NCCL = 6,          /* NCCL missing or a collective failed                          */
+    WGB_ERR_OUT_OF_BOUNDS = 7, /* a view reaches past the end of its buffer                    */
+    WGB_ERR_NO_DEVICE = 8      /* no CUDA device with compute capability 10.x                  */
+} wgb_status;
+
+/* crates/wgcore/src/shapes.rs:9-21 — identical field order and size (24 bytes). */
+typedef struct wgb_view_shape {
+    uint32_t size[3];    /* rows, columns, matrices                                  */
+    uint32_t stride;     /* elements between two columns                             */
+    uint32_t stride_mat; /* elements between two matrices                            */
+    uint32_t offset;     /* index of the first element in the underlying buffer      */
+} wgb_view_shape;
+
+typedef enum wgb_dtype { WGB_F32 = 0, WGB_BF16 = 1 } wgb_dtype;
+
+/* wgebra/src/linalg/gemm.rs:25-35 (same order as the Rust enum) */
+typedef enum wgb_gemm_variant {
+    WGB_GEMM = 0,
+    WGB_GEMM_FAST = 1,
+    WGB_GEMM_TR = 2,
+    WGB_GEMM_TR_FAST = 3
+} wgb_gemm_variant;
+
+/* wgebra/src/linalg/gemv.rs:24-34 */
+typedef enum wgb_gemv_variant {
+    WGB_GEMV = 0,
+    WGB_GEMV_FAST = 1,
+    WGB_GEMV_TR = 2,
+    WGB_GEMV_TR_FAST = 3
+} wgb_gemv_variant;
+
+/* wgebra/src/linalg/op_assign.rs:15-26 */
+typedef enum wgb_op_assign_variant {
+    WGB_OP_ADD = 0,
+    WGB_OP_SUB = 1,
+    WGB_OP_MUL = 2,
+    WGB_OP_DIV = 3,
+    WGB_OP_COPY = 4
+} wgb_op_assign_variant;
+
+/* wgebra/src/linalg/reduce.rs:16-27 */
+typedef enum wgb_reduce_op {
+    WGB_RED_MIN = 0,
+    WGB_RED_MAX = 1,
+    WGB_RED_SUM = 2,
+    WGB_RED_PROD = 3,
+    WGB_RED_SQNORM = 4
+} wgb_reduce_op;
+
+/* How an f32 x f32 GEMM is computed on the tensor cores. */
+typedef enum wgb_f32_mode {
+    WGB_F32_AUTO = 0,   /* 3xTF32 when the views are TMA-eligible, else SIMT FFMA        */
+    WGB_F32_3XTF32 = 1, /* error-compensated hi/lo split, f32-level accuracy (parity gate)*/
+    WGB_F32_TF32 = 2,   /* single-pass TF32: fast, ~1e-4 relative (informational)        */
+    WGB_F32_SIMT = 3    /* FFMA on CUDA cores: exact f32 products                         */
+} wgb_f32_mode;
+
+/* wgpu::BufferUsages bit values, so a Rust shim can pass `usage.bits()` straight through. */
+enum {
+    WGB_USAGE_MAP_READ = 1 << 0, /* host-visible staging buffer: allocated as pinned host memory */
+    WGB_USAGE_MAP_WRITE = 1 << 1,
+    WGB_USAGE_COPY_SRC = 1 << 2,
+    WGB_USAGE_COPY_DST = 1 << 3,
+    WGB_USAGE_UNIFORM = 1 << 6,
+    WGB_USAGE_STORAGE = 1 << 7
+};
+
+/* ------------------------------------------------------------------ library ---------- */
+int wgb_abi_version(void);
+/* Thread-local, human-readable description of the last non-OK status on this thread. */
+const char *wgb_last_error_string(void);
+
+/* ------------------------------------------------------------------ context ---------- */
+/* gpu.rs:15-58 GpuInstance::new: pick the device, create its in-order queue (stream). */
+wgb_status wgb_ctx_create(int device_ordinal, wgb_ctx **out);
+wgb_status wgb_ctx_destroy(wgb_ctx *ctx);
+/* device.poll(PollType::wait()) — tensor.rs:304-312: block until all submitted work is done. */
+wgb_status wgb_ctx_sync(wgb_ctx *ctx);
+wgb_status wgb_ctx_device_info(wgb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor,
+                               size_t *total_mem_bytes, char *name, size_t name_len);
+/* Number of kernels this library has launched on this context (bench.py's gpu_launches). */
+wgb_status wgb_ctx_launch_count(wgb_ctx *ctx, uint64_t *count);
+/* The context's queue as a cudaStream_t (for interop with a host framework's allocator). */
+wgb_status wgb_ctx_stream(wgb_ctx *ctx, void **cuda_stream);
+
+/* ------------------------------------------------------------------ passes ----------- */
+/* kernel.rs:15-26 compute_pass(label, timestamps): begin recording on the queue.  `begin_ts`
+ * / `end_ts` may be NULL; when given they are recorded at pass begin / end (timestamps.rs:63-70). */
+wgb_status wgb_pass_begin(wgb_ctx *ctx, const char *label, wgb_event *begin_ts, wgb_event *end_ts,
+                          wgb_pass **out);
+/* drop(pass): ends the pass.  The handle is invalid afterwards. */
+wgb_status wgb_pass_end(wgb_pass *pass);
+/* queue.submit(encoder.finish()): CUDA work is already in flight, this only flushes. */
+wgb_status wgb_submit(wgb_ctx *ctx);
+
+/* ------------------------------------------------------------------ buffers ---------- */
+/* tensor.rs:112-129 TensorBuilder::build: uninitialised buffer of `bytes` bytes. */
+wgb_status wgb_buffer_create(wgb_ctx *ctx, size_t bytes, uint32_t usage, wgb_buffer **out);
+/* tensor.rs:149-161 build_bytes / :175-186 build_init: create + upload from host memory. */
+wgb_status wgb_buffer_create_init(wgb_ctx *ctx, const void *host_data, size_t bytes, uint32_t usage,
+                                  wgb_buffer **out);
+/* Wrap device memory owned by the caller (not freed on destroy). */
+wgb_status wgb_buffer_wrap(wgb_ctx *ctx, void *device_ptr, size_t bytes, wgb_buffer **out);
+wgb_status wgb_buffer_destroy(wgb_buffer *buf);
+wgb_status wgb_buffer_size(const wgb_buffer *buf, size_t *bytes);
+wgb_status wgb_buffer_device_ptr(const wgb_buffer *buf, void **ptr);
+/* queue.write_buffer: asynchronous host -> device copy on the queue (host memory must stay
+ * valid until the next sync; pinned memory makes it truly asynchronous). */
+wgb_status wgb_buffer_write(wgb_ctx *ctx, wgb_buffer *dst, size_t dst_offset_bytes,
+                            const void *host_src, size_t bytes);
+/* tensor.rs:227-233 copy_from / :244-265 copy_from_view: buffer-to-buffer copy on the pass's
+ * stream (pass may be NULL: the copy is then recorded on the context queue, as
+ * CommandEncoder::copy_buffer_to_buffer is outside any compute pass). */
+wgb_status wgb_buffer_copy(wgb_ctx *ctx, wgb_pass *pass, wgb_buffer *dst, size_t dst_offset_bytes,
+                           const wgb_buffer *src, size_t src_offset_bytes, size_t bytes);
+/* tensor.rs:300-384 read / read_to: blocks until all queued work is done, then copies out. */
+wgb_status wgb_buffer_read(wgb_ctx *ctx, const wgb_buffer *src, size_t src_offset_bytes,
+                           void *host_dst, size_t bytes);
+/* Pinned host memory for callers that want asynchronous uploads / downloads. */
+wgb_status wgb_host_alloc(size_t bytes, void **out);
+wgb_status wgb_host_free(void *ptr);
+
+/* ------------------------------------------------------------------ operators -------- */
+/* gemm.rs:65-127.  out = m1 * m2 (GEMM, GEMM_FAST) or tr(m1) * m2 (GEMM_TR, GEMM_TR_FAST),
+ * overwrite, batched over size[2].  f32 operands and output; equivalent to
+ * wgb_gemm_ex(.., WGB_F32, WGB_F32, WGB_F32_AUTO).  The four variants give the same result
+ * (they differ only in the reference's launch shape); the variant selects tr / non-tr. */
+wgb_status wgb_gemm(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out,
+                    const wgb_view_shape *out_shape, const wgb_buffer *m1,
+                    const wgb_view_shape *m1_shape, const wgb_buffer *m2,
+                    const wgb_view_shape *m2_shape);
+/* in_dtype: element type of m1 and m2; out_dtype: element type of out (accumulation is f32). */
+wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out,
+                       const wgb_view_shape *out_shape, const wgb_buffer *m1,
+                       const wgb_view_shape *m1_shape, const wgb_buffer *m2,
+                       const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                       wgb_f32_mode f32_mode);
+/* Which kernel family the last wgb_gemm* call on this pass dispatched to:
+ * 0 none, 1 SIMT FFMA, 2 tcgen05 bf16, 3 tcgen05 tf32, 4 tcgen05 3xtf32. */
+wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);
+
+/* gemv.rs:64-137.  out = m * v or tr(m) * v; v / out may carry several columns and batches. */
+wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out,
+                    const wgb_view_shape *out_shape, const wgb_buffer *m,
+                    const wgb_view_shape *m_shape, const wgb_buffer *v,
+                    const wgb_view_shape *v_shape);
+
+/* op_assign.rs:71-94.  a[i] = a[i] (op) b[i]; only size[0] and offset of the shapes are used
+ * (shape.wgsl:36-38 iv()). */
+wgb_status wgb_op_assign(wgb_pass *pass, wgb_op_assign_variant op, wgb_buffer *in_out_a,
+                         const wgb_view_shape *a_shape, const wgb_buffer *in_b,
+                         const wgb_view_shape *b_shape);
+
+/* reduce.rs:100-113.  result[0] = reduce(op, value[offset .. offset+size[0]]). */
+wgb_status wgb_reduce(wgb_pass *pass, wgb_reduce_op op, const wgb_buffer *value,
+                      const wgb_view_shape *value_shape, wgb_buffer *result);
+
+/* Extension: result[0] = sum_i a[i] * b[i]. */
+wgb_status wgb_dot(wgb_pass *pass, const wgb_buffer *a, const wgb_view_shape *a_shape,
+                   const wgb_buffer *b, const wgb_view_shape *b_shape, wgb_buffer *result);
+
+/* Extension: out[offset + j] = reduce(op, column j of matrix t) for every column of the view,
+ * in one launch (out is a vector view with size[0] == m.size[1] * m.size[2]). */
+wgb_status wgb_reduce_columns(wgb_pass *pass, wgb_reduce_op op, const wgb_buffer *m,
+                              const wgb_view_shape *m_shape, wgb_buffer *out,
+                              const wgb_view_shape *out_shape);
+
+/* Seeded U[0,1) fill of a matrix view: element (i, j) of matrix t gets
+ * f(seed, row0 + i, col0 + j + t * size[1]); bit-identical to oracle.uniform().  dtype selects
+ * f32 or bf16 (round-to-nearest-even of the f32 stream). */
+wgb_status wgb_fill_uniform(wgb_pass *pass, wgb_buffer *buf, const wgb_view_shape *shape,
+                            wgb_dtype dtype, uint64_t seed, uint32_t row0, uint32_t col0);
+
+/* ------------------------------------------------------------------ timestamps ------- */
+/* timestamps.rs: one wgb_event <-> one timestamp slot; elapsed <-> wait_for_results_ms. */
+wgb_status wgb_event_create(wgb_ctx *ctx, wgb_event **out);
+wgb_status wgb_event_destroy(wgb_event *ev);
+wgb_status wgb_event_record(wgb_event *ev, wgb_pass *pass /* NULL: context queue */);
+wgb_status wgb_event_elapsed_ms(wgb_event *begin, wgb_event *end, float *ms); /* blocks on `end` */
+
+/* ------------------------------------------------------------------ multi-GPU -------- */
+/* One process per GPU.  Rank 0 calls wgb_comm_get_unique_id and distributes the 128-byte id
+ * (e.g. through torch.distributed); every rank then calls wgb_comm_init_rank. */
+#define WGB_COMM_ID_BYTES 128
+wgb_status wgb_comm_get_unique_id(void *id_out /* WGB_COMM_ID_BYTES */);
+wgb_status wgb_comm_init_rank(wgb_ctx *ctx, int nranks, int rank, const void *id);
+wgb_status wgb_comm_destroy(wgb_ctx *ctx);
+/* Row-sharded GEMM: rank p owns rows [p*M/P, (p+1)*M/P) of m1 and of the
+ * product.  m1_local is the local [M/P, K] row block (or [K, M/P] for the TR variants), m2 the
+ * full [K, N] matrix (replicated).  out_gathered receives all P row-block panels back to back:
+ * a cube view size = [M/P, N, P], stride = M/P, stride_mat = (M/P)*N, i.e. panel p is rows
+ * [p*M/P, ..) of the product.  The all-gather is chunked by column panel and overlapped with
+ * the remaining tiles of the local GEMM.  `n_chunks` <= 0 selects the default. */
+wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out_gathered,
+                                const wgb_buffer *m1_local, const wgb_view_shape *m1_local_shape,
+                                const wgb_buffer *m2, const wgb_view_shape *m2_shape,
+                                wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode f32_mode,
+                                int n_chunks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WGB200_H */

@@ -1,0 +1,508 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the reference-shaped host API and the
+C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): f32 results within 1e-5 relative of the oracle, bf16 within
+1e-2; op_assign is bit-exact (the reference's own bound there is 1e-7, op_assign.rs:154).
+The first block replays the reference's four unit tests (gemm.rs:144-202, gemv.rs:153-197,
+op_assign.rs:109-157, reduce.rs:139-179); the rest covers what those tests never exercise:
+sub-views, offsets, batches, ragged sizes, and the full BASELINE.json sizes through
+size-independent properties."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import wgmath_b200 as w
+from oracle import oracle as O
+from tests.helpers import SEED_A, SEED_B, SEED_OUT, SEED_V, STORAGE, oshape, rel_err, run_pass, upload
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 1e-5
+BF16_TOL = 1e-2
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def cm(flat, r, c):
+    return np.asarray(flat).reshape(c, r).T
+
+
+# ------------------------------------------------------------------ reference test replays
+@pytest.mark.parametrize("variant", [w.GemmVariant.Gemm, w.GemmVariant.GemmTr, w.GemmVariant.GemmFast, w.GemmVariant.GemmTrFast])
+def test_gpu_gemm_reference_replay(gpu, shapes, variant):
+    n = 256
+    m1c, m2c = O.uniform(SEED_A, n, n), O.uniform(SEED_B, n, n)
+    gemm = w.Gemm.from_device(gpu.device())
+    m1 = w.TensorBuilder.matrix(n, n, STORAGE).build_init(gpu.device(), m1c)
+    m2 = w.TensorBuilder.matrix(n, n, STORAGE).build_init(gpu.device(), m2c)
+    result = w.TensorBuilder.matrix(n, n, STORAGE).build_init(gpu.device(), np.zeros(n * n, np.float32))
+    staging = w.TensorBuilder.matrix(n, n, w.BufferUsages.MAP_READ | w.BufferUsages.COPY_DST).build(gpu.device())
+    enc = gpu.device().create_command_encoder()
+    p = enc.compute_pass("test", None)
+    gemm.dispatch_generic(gpu.device(), shapes, p, result.as_embedded_view(), m1.as_embedded_view(), m2.as_embedded_view(), variant)
+    p.end()
+    staging.copy_from(enc, result)
+    gpu.queue().submit(enc.finish())
+    got = staging.read(gpu.device())
+    ref = np.zeros(n * n, np.float32)
+    assert O.gemm(int(variant), ref, O.shape(n, n), m1c, O.shape(n, n), m2c, O.shape(n, n)) == O.ORC_OK
+    assert rel_err(got, ref) < F32_TOL
+    a, b = cm(m1c, n, n).astype(np.float64), cm(m2c, n, n).astype(np.float64)
+    exact = (a.T if variant in (w.GemmVariant.GemmTr, w.GemmVariant.GemmTrFast) else a) @ b
+    assert np.max(np.abs(cm(got, n, n) - exact)) < 1e-3          # the reference's own bound, gemm.rs:200
+
+
+@pytest.mark.parametrize("variant", [w.GemvVariant.Gemv, w.GemvVariant.GemvTr, w.GemvVariant.GemvFast, w.GemvVariant.GemvTrFast])
+def test_gpu_gemv_reference_replay(gpu, shapes, variant):
+    n = 1024
+    mc, vc, oc = O.uniform(SEED_A, n, n), O.uniform(SEED_V, n), O.uniform(SEED_OUT, n)
+    gemv = w.Gemv.from_device(gpu.device())
+    m = w.TensorBuilder.matrix(n, n, STORAGE).build_init(gpu.device(), mc)
+    v = w.TensorBuilder.vector(n, STORAGE).build_init(gpu.device(), vc)
+    result = w.TensorBuilder.vector(n, STORAGE).build_init(gpu.device(), oc)      # pre-randomised: overwrite semantics
+    run_pass(gpu, lambda p: gemv.dispatch_generic(gpu.device(), shapes, p, result, m, v, variant))
+    got = result.read()
+    ref = oc.copy()
+    rc, _ = O.gemv(int(variant), ref, O.shape(n), mc, O.shape(n, n), vc, O.shape(n))
+    assert rc == O.ORC_OK and rel_err(got, ref) < F32_TOL
+
+
+@pytest.mark.parametrize("op", list(w.OpAssignVariant))
+def test_gpu_op_assign_reference_replay(gpu, shapes, op):
+    n = 1757
+    i = np.arange(n, dtype=np.float32)
+    v0, v1 = i + np.float32(0.1), i * np.float32(10.0) + np.float32(0.1)
+    a = w.TensorBuilder.vector(n, STORAGE).build_init(gpu.device(), v0)
+    b = w.TensorBuilder.vector(n, STORAGE).build_init(gpu.device(), v1)
+    opk = w.OpAssign.new(gpu.device(), op)
+    run_pass(gpu, lambda p: opk.dispatch(gpu.device(), shapes, p, a, b))
+    ref = v0.copy()
+    assert O.op_assign(int(op), ref, O.shape(n), v1, O.shape(n)) == O.ORC_OK
+    np.testing.assert_array_equal(a.read(), ref)                  # bit-exact
+    np.testing.assert_array_equal(b.read(), v1)                   # b untouched
+
+
+@pytest.mark.parametrize("op", list(w.ReduceOp))
+def test_gpu_reduce_reference_replay(gpu, shapes, op):
+    n = 345
+    x = O.uniform(SEED_V, n)
+    vec = w.TensorBuilder.vector(n, STORAGE).build_init(gpu.device(), x)
+    res = w.TensorBuilder.scalar(STORAGE).build(gpu.device())
+    red = w.Reduce.new(gpu.device(), op)
+    run_pass(gpu, lambda p: red.dispatch(gpu.device(), shapes, p, vec, res))
+    got = float(res.read()[0])
+    ref = O.reduce(int(op), x, O.shape(n))
+    assert abs(got - ref) <= F32_TOL * abs(ref) + 1e-37
+    assert abs(got - red.eval_cpu(x)) < 1e-3                      # reduce.rs:176
+
+
+# ------------------------------------------------------------------ golden fixtures (BASELINE configs[0])
+def test_cfg1_gemm_64_golden(gpu, shapes):
+    g = np.load(os.path.join(GOLD, "cfg1_gemm64.npz"))
+    gemm = w.Gemm.from_device(gpu.device())
+    m1, m2 = upload(gpu, g["m1"], (64, 64)), upload(gpu, g["m2"], (64, 64))
+    for variant, key in [(w.GemmVariant.Gemm, "gemm"), (w.GemmVariant.GemmTr, "gemm_tr")]:
+        out = upload(gpu, np.full(64 * 64, -1.0, np.float32), (64, 64))
+        run_pass(gpu, lambda p: gemm.dispatch_generic(gpu.device(), shapes, p, out, m1, m2, variant))
+        assert rel_err(out.read(), g[key]) < F32_TOL
+
+
+def test_level12_golden(gpu, shapes):
+    l1 = np.load(os.path.join(GOLD, "level12.npz"))
+    gemv = w.Gemv.from_device(gpu.device())
+    m, v, x128 = upload(gpu, l1["m"], (128, 64)), upload(gpu, l1["v"], (64,)), upload(gpu, l1["x128"], (128,))
+    o1, o2 = upload(gpu, np.zeros(128, np.float32), (128,)), upload(gpu, np.zeros(64, np.float32), (64,))
+    run_pass(gpu, lambda p: (gemv.dispatch(gpu.device(), shapes, p, o1, m, v), gemv.dispatch_tr(gpu.device(), shapes, p, o2, m, x128)))
+    assert rel_err(o1.read(), l1["gemv"]) < F32_TOL and rel_err(o2.read(), l1["gemv_tr"]) < F32_TOL
+    x = upload(gpu, l1["x345"], (345,))
+    res = w.TensorBuilder.scalar(STORAGE).build(gpu.device())
+    for op, key in [(w.ReduceOp.Min, "min"), (w.ReduceOp.Max, "max"), (w.ReduceOp.Sum, "sum"), (w.ReduceOp.Prod, "prod"), (w.ReduceOp.SqNorm, "sqnorm")]:
+        red = w.Reduce.new(gpu.device(), op)
+        run_pass(gpu, lambda p: red.dispatch(gpu.device(), shapes, p, x, res))
+        assert abs(float(res.read()[0]) - l1[key]) <= F32_TOL * abs(l1[key]) + 1e-37
+
+
+# ------------------------------------------------------------------ seeded fill == oracle generator
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_fill_uniform_matches_oracle_bitwise(gpu, dtype):
+    r, c = 100, 37
+    t = w.TensorBuilder.matrix(r, c, STORAGE).build(gpu.device(), dtype)
+    run_pass(gpu, lambda p: w.fill_uniform(gpu.device(), p, t, SEED_A, row0=5, col0=9))
+    ref = O.uniform(SEED_A, r, c, row0=5, col0=9)
+    if dtype == "f32":
+        np.testing.assert_array_equal(t.read(), ref)
+    else:
+        np.testing.assert_array_equal(t.read(), O.bf16_bits(ref))
+
+
+# ------------------------------------------------------------------ GEMM: views, batches, ragged sizes
+def gemm_case(gpu, shapes, M, N, K, T=1, tr=False, pad=(0, 0, 0), off=(0, 0, 0), mode=None, tol=F32_TOL, dtype="f32", out_dtype="f32"):
+    """m1 / m2 / out live in padded parents with non-zero offsets; result checked against the float64 reference
+    (the oracle's literal WGSL restatement is only defined for multiples of 4)."""
+    ar, ac = (K, M) if tr else (M, K)
+    lda, ldb, ldc = ar + pad[0], K + pad[1], M + pad[2]
+    sa, sb, sc = lda * ac + 8, ldb * N + 8, ldc * N + 12
+    A = O.uniform(SEED_A, off[0] + sa * T)
+    B = O.uniform(SEED_B, off[1] + sb * T)
+    if dtype == "bf16":
+        A, B = O.to_bf16_rne(A), O.to_bf16_rne(B)
+    s1 = w.ViewShape((ar, ac, T), lda, sa, off[0])
+    s2 = w.ViewShape((K, N, T), ldb, sb, off[1])
+    so = w.ViewShape((M, N, T), ldc, sc, off[2])
+    sentinel = np.float32(-3.0)
+    C0 = np.full(off[2] + sc * T, sentinel, np.float32)
+    if dtype == "bf16":
+        ta, tb = upload(gpu, O.bf16_bits(A), (A.size,), "bf16"), upload(gpu, O.bf16_bits(B), (B.size,), "bf16")
+    else:
+        ta, tb = upload(gpu, A, (A.size,)), upload(gpu, B, (B.size,))
+    tc = upload(gpu, O.bf16_bits(C0) if out_dtype == "bf16" else C0, (C0.size,), out_dtype)
+    gemm = w.Gemm.from_device(gpu.device())
+    va = w.GpuTensorView(s1, ta.buffer(), dtype, 3)
+    vb = w.GpuTensorView(s2, tb.buffer(), dtype, 3)
+    vc = w.GpuTensorView(so, tc.buffer(), out_dtype, 3)
+    path = []
+
+    def go(p):
+        gemm.dispatch_generic(gpu.device(), shapes, p, vc, va, vb, w.GemmVariant.GemmTr if tr else w.GemmVariant.Gemm, f32_mode=mode)
+        path.append(p.last_gemm_path())
+    run_pass(gpu, go)
+    got = tc.read()
+    if out_dtype == "bf16":
+        got = O.bf16_from_bits(got)
+    ref = O.gemm_f64(tr, M, N, K, T, A, oshape(s1), B, oshape(s2))      # [t][n][m]
+    mask = np.ones(C0.size, bool)
+    worst = 0.0
+    for t in range(T):
+        for n in range(N):
+            lo = off[2] + t * sc + n * ldc
+            worst = max(worst, rel_err(got[lo:lo + M], ref[t, n]))
+            mask[lo:lo + M] = False
+    assert worst < tol, f"rel err {worst:.3e} (path {path})"
+    assert np.all(got[mask] == sentinel), "wrote outside the output view"
+    return path[0]
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (4, 4, 4), (1, 1, 1), (5, 3, 7), (130, 70, 33), (257, 129, 65), (128, 256, 512)])
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_simt_any_shape(gpu, shapes, M, N, K, tr):
+    assert gemm_case(gpu, shapes, M, N, K, tr=tr, mode=w.F32Mode.Simt) == 1
+
+
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_views_offsets_batches_unaligned(gpu, shapes, tr):
+    # odd leading dimensions and offsets: not TMA-eligible -> must still be correct (FFMA path)
+    assert gemm_case(gpu, shapes, 100, 60, 52, T=3, tr=tr, pad=(3, 5, 1), off=(7, 9, 3)) == 1
+    # aligned sub-views of larger parents, batched: TMA-eligible
+    gemm_case(gpu, shapes, 192, 136, 96, T=3, tr=tr, pad=(64, 32, 128), off=(16, 32, 64))
+
+
+def test_gemm_k_zero_writes_zeros(gpu, shapes):
+    out = upload(gpu, np.full(8 * 8, 5.0, np.float32), (8, 8))
+    a = w.GpuTensorView(w.ViewShape((8, 0, 1), 8, 0, 0), upload(gpu, np.zeros(8, np.float32), (8,)).buffer(), "f32", 3)
+    b = w.GpuTensorView(w.ViewShape((0, 8, 1), 0, 0, 0), upload(gpu, np.zeros(8, np.float32), (8,)).buffer(), "f32", 3)
+    gemm = w.Gemm.from_device(gpu.device())
+    run_pass(gpu, lambda p: gemm.dispatch(gpu.device(), shapes, p, out, a, b))
+    np.testing.assert_array_equal(out.read(), np.zeros(64, np.float32))      # gemm.wgsl:89,106-110: sum = 0 is stored
+
+
+def test_gemm_dimension_mismatch_panics(gpu, shapes):
+    gemm = w.Gemm.from_device(gpu.device())
+    z = lambda r, c: upload(gpu, np.zeros(r * c, np.float32), (r, c))
+    with pytest.raises(w.DimensionMismatch, match="Gemm: dimension mismatch"):
+        run_pass(gpu, lambda p: gemm.dispatch(gpu.device(), shapes, p, z(8, 8), z(8, 4), z(8, 8)))
+    with pytest.raises(w.DimensionMismatch):
+        run_pass(gpu, lambda p: gemm.dispatch_tr(gpu.device(), shapes, p, z(8, 8), z(8, 4), z(8, 8)))
+    with pytest.raises(w.WgbError, match="reaches"):
+        bad = w.GpuTensorView(w.ViewShape((8, 8, 1), 8, 64, 1), z(8, 8).buffer(), "f32", 3)
+        run_pass(gpu, lambda p: gemm.dispatch(gpu.device(), shapes, p, bad, z(8, 8), z(8, 8)))
+
+
+def test_empty_dispatch_is_skipped(gpu, shapes):
+    # kernel.rs:111-113,144: zero-sized binding or empty grid => nothing queued, no error
+    e = w.TensorBuilder.vector(0, STORAGE).build(gpu.device())
+    opk = w.OpAssign.new(gpu.device(), w.OpAssignVariant.Add)
+    n0 = gpu.device().launch_count()
+    run_pass(gpu, lambda p: opk.dispatch(gpu.device(), shapes, p, e, e))
+    assert gpu.device().launch_count() == n0
+
+
+# ------------------------------------------------------------------ GEMM on the tensor cores
+TC_SHAPES = [(128, 256, 64), (256, 256, 256), (384, 512, 192), (200, 136, 72), (1024, 768, 520), (136, 264, 40)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_bf16_tcgen05(gpu, shapes, M, N, K, tr):
+    path = gemm_case(gpu, shapes, M, N, K, tr=tr, dtype="bf16", out_dtype="f32", tol=1e-4, pad=(8, 8, 4))
+    assert path == 2, f"expected the tcgen05 bf16 path, got {path}"
+    gemm_case(gpu, shapes, M, N, K, tr=tr, dtype="bf16", out_dtype="bf16", tol=BF16_TOL)
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_f32_3xtf32(gpu, shapes, M, N, K, tr):
+    path = gemm_case(gpu, shapes, M, N, K, tr=tr, mode=w.F32Mode.X3Tf32, tol=F32_TOL, pad=(4, 8, 4))
+    assert path == 4, f"expected the 3xTF32 path, got {path}"
+
+
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_f32_single_tf32_is_tf32_accurate(gpu, shapes, tr):
+    path = gemm_case(gpu, shapes, 256, 256, 512, tr=tr, mode=w.F32Mode.Tf32, tol=2e-3)
+    assert path == 3
+
+
+def test_gemm_f32_default_is_parity_gated(gpu, shapes):
+    # WGB_F32_AUTO must meet 1e-5 whichever path it picks
+    for (M, N, K) in [(512, 512, 2048), (256, 128, 8192)]:
+        gemm_case(gpu, shapes, M, N, K, tol=F32_TOL)
+
+
+def test_gemm_batched_tc(gpu, shapes):
+    gemm_case(gpu, shapes, 256, 192, 128, T=5, dtype="bf16", tol=1e-4)
+    gemm_case(gpu, shapes, 256, 192, 128, T=3, mode=w.F32Mode.X3Tf32)
+
+
+# ------------------------------------------------------------------ GEMV
+def gemv_case(gpu, shapes, R, Cc, ncol=1, T=1, tr=False, pad=0, off=(0, 0, 0), variant=None):
+    """m is R x Cc (+pad rows in the parent).  out = m v (len R) or tr(m) v (len Cc)."""
+    ldm = R + pad
+    sm = ldm * Cc + (4 if pad % 4 == 0 else 3)
+    klen, olen = (R, Cc) if tr else (Cc, R)
+    ldv, ldo = klen + pad, olen + pad
+    sv, so_ = ldv * ncol + 8, ldo * ncol + 4
+    Mbuf = O.uniform(SEED_A, off[0] + sm * T)
+    Vbuf = O.uniform(SEED_V, off[1] + sv * T)
+    sentinel = np.float32(-9.0)
+    Obuf = np.full(off[2] + so_ * T, sentinel, np.float32)
+    vm = w.ViewShape((R, Cc, T), ldm, sm, off[0])
+    vv = w.ViewShape((klen, ncol, T), ldv, sv, off[1])
+    vo = w.ViewShape((olen, ncol, T), ldo, so_, off[2])
+    tm, tv, to = upload(gpu, Mbuf, (Mbuf.size,)), upload(gpu, Vbuf, (Vbuf.size,)), upload(gpu, Obuf, (Obuf.size,))
+    gemv = w.Gemv.from_device(gpu.device())
+    var = variant if variant is not None else (w.GemvVariant.GemvTr if tr else w.GemvVariant.Gemv)
+    run_pass(gpu, lambda p: gemv.dispatch_generic(gpu.device(), shapes, p, w.GpuTensorView(vo, to.buffer(), "f32", 3),
+                                                  w.GpuTensorView(vm, tm.buffer(), "f32", 3),
+                                                  w.GpuTensorView(vv, tv.buffer(), "f32", 3), var))
+    got = to.read()
+    mask = np.ones(Obuf.size, bool)
+    worst = 0.0
+    for t in range(T):
+        m = np.stack([Mbuf[off[0] + t * sm + j * ldm: off[0] + t * sm + j * ldm + R] for j in range(Cc)], axis=1).astype(np.float64)
+        for c in range(ncol):
+            v = Vbuf[off[1] + t * sv + c * ldv: off[1] + t * sv + c * ldv + klen].astype(np.float64)
+            ref = (m.T if tr else m) @ v
+            lo = off[2] + t * so_ + c * ldo
+            worst = max(worst, rel_err(got[lo:lo + olen], ref))
+            mask[lo:lo + olen] = False
+    assert worst < F32_TOL, f"rel err {worst:.3e}"
+    assert np.all(got[mask] == sentinel), "wrote outside the output view"
+
+
+@pytest.mark.parametrize("tr", [False, True])
+@pytest.mark.parametrize("R,Cc", [(4, 4), (1, 1), (128, 128), (1024, 256), (130, 67), (3, 1000), (5000, 12), (64, 4096), (8192, 96)])
+def test_gemv_shapes(gpu, shapes, R, Cc, tr):
+    gemv_case(gpu, shapes, R, Cc, tr=tr)
+
+
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemv_multi_column_batched_views(gpu, shapes, tr):
+    gemv_case(gpu, shapes, 256, 128, ncol=3, T=2, tr=tr, pad=4, off=(8, 4, 12))      # aligned sub-views
+    gemv_case(gpu, shapes, 250, 131, ncol=5, T=2, tr=tr, pad=3, off=(1, 2, 3))       # unaligned: scalar path
+    gemv_case(gpu, shapes, 512, 512, ncol=2, tr=tr)
+
+
+def test_gemv_fast_variant_rules(gpu, shapes):
+    gemv_case(gpu, shapes, 256, 256, variant=w.GemvVariant.GemvFast)
+    gemv_case(gpu, shapes, 256, 256, tr=True, variant=w.GemvVariant.GemvTrFast)
+    gemv_case(gpu, shapes, 100, 256, tr=True, variant=w.GemvVariant.GemvTrFast)      # gemv.rs:99-104 fallback: still valid
+    with pytest.raises(w.DimensionMismatch):                                         # gemv.rs:122
+        gemv_case(gpu, shapes, 6, 128, variant=w.GemvVariant.GemvFast)
+    gemv = w.Gemv.from_device(gpu.device())
+    z = lambda *s: upload(gpu, np.zeros(int(np.prod(s)), np.float32), s)
+    with pytest.raises(w.DimensionMismatch, match="Gemv: dimension mismatch"):       # gemv.rs:89
+        run_pass(gpu, lambda p: gemv.dispatch(gpu.device(), shapes, p, z(8), z(8, 4), z(5)))
+
+
+# ------------------------------------------------------------------ op_assign / reduce / dot / column reduce
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 63, 1757, (1 << 20) + 3])
+@pytest.mark.parametrize("offs", [(0, 0), (1, 0), (0, 1), (3, 2), (4, 8)])
+def test_op_assign_lengths_and_misalignment(gpu, shapes, n, offs):
+    total = n + 16
+    a0 = O.uniform(SEED_A, total) + np.float32(0.5)
+    b0 = O.uniform(SEED_B, total) + np.float32(0.5)
+    for op in w.OpAssignVariant:
+        ta, tb = upload(gpu, a0, (total,)), upload(gpu, b0, (total,))
+        va = w.GpuTensorView(w.ViewShape((n, 1, 1), total, total, offs[0]), ta.buffer(), "f32", 1)
+        vb = w.GpuTensorView(w.ViewShape((n, 1, 1), total, total, offs[1]), tb.buffer(), "f32", 1)
+        opk = w.OpAssign.new(gpu.device(), op)
+        run_pass(gpu, lambda p: opk.dispatch(gpu.device(), shapes, p, va, vb))
+        ref = a0.copy()
+        assert O.op_assign(int(op), ref, O.Shape(n, 1, 1, total, total, offs[0]), b0, O.Shape(n, 1, 1, total, total, offs[1])) == O.ORC_OK
+        np.testing.assert_array_equal(ta.read(), ref)
+
+
+def test_op_assign_dimension_mismatch(gpu, shapes):
+    a, b = upload(gpu, np.zeros(8, np.float32), (8,)), upload(gpu, np.zeros(9, np.float32), (9,))
+    with pytest.raises(w.DimensionMismatch, match="Op-assign: dimension mismatch"):
+        run_pass(gpu, lambda p: w.OpAssign.new(gpu.device(), w.OpAssignVariant.Add).dispatch(gpu.device(), shapes, p, a, b))
+
+
+@pytest.mark.parametrize("n,off", [(0, 0), (1, 0), (127, 1), (128, 2), (4099, 3), ((1 << 22) + 5, 1)])
+def test_reduce_all_ops(gpu, shapes, n, off):
+    total = n + 8
+    x = O.uniform(SEED_V, total)
+    tx = upload(gpu, x, (total,))
+    view = w.GpuTensorView(w.ViewShape((n, 1, 1), total, total, off), tx.buffer(), "f32", 1)
+    res = w.TensorBuilder.scalar(STORAGE).build(gpu.device())
+    xs = x[off:off + n].astype(np.float64)
+    for op in w.ReduceOp:
+        if op == w.ReduceOp.Prod and n > 4099:
+            continue  # underflows to 0 on both sides; nothing to compare
+        red = w.Reduce.new(gpu.device(), op)
+        run_pass(gpu, lambda p: red.dispatch(gpu.device(), shapes, p, view, res))
+        got = float(res.read()[0])
+        ref = O.reduce(int(op), x, O.Shape(n, 1, 1, total, total, off))
+        exact = {w.ReduceOp.Min: min(xs.min(initial=3.4e38), float(np.float32(3.4e38))), w.ReduceOp.Max: max(xs.max(initial=-3.4e38), float(np.float32(-3.4e38))),
+                 w.ReduceOp.Sum: xs.sum(), w.ReduceOp.Prod: xs.prod(), w.ReduceOp.SqNorm: (xs * xs).sum()}[op]
+        assert abs(got - ref) <= F32_TOL * abs(ref) + 1e-37, (op, got, ref)
+        assert abs(got - exact) <= F32_TOL * abs(exact) + 1e-37, (op, got, exact)
+
+
+def test_reduce_is_deterministic(gpu, shapes):
+    n = (1 << 21) + 17
+    tx = upload(gpu, O.uniform(SEED_V, n), (n,))
+    res = w.TensorBuilder.scalar(STORAGE).build(gpu.device())
+    red = w.Reduce.new(gpu.device(), w.ReduceOp.Sum)
+    vals = set()
+    for _ in range(5):
+        run_pass(gpu, lambda p: red.dispatch(gpu.device(), shapes, p, tx, res))
+        vals.add(res.read()[0].tobytes())
+    assert len(vals) == 1
+
+
+@pytest.mark.parametrize("n,offs", [(1, (0, 0)), (1000, (1, 2)), ((1 << 20) + 1, (0, 3)), (4096, (4, 4))])
+def test_dot(gpu, shapes, n, offs):
+    total = n + 8
+    a, b = O.uniform(SEED_A, total), O.uniform(SEED_B, total)
+    ta, tb = upload(gpu, a, (total,)), upload(gpu, b, (total,))
+    res = w.TensorBuilder.scalar(STORAGE).build(gpu.device())
+    va = w.GpuTensorView(w.ViewShape((n, 1, 1), total, total, offs[0]), ta.buffer(), "f32", 1)
+    vb = w.GpuTensorView(w.ViewShape((n, 1, 1), total, total, offs[1]), tb.buffer(), "f32", 1)
+    run_pass(gpu, lambda p: w.Dot.new(gpu.device()).dispatch(gpu.device(), shapes, p, va, vb, res))
+    ref = float(a[offs[0]:offs[0] + n].astype(np.float64) @ b[offs[1]:offs[1] + n].astype(np.float64))
+    assert abs(float(res.read()[0]) - ref) <= F32_TOL * abs(ref)
+
+
+@pytest.mark.parametrize("R,Cc,T,pad,off", [(345, 7, 1, 0, 0), (4096, 33, 2, 4, 8), (100, 1000, 1, 3, 1), (2, 5, 3, 0, 0)])
+def test_reduce_columns_equals_one_reduce_per_column(gpu, shapes, R, Cc, T, pad, off):
+    ld, sm = R + pad, (R + pad) * Cc + 5
+    buf = O.uniform(SEED_A, off + sm * T) + np.float32(0.25)
+    tm = upload(gpu, buf, (buf.size,))
+    view = w.GpuTensorView(w.ViewShape((R, Cc, T), ld, sm, off), tm.buffer(), "f32", 3)
+    out = upload(gpu, np.zeros(Cc * T, np.float32), (Cc * T,))
+    for op in w.ReduceOp:
+        if op == w.ReduceOp.Prod and R > 400:
+            continue
+        red = w.Reduce.new(gpu.device(), op)
+        run_pass(gpu, lambda p: red.dispatch_columns(gpu.device(), shapes, p, view, out))
+        got = out.read()
+        for t in range(T):
+            for j in range(Cc):
+                # the reference's way: Reduce over GpuMatrix::column(j)  (tensor.rs:574-585)
+                ref = O.reduce(int(op), buf, O.Shape(R, 1, 1, 1, 1, off + t * sm + j * ld))
+                assert abs(got[t * Cc + j] - ref) <= F32_TOL * abs(ref) + 1e-37
+
+
+# ------------------------------------------------------------------ BASELINE sizes through properties
+def test_cfg4_gemv_full_size_properties(gpu, shapes):
+    """f32 GEMV 65536 x 4096 (BASELINE configs[3]): too big for the scalar oracle in seconds, so check
+    (1) m e_k = column k exactly, (2) linearity m(x+y) = mx + my, (3) sampled rows against float64."""
+    M, K = 65536, 4096
+    dev = gpu.device()
+    m = w.TensorBuilder.matrix(M, K, STORAGE).build(dev)
+    run_pass(gpu, lambda p: w.fill_uniform(dev, p, m, SEED_A))
+    gemv = w.Gemv.from_device(dev)
+    x, y = O.uniform(SEED_V, K), O.uniform(SEED_V + 100, K)
+    ek = np.zeros(K, np.float32); ek[1234] = 1.0
+    vx, vy, vxy, vek = (upload(gpu, a, (K,)) for a in (x, y, x + y, ek))
+    ox, oy, oxy, oek = (w.TensorBuilder.vector(M, STORAGE).build(dev) for _ in range(4))
+    run_pass(gpu, lambda p: [gemv.dispatch(dev, shapes, p, o, m, v) for o, v in ((ox, vx), (oy, vy), (oxy, vxy), (oek, vek))])
+    np.testing.assert_array_equal(oek.read(), O.uniform(SEED_A, M, 1, col0=1234))
+    rx, ry, rxy = ox.read(), oy.read(), oxy.read()
+    assert rel_err(rxy, rx.astype(np.float64) + ry.astype(np.float64)) < 5e-6
+    rows = np.array([0, 1, 77, 4095, 4096, 32768, 65535])
+    mr = np.stack([O.uniform(SEED_A, 1, K, row0=int(r)) for r in rows]).astype(np.float64)
+    assert rel_err(rx[rows], mr @ x.astype(np.float64)) < F32_TOL
+    # gemv_tr on the same matrix: tr(m) u, u = ones  ==> column sums == Reduce(Sum) over each column
+    ones = upload(gpu, np.ones(M, np.float32), (M,))
+    ot = w.TensorBuilder.vector(K, STORAGE).build(dev)
+    oc = w.TensorBuilder.vector(K, STORAGE).build(dev)
+    red = w.Reduce.new(dev, w.ReduceOp.Sum)
+    run_pass(gpu, lambda p: (gemv.dispatch_tr(dev, shapes, p, ot, m, ones), red.dispatch_columns(dev, shapes, p, m, oc)))
+    assert rel_err(ot.read(), oc.read()) < 5e-6
+    col = O.uniform(SEED_A, M, 1, col0=4095).astype(np.float64)
+    assert abs(float(ot.read()[4095]) - col.sum()) <= F32_TOL * col.sum()
+
+
+def test_cfg3_bf16_gemm_4096_properties(gpu, shapes):
+    """bf16 GEMM 4096^3 (BASELINE configs[2]): (1) A I = A bit-exactly, (2) sampled rows vs float64 on the same
+    bf16-rounded inputs within 1e-2, (3) tr(A) B agrees with the same samples."""
+    n = 4096
+    dev = gpu.device()
+    a = w.TensorBuilder.matrix(n, n, STORAGE).build(dev, "bf16")
+    b = w.TensorBuilder.matrix(n, n, STORAGE).build(dev, "bf16")
+    run_pass(gpu, lambda p: (w.fill_uniform(dev, p, a, SEED_A), w.fill_uniform(dev, p, b, SEED_B)))
+    eye = np.zeros((n, n), np.float32); np.fill_diagonal(eye, 1.0)
+    ident = upload(gpu, O.bf16_bits(eye.reshape(-1)), (n, n), "bf16")
+    out = w.TensorBuilder.matrix(n, n, STORAGE).build(dev, "bf16")
+    gemm = w.Gemm.from_device(dev)
+    run_pass(gpu, lambda p: gemm.dispatch(dev, shapes, p, out, a, ident))
+    np.testing.assert_array_equal(out.read(), a.read())
+    outf = w.TensorBuilder.matrix(n, n, STORAGE).build(dev, "f32")
+    path = []
+    run_pass(gpu, lambda p: (gemm.dispatch(dev, shapes, p, outf, a, b), path.append(p.last_gemm_path())))
+    assert path == [2]
+    got = cm(outf.read(), n, n)
+    rows = np.array([0, 5, 127, 128, 2049, 4095])
+    A = np.stack([O.to_bf16_rne(O.uniform(SEED_A, 1, n, row0=int(r))) for r in rows]).astype(np.float64)
+    B = cm(O.to_bf16_rne(O.uniform(SEED_B, n, n)), n, n).astype(np.float64)
+    assert rel_err(got[rows, :], A @ B) < 1e-4           # f32 output of bf16 inputs: only accumulation error
+    run_pass(gpu, lambda p: gemm.dispatch_tr(dev, shapes, p, outf, a, b))
+    gt = cm(outf.read(), n, n)
+    cols = np.stack([O.to_bf16_rne(O.uniform(SEED_A, n, 1, col0=int(r))) for r in rows]).astype(np.float64)   # columns of A = rows of tr(A)
+    assert rel_err(gt[rows, :], cols @ B) < 1e-4
+
+
+def test_cfg2_f32_gemm_large_sampled(gpu, shapes):
+    """f32 GEMM N = 2048 (inside BASELINE configs[1]'s sweep): sampled rows vs float64, 1e-5."""
+    n = 2048
+    dev = gpu.device()
+    a, b, c = (w.TensorBuilder.matrix(n, n, STORAGE).build(dev) for _ in range(3))
+    run_pass(gpu, lambda p: (w.fill_uniform(dev, p, a, SEED_A), w.fill_uniform(dev, p, b, SEED_B)))
+    gemm = w.Gemm.from_device(dev)
+    run_pass(gpu, lambda p: gemm.dispatch(dev, shapes, p, c, a, b))
+    got = cm(c.read(), n, n)
+    rows = np.array([0, 3, 129, 1024, 2047])
+    A = np.stack([O.uniform(SEED_A, 1, n, row0=int(r)) for r in rows]).astype(np.float64)
+    B = cm(O.uniform(SEED_B, n, n), n, n).astype(np.float64)
+    assert rel_err(got[rows, :], A @ B) < F32_TOL
+
+
+def test_timestamps_and_launch_counter(gpu, shapes):
+    dev = gpu.device()
+    ts = w.GpuTimestamps.new(dev, 8)
+    n = 1 << 22
+    a, b = (w.TensorBuilder.vector(n, STORAGE).build(dev) for _ in range(2))
+    opk = w.OpAssign.new(dev, w.OpAssignVariant.Copy)
+    enc = dev.create_command_encoder()
+    n0 = dev.launch_count()
+    p = enc.compute_pass("timed", ts)
+    for _ in range(4):
+        opk.dispatch(dev, shapes, p, a, b)
+    p.end()
+    ts.resolve(enc)
+    gpu.queue().submit(enc.finish())
+    ms = ts.wait_for_results_ms(dev, gpu.queue())
+    assert len(ms) == 2 and ms[1] > 0.0
+    assert dev.launch_count() - n0 == 4

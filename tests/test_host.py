@@ -1,0 +1,108 @@
+"""CPU tests (-m "not gpu") for the boundary: the C-ABI library loads and exports every symbol
+include/wgb200.h declares, fails loudly without a GPU, and the host-side mirror reproduces the
+view arithmetic of /root/reference/crates/wgcore/src/tensor.rs."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import wgmath_b200 as w
+from wgmath_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "wgb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wgb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = header_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(L, n), f"libwgebra_b200.so does not export {n}"
+    assert sorted(_lib.EXPORTED) == names, "python binding list and header disagree"
+    assert L.wgb_abi_version() == 1
+
+
+def test_view_shape_layout_matches_reference():
+    assert ctypes.sizeof(_lib.ViewShapeC) == 24            # shapes.rs:9-21, #[repr(C)] 6 x u32
+    c = w.ViewShape((3, 5, 7), 11, 13, 17).to_c()
+    raw = (ctypes.c_uint32 * 6).from_buffer_copy(c)
+    assert list(raw) == [3, 5, 7, 11, 13, 17]
+    with pytest.raises(OverflowError):
+        w.ViewShape((1 << 32, 1, 1), 1, 1, 0).to_c()
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    h = ctypes.c_void_p()
+    st = _lib.lib().wgb_ctx_create(0, ctypes.byref(h))
+    if st == _lib.OK:      # running on a GPU box
+        _lib.lib().wgb_ctx_destroy(h)
+        return
+    assert st == _lib.ERR_NO_DEVICE
+    assert b"no CPU fallback" in _lib.lib().wgb_last_error_string()
+    with pytest.raises(w.WgbError):
+        w.GpuInstance.new()
+
+
+def test_null_arguments_are_rejected():
+    L = _lib.lib()
+    assert L.wgb_gemm(None, 0, None, None, None, None, None, None) == _lib.ERR_INVALID
+    assert L.wgb_op_assign(None, 0, None, None, None, None) == _lib.ERR_INVALID
+    assert L.wgb_ctx_sync(None) == _lib.ERR_INVALID
+    assert L.wgb_buffer_destroy(None) == _lib.OK and L.wgb_ctx_destroy(None) == _lib.OK
+
+
+def T(shape, dtype="f32"):
+    return w.GpuTensor(shape, buffer=None, dtype=dtype)    # view arithmetic never touches the buffer
+
+
+def test_view_arithmetic_matches_tensor_rs():
+    m = T((64, 48))
+    v = m.as_embedded_view(3).shape()                       # tensor.rs:287-297 + :514-541
+    assert (v.size, v.stride, v.stride_mat, v.offset) == ((64, 48, 1), 64, 64 * 48, 0)
+    c = m.column(5).shape()                                 # :574-585
+    assert (c.size, c.stride, c.stride_mat, c.offset) == ((64, 1, 1), 1, 1, 320)
+    cs = m.columns(4, 20).shape()                           # :600-612
+    assert (cs.size, cs.stride, cs.stride_mat, cs.offset) == ((64, 20, 1), 64, 64 * 48, 256)
+    rs = m.rows(8, 32).shape()                              # :614-626
+    assert (rs.size, rs.stride, rs.offset) == ((32, 48, 1), 64, 8)
+    rc = m.rows(8, 32).columns(2, 3).shape()                # :484-496 on a view
+    assert (rc.size, rc.stride, rc.offset) == ((32, 3, 1), 64, 8 + 2 * 64)
+    cube = T((16, 8, 4))
+    mat = cube.as_view().matrix(2).shape()                  # :466-481
+    assert (mat.size, mat.stride, mat.stride_mat, mat.offset) == ((16, 8, 1), 16, 1, 2 * 128)
+    vec = T((100,))
+    r = vec.rows(10, 20).shape()                            # :669-681
+    assert (r.size, r.stride, r.stride_mat, r.offset) == ((20, 1, 1), 100, 100, 10)
+    rr = vec.rows(10, 20).rows(5, 10).shape()               # :445-462
+    assert (rr.size, rr.offset) == ((10, 1, 1), 15)
+    with pytest.raises(AssertionError):
+        vec.rows(10, 20).rows(15, 10)
+    with pytest.raises(AssertionError):
+        m.reshape((64, 49))                                 # :520
+    assert w.ViewShape((64, 48, 1), 64, 3072, 8).f32_to_vec4() == w.ViewShape((16, 48, 1), 16, 768, 2)  # shapes.rs:25-39
+
+
+def test_slice_quirk_is_fixed_on_purpose():
+    # tensor.rs:587-598 computes offset = i + j * <slice nrows>; that is only right when the slice spans all rows.
+    s = T((64, 48)).slice((4, 3), (16, 8)).shape()
+    assert (s.size, s.stride, s.offset) == ((16, 8, 1), 64, 4 + 3 * 64)
+
+
+def test_enums_match_reference_order():
+    assert [v.name for v in w.GemmVariant] == ["Gemm", "GemmFast", "GemmTr", "GemmTrFast"]           # gemm.rs:25-35
+    assert [v.name for v in w.GemvVariant] == ["Gemv", "GemvFast", "GemvTr", "GemvTrFast"]           # gemv.rs:24-34
+    assert [v.name for v in w.OpAssignVariant] == ["Add", "Sub", "Mul", "Div", "Copy"]               # op_assign.rs:15-26
+    assert [v.name for v in w.ReduceOp] == ["Min", "Max", "Sum", "Prod", "SqNorm"]                   # reduce.rs:16-27
+
+
+def test_reduce_eval_cpu():
+    import numpy as np
+    x = np.array([3.0, -1.0, 2.0], np.float32)
+    assert w.Reduce(None, w.ReduceOp.Min).eval_cpu(x) == -1.0 and w.Reduce(None, w.ReduceOp.SqNorm).eval_cpu(x) == 14.0

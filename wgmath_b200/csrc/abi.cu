@@ -1,0 +1,548 @@
+// abi.cu — the extern "C" surface of libwgebra_b200.so (include/wgb200.h): contexts, passes,
+// buffers, events, and the validation / dispatch layer in front of the kernels.
+//
+// Reference behaviour mirrored here (paths under /root/reference/crates/):
+//   wgcore/src/gpu.rs:15-58            GpuInstance::new           -> wgb_ctx_create
+//   wgcore/src/kernel.rs:7-27          compute_pass               -> wgb_pass_begin / _end
+//   wgcore/src/kernel.rs:103-148       zero-sized binding / empty grid => dispatch skipped
+//   wgcore/src/tensor.rs:112-186       TensorBuilder::build*      -> wgb_buffer_create*
+//   wgcore/src/tensor.rs:227-265       copy_from / copy_from_view -> wgb_buffer_copy
+//   wgcore/src/tensor.rs:300-384       read*                      -> wgb_buffer_read
+//   wgebra/src/linalg/gemm.rs:78-96    dimension asserts          -> WGB_ERR_DIM_MISMATCH
+//   wgebra/src/linalg/gemv.rs:77-124   dimension asserts, TrFast fallback
+//   wgebra/src/linalg/op_assign.rs:82-86, reduce.rs:100-113
+#include "common.cuh"
+
+namespace wgb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+wgb_status check_view(const wgb_buffer *b, const wgb_view_shape &s, size_t elem_size, const char *what,
+                      bool vector_only) {
+    const uint64_t ext = vector_only ? vector_extent(s) : view_extent(s);
+    if (ext * elem_size > b->bytes)
+        WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "%s: view reaches element %llu but the buffer holds %llu", what,
+                 (unsigned long long)ext, (unsigned long long)(b->bytes / elem_size));
+    return WGB_OK;
+}
+
+wgb_status workspace_reserve(wgb_ctx *ctx, int slot, size_t bytes, void **out) {
+    Workspace &w = ctx->ws[slot];
+    if (w.bytes < bytes) {
+        // Growing is rare (first call at a new size); synchronise so no in-flight kernel loses its operands.
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (w.ptr) WGB_CUDA(cudaFree(w.ptr));
+        w.ptr = nullptr;
+        w.bytes = 0;
+        size_t want = bytes + (bytes >> 3);
+        cudaError_t e = cudaMalloc(&w.ptr, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            want = bytes;
+            WGB_CUDA(cudaMalloc(&w.ptr, want));
+        }
+        w.bytes = want;
+    }
+    *out = w.ptr;
+    return WGB_OK;
+}
+
+wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters) {
+    Scratch &s = ctx->scratch;
+    if (s.partials_floats < partial_floats) {
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s.partials) WGB_CUDA(cudaFree(s.partials));
+        s.partials = nullptr;
+        s.partials_floats = 0;
+        WGB_CUDA(cudaMalloc(&s.partials, partial_floats * sizeof(float)));
+        s.partials_floats = partial_floats;
+    }
+    if (s.n_counters < counters) {
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (s.counters) WGB_CUDA(cudaFree(s.counters));
+        s.counters = nullptr;
+        s.n_counters = 0;
+        WGB_CUDA(cudaMalloc(&s.counters, counters * sizeof(unsigned int)));
+        WGB_CUDA(cudaMemset(s.counters, 0, counters * sizeof(unsigned int)));
+        s.n_counters = counters;
+    }
+    return WGB_OK;
+}
+
+void tmap_cache_destroy(wgb_ctx *ctx);  // gemm_tc.cu
+void comm_destroy(wgb_ctx *ctx);        // comm.cu
+
+}  // namespace wgb
+
+using namespace wgb;
+
+extern "C" {
+
+int wgb_abi_version(void) { return WGB200_ABI_VERSION; }
+const char *wgb_last_error_string(void) { return wgb::g_err; }
+
+// --------------------------------------------------------------------------- context
+wgb_status wgb_ctx_create(int device_ordinal, wgb_ctx **out) {
+    if (!out) WGB_FAIL(WGB_ERR_INVALID, "wgb_ctx_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        WGB_FAIL(WGB_ERR_NO_DEVICE, "no CUDA device visible (%s); this library has no CPU fallback",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device_ordinal < 0 || device_ordinal >= ndev)
+        WGB_FAIL(WGB_ERR_INVALID, "device ordinal %d out of range [0, %d)", device_ordinal, ndev);
+    wgb_ctx *ctx = new wgb_ctx();
+    ctx->device = device_ordinal;
+    if (cudaGetDeviceProperties(&ctx->prop, device_ordinal) != cudaSuccess) {
+        delete ctx;
+        WGB_FAIL(WGB_ERR_CUDA, "cudaGetDeviceProperties failed");
+    }
+    if (ctx->prop.major != 10) {
+        int maj = ctx->prop.major, min = ctx->prop.minor;
+        delete ctx;
+        WGB_FAIL(WGB_ERR_NO_DEVICE, "device %d is sm_%d%d; libwgebra_b200 is built for sm_100a only", device_ordinal,
+                 maj, min);
+    }
+    DeviceGuard g(device_ordinal);
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        WGB_FAIL(WGB_ERR_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    wgb_status s = scratch_reserve(ctx, (size_t)1 << 20, (size_t)1 << 16);
+    if (s != WGB_OK) {
+        delete ctx;
+        return s;
+    }
+    *out = ctx;
+    return WGB_OK;
+}
+
+wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
+    if (!ctx) return WGB_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->comm_stream);
+    comm_destroy(ctx);
+    tmap_cache_destroy(ctx);
+    if (ctx->scratch.partials) cudaFree(ctx->scratch.partials);
+    if (ctx->scratch.counters) cudaFree(ctx->scratch.counters);
+    for (auto &w : ctx->ws)
+        if (w.ptr) cudaFree(w.ptr);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+    return WGB_OK;
+}
+
+wgb_status wgb_ctx_sync(wgb_ctx *ctx) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "wgb_ctx_sync: null context");
+    DeviceGuard g(ctx->device);
+    WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+    WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    return WGB_OK;
+}
+
+wgb_status wgb_ctx_device_info(wgb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, size_t *total_mem,
+                               char *name, size_t name_len) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "null context");
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+    if (name && name_len) {
+        strncpy(name, ctx->prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return WGB_OK;
+}
+
+wgb_status wgb_ctx_launch_count(wgb_ctx *ctx, uint64_t *count) {
+    if (!ctx || !count) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *count = ctx->launches.load();
+    return WGB_OK;
+}
+
+wgb_status wgb_ctx_stream(wgb_ctx *ctx, void **cuda_stream) {
+    if (!ctx || !cuda_stream) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *cuda_stream = (void *)ctx->stream;
+    return WGB_OK;
+}
+
+// --------------------------------------------------------------------------- passes
+wgb_status wgb_pass_begin(wgb_ctx *ctx, const char *label, wgb_event *begin_ts, wgb_event *end_ts, wgb_pass **out) {
+    (void)label;
+    if (!ctx || !out) WGB_FAIL(WGB_ERR_INVALID, "wgb_pass_begin: null argument");
+    wgb_pass *p = new wgb_pass();
+    p->ctx = ctx;
+    p->stream = ctx->stream;
+    p->end_ts = end_ts;
+    if (begin_ts) {
+        DeviceGuard g(ctx->device);
+        cudaError_t e = cudaEventRecord(begin_ts->ev, p->stream);
+        if (e != cudaSuccess) {
+            delete p;
+            WGB_FAIL(WGB_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = p;
+    return WGB_OK;
+}
+
+wgb_status wgb_pass_end(wgb_pass *pass) {
+    if (!pass) return WGB_OK;
+    wgb_status st = WGB_OK;
+    if (pass->end_ts) {
+        DeviceGuard g(pass->ctx->device);
+        if (cudaEventRecord(pass->end_ts->ev, pass->stream) != cudaSuccess) {
+            set_error("cudaEventRecord failed at pass end");
+            st = WGB_ERR_CUDA;
+        }
+    }
+    delete pass;
+    return st;
+}
+
+wgb_status wgb_submit(wgb_ctx *ctx) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "null context");
+    // Kernels were enqueued at dispatch time; cudaStreamQuery nudges the driver to flush (WDDM-style batching
+    // does not exist on Linux, so this is effectively free).
+    DeviceGuard g(ctx->device);
+    cudaError_t e = cudaStreamQuery(ctx->stream);
+    if (e != cudaSuccess && e != cudaErrorNotReady) WGB_FAIL(WGB_ERR_CUDA, "queue error: %s", cudaGetErrorString(e));
+    return WGB_OK;
+}
+
+wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path) {
+    if (!pass || !path) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *path = pass->last_gemm_path;
+    return WGB_OK;
+}
+
+// --------------------------------------------------------------------------- buffers
+wgb_status wgb_buffer_create(wgb_ctx *ctx, size_t bytes, uint32_t usage, wgb_buffer **out) {
+    if (!ctx || !out) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_create: null argument");
+    DeviceGuard g(ctx->device);
+    wgb_buffer *b = new wgb_buffer();
+    b->ctx = ctx;
+    b->bytes = bytes;
+    b->usage = usage;
+    b->host_pinned = (usage & (WGB_USAGE_MAP_READ | WGB_USAGE_MAP_WRITE)) != 0;
+    if (bytes) {
+        cudaError_t e = b->host_pinned ? cudaHostAlloc(&b->ptr, bytes, cudaHostAllocDefault) : cudaMalloc(&b->ptr, bytes);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            delete b;
+            WGB_FAIL(WGB_ERR_OOM, "allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        }
+    }
+    *out = b;
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_create_init(wgb_ctx *ctx, const void *host_data, size_t bytes, uint32_t usage,
+                                  wgb_buffer **out) {
+    if (bytes && !host_data) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_create_init: null data");
+    WGB_TRY(wgb_buffer_create(ctx, bytes, usage, out));
+    if (bytes) {
+        DeviceGuard g(ctx->device);
+        wgb_buffer *b = *out;
+        if (b->host_pinned) {
+            memcpy(b->ptr, host_data, bytes);
+        } else {
+            // create_buffer_init semantics: the data is captured at creation, so the copy is complete on return.
+            cudaError_t e = cudaMemcpyAsync(b->ptr, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                wgb_buffer_destroy(b);
+                *out = nullptr;
+                WGB_FAIL(WGB_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+            }
+        }
+    }
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_wrap(wgb_ctx *ctx, void *device_ptr, size_t bytes, wgb_buffer **out) {
+    if (!ctx || !out || (!device_ptr && bytes)) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_wrap: null argument");
+    wgb_buffer *b = new wgb_buffer();
+    b->ctx = ctx;
+    b->ptr = device_ptr;
+    b->bytes = bytes;
+    b->owned = false;
+    b->usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    *out = b;
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_destroy(wgb_buffer *buf) {
+    if (!buf) return WGB_OK;
+    if (buf->owned && buf->ptr) {
+        DeviceGuard g(buf->ctx->device);
+        // wgpu keeps a destroyed buffer alive until queued work that uses it has finished.
+        cudaStreamSynchronize(buf->ctx->stream);
+        if (buf->host_pinned) cudaFreeHost(buf->ptr);
+        else cudaFree(buf->ptr);
+    }
+    delete buf;
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_size(const wgb_buffer *buf, size_t *bytes) {
+    if (!buf || !bytes) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *bytes = buf->bytes;
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_device_ptr(const wgb_buffer *buf, void **ptr) {
+    if (!buf || !ptr) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *ptr = buf->ptr;
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_write(wgb_ctx *ctx, wgb_buffer *dst, size_t dst_off, const void *host_src, size_t bytes) {
+    if (!ctx || !dst || (!host_src && bytes)) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_write: null argument");
+    if (dst_off + bytes > dst->bytes) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_buffer_write: range exceeds the buffer");
+    if (!bytes) return WGB_OK;
+    DeviceGuard g(ctx->device);
+    WGB_CUDA(cudaMemcpyAsync((char *)dst->ptr + dst_off, host_src, bytes,
+                             dst->host_pinned ? cudaMemcpyHostToHost : cudaMemcpyHostToDevice, ctx->stream));
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_copy(wgb_ctx *ctx, wgb_pass *pass, wgb_buffer *dst, size_t dst_off, const wgb_buffer *src,
+                           size_t src_off, size_t bytes) {
+    if (!ctx || !dst || !src) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_copy: null argument");
+    if (dst_off + bytes > dst->bytes || src_off + bytes > src->bytes)
+        WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_buffer_copy: range exceeds a buffer");
+    if (!bytes) return WGB_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = pass ? pass->stream : ctx->stream;
+    WGB_CUDA(cudaMemcpyAsync((char *)dst->ptr + dst_off, (const char *)src->ptr + src_off, bytes, cudaMemcpyDefault, st));
+    return WGB_OK;
+}
+
+wgb_status wgb_buffer_read(wgb_ctx *ctx, const wgb_buffer *src, size_t src_off, void *host_dst, size_t bytes) {
+    if (!ctx || !src || (!host_dst && bytes)) WGB_FAIL(WGB_ERR_INVALID, "wgb_buffer_read: null argument");
+    if (src_off + bytes > src->bytes) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_buffer_read: range exceeds the buffer");
+    DeviceGuard g(ctx->device);
+    if (src->host_pinned) {
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));  // device.poll(wait)
+        if (bytes) memcpy(host_dst, (const char *)src->ptr + src_off, bytes);
+        return WGB_OK;
+    }
+    if (bytes)
+        WGB_CUDA(cudaMemcpyAsync(host_dst, (const char *)src->ptr + src_off, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return WGB_OK;
+}
+
+wgb_status wgb_host_alloc(size_t bytes, void **out) {
+    if (!out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!bytes) return WGB_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        WGB_FAIL(WGB_ERR_OOM, "pinned allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return WGB_OK;
+}
+
+wgb_status wgb_host_free(void *ptr) {
+    if (ptr) cudaFreeHost(ptr);
+    return WGB_OK;
+}
+
+// --------------------------------------------------------------------------- events
+wgb_status wgb_event_create(wgb_ctx *ctx, wgb_event **out) {
+    if (!ctx || !out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(ctx->device);
+    wgb_event *ev = new wgb_event();
+    ev->ctx = ctx;
+    cudaError_t e = cudaEventCreate(&ev->ev);
+    if (e != cudaSuccess) {
+        delete ev;
+        WGB_FAIL(WGB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
+    *out = ev;
+    return WGB_OK;
+}
+
+wgb_status wgb_event_destroy(wgb_event *ev) {
+    if (!ev) return WGB_OK;
+    cudaEventDestroy(ev->ev);
+    delete ev;
+    return WGB_OK;
+}
+
+wgb_status wgb_event_record(wgb_event *ev, wgb_pass *pass) {
+    if (!ev) WGB_FAIL(WGB_ERR_INVALID, "null event");
+    DeviceGuard g(ev->ctx->device);
+    WGB_CUDA(cudaEventRecord(ev->ev, pass ? pass->stream : ev->ctx->stream));
+    return WGB_OK;
+}
+
+wgb_status wgb_event_elapsed_ms(wgb_event *begin, wgb_event *end, float *ms) {
+    if (!begin || !end || !ms) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(end->ctx->device);
+    WGB_CUDA(cudaEventSynchronize(end->ev));
+    WGB_CUDA(cudaEventElapsedTime(ms, begin->ev, end->ev));
+    return WGB_OK;
+}
+
+// --------------------------------------------------------------------------- operators
+static bool any_zero_buffer(std::initializer_list<const wgb_buffer *> bufs) {
+    for (auto b : bufs)
+        if (b->bytes == 0) return true;  // kernel.rs:111-113: zero-sized binding => not queueable
+    return false;
+}
+
+wgb_status wgb_op_assign(wgb_pass *pass, wgb_op_assign_variant op, wgb_buffer *a, const wgb_view_shape *sa,
+                         const wgb_buffer *b, const wgb_view_shape *sb) {
+    if (!pass || !a || !b || !sa || !sb) WGB_FAIL(WGB_ERR_INVALID, "wgb_op_assign: null argument");
+    if ((int)op < 0 || (int)op > WGB_OP_COPY) WGB_FAIL(WGB_ERR_INVALID, "wgb_op_assign: unknown op %d", (int)op);
+    if (sa->size[0] != sb->size[0])  // op_assign.rs:82-86
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Op-assign: dimension mismatch. (%u vs %u)", sa->size[0], sb->size[0]);
+    if (any_zero_buffer({a, b}) || sa->size[0] == 0) return WGB_OK;
+    WGB_TRY(check_view(a, *sa, 4, "op_assign a", true));
+    WGB_TRY(check_view(b, *sb, 4, "op_assign b", true));
+    DeviceGuard g(pass->ctx->device);
+    return launch_op_assign(pass, (int)op, (float *)a->ptr + sa->offset, (const float *)b->ptr + sb->offset, sa->size[0]);
+}
+
+wgb_status wgb_reduce(wgb_pass *pass, wgb_reduce_op op, const wgb_buffer *value, const wgb_view_shape *vs,
+                      wgb_buffer *result) {
+    if (!pass || !value || !vs || !result) WGB_FAIL(WGB_ERR_INVALID, "wgb_reduce: null argument");
+    if ((int)op < 0 || (int)op > WGB_RED_SQNORM) WGB_FAIL(WGB_ERR_INVALID, "wgb_reduce: unknown op %d", (int)op);
+    if (any_zero_buffer({value, result})) return WGB_OK;
+    if (result->bytes < 4) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_reduce: result buffer smaller than one f32");
+    WGB_TRY(check_view(value, *vs, 4, "reduce value", true));
+    DeviceGuard g(pass->ctx->device);
+    return launch_reduce(pass, (int)op, (const float *)value->ptr + vs->offset, nullptr, vs->size[0], (float *)result->ptr);
+}
+
+wgb_status wgb_dot(wgb_pass *pass, const wgb_buffer *a, const wgb_view_shape *sa, const wgb_buffer *b,
+                   const wgb_view_shape *sb, wgb_buffer *result) {
+    if (!pass || !a || !b || !sa || !sb || !result) WGB_FAIL(WGB_ERR_INVALID, "wgb_dot: null argument");
+    if (sa->size[0] != sb->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Dot: dimension mismatch. (%u vs %u)", sa->size[0], sb->size[0]);
+    if (any_zero_buffer({a, b, result})) return WGB_OK;
+    if (result->bytes < 4) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_dot: result buffer smaller than one f32");
+    WGB_TRY(check_view(a, *sa, 4, "dot a", true));
+    WGB_TRY(check_view(b, *sb, 4, "dot b", true));
+    DeviceGuard g(pass->ctx->device);
+    return launch_reduce(pass, 5 /* dot */, (const float *)a->ptr + sa->offset, (const float *)b->ptr + sb->offset,
+                         sa->size[0], (float *)result->ptr);
+}
+
+wgb_status wgb_reduce_columns(wgb_pass *pass, wgb_reduce_op op, const wgb_buffer *m, const wgb_view_shape *ms,
+                              wgb_buffer *out, const wgb_view_shape *os) {
+    if (!pass || !m || !ms || !out || !os) WGB_FAIL(WGB_ERR_INVALID, "wgb_reduce_columns: null argument");
+    if ((int)op < 0 || (int)op > WGB_RED_SQNORM) WGB_FAIL(WGB_ERR_INVALID, "wgb_reduce_columns: unknown op %d", (int)op);
+    if ((uint64_t)ms->size[1] * ms->size[2] != os->size[0])
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Reduce-columns: dimension mismatch. (%u x %u columns vs %u outputs)", ms->size[1],
+                 ms->size[2], os->size[0]);
+    if (any_zero_buffer({m, out}) || os->size[0] == 0) return WGB_OK;
+    WGB_TRY(check_view(m, *ms, 4, "reduce_columns m"));
+    WGB_TRY(check_view(out, *os, 4, "reduce_columns out", true));
+    DeviceGuard g(pass->ctx->device);
+    return launch_reduce_columns(pass, (int)op, (const float *)m->ptr, *ms, (float *)out->ptr + os->offset);
+}
+
+wgb_status wgb_fill_uniform(wgb_pass *pass, wgb_buffer *buf, const wgb_view_shape *s, wgb_dtype dt, uint64_t seed,
+                            uint32_t row0, uint32_t col0) {
+    if (!pass || !buf || !s) WGB_FAIL(WGB_ERR_INVALID, "wgb_fill_uniform: null argument");
+    if (buf->bytes == 0 || view_extent(*s) == 0) return WGB_OK;
+    WGB_TRY(check_view(buf, *s, dtype_size(dt), "fill_uniform"));
+    DeviceGuard g(pass->ctx->device);
+    return launch_fill_uniform(pass, buf->ptr, *s, dt, seed, row0, col0);
+}
+
+wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *so,
+                    const wgb_buffer *m, const wgb_view_shape *sm, const wgb_buffer *v, const wgb_view_shape *sv) {
+    if (!pass || !out || !so || !m || !sm || !v || !sv) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: null argument");
+    if ((int)variant < 0 || (int)variant > WGB_GEMV_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: unknown variant %d", (int)variant);
+    const bool tr = variant == WGB_GEMV_TR || variant == WGB_GEMV_TR_FAST;
+    const uint32_t m_rows = tr ? sm->size[1] : sm->size[0];
+    const uint32_t m_cols = tr ? sm->size[0] : sm->size[1];
+    if (m_cols != sv->size[0])  // gemv.rs:89
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemv: dimension mismatch. (matrix cols %u vs vector rows %u)", m_cols, sv->size[0]);
+    if (m_rows != so->size[0])  // gemv.rs:90
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemv: dimension mismatch. (matrix rows %u vs out rows %u)", m_rows, so->size[0]);
+    // gemv.rs:99-104: GemvTrFast silently becomes GemvTr when m.nrows % 128 != 0; gemv.rs:122: the *_fast
+    // variants assert out_nrows % 4 == 0.  Here all variants share one kernel pair that is valid for every
+    // shape, so the fallback is moot; the assert is kept so callers see the reference's panic.
+    const bool fast = variant == WGB_GEMV_FAST || (variant == WGB_GEMV_TR_FAST && sm->size[0] % 128u == 0);
+    if (fast && so->size[0] % 4u != 0)
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemv: the fast variants require out rows %% 4 == 0 (got %u)", so->size[0]);
+    // The reference reads v / m with the *output's* column and batch counts (grid = [.., out_ncols, out_nmats],
+    // gemv.rs:136) and never checks them against v / m: make the implied requirement explicit.
+    if (sv->size[1] < so->size[1] || sv->size[2] < so->size[2] || sm->size[2] < so->size[2])
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemv: out has %u columns x %u matrices but v has %u x %u and m has %u matrices",
+                 so->size[1], so->size[2], sv->size[1], sv->size[2], sm->size[2]);
+    if (any_zero_buffer({out, m, v}) || view_extent(*so) == 0) return WGB_OK;
+    wgb_view_shape sv_used = *sv, sm_used = *sm;
+    sv_used.size[1] = so->size[1];
+    sv_used.size[2] = so->size[2];
+    sm_used.size[2] = so->size[2];
+    WGB_TRY(check_view(out, *so, 4, "gemv out"));
+    WGB_TRY(check_view(m, sm_used, 4, "gemv m"));
+    WGB_TRY(check_view(v, sv_used, 4, "gemv v"));
+    DeviceGuard g(pass->ctx->device);
+    return launch_gemv(pass, tr, (float *)out->ptr, *so, (const float *)m->ptr, sm_used, (const float *)v->ptr, sv_used);
+}
+
+wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
+                       const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
+                       wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode) {
+    if (!pass || !out || !so || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: null argument");
+    if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown variant %d", (int)variant);
+    if ((in_dtype != WGB_F32 && in_dtype != WGB_BF16) || (out_dtype != WGB_F32 && out_dtype != WGB_BF16))
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm: unsupported dtype");
+    if ((int)mode < 0 || (int)mode > WGB_F32_SIMT) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown f32 mode %d", (int)mode);
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    const uint32_t m_rows = tr ? s1->size[1] : s1->size[0];
+    const uint32_t m_cols = tr ? s1->size[0] : s1->size[1];
+    // gemm.rs:91-95, same order and message
+    if (m_cols != s2->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 cols %u vs m2 rows %u)", m_cols, s2->size[0]);
+    if (m_rows != so->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 rows %u vs out rows %u)", m_rows, so->size[0]);
+    if (so->size[1] != s2->size[1]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (out cols %u vs m2 cols %u)", so->size[1], s2->size[1]);
+    if (so->size[2] != s1->size[2]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (out mats %u vs m1 mats %u)", so->size[2], s1->size[2]);
+    if (so->size[2] != s2->size[2]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (out mats %u vs m2 mats %u)", so->size[2], s2->size[2]);
+    pass->last_gemm_path = 0;
+    if (any_zero_buffer({out, m1, m2}) || view_extent(*so) == 0) return WGB_OK;
+    WGB_TRY(check_view(out, *so, dtype_size(out_dtype), "gemm out"));
+    WGB_TRY(check_view(m1, *s1, dtype_size(in_dtype), "gemm m1"));
+    WGB_TRY(check_view(m2, *s2, dtype_size(in_dtype), "gemm m2"));
+    GemmProblem g{};
+    g.tr = tr;
+    g.M = so->size[0];
+    g.N = so->size[1];
+    g.K = m_cols;
+    g.nmats = so->size[2];
+    g.a = m1->ptr; g.b = m2->ptr; g.c = out->ptr;
+    g.a_off = s1->offset; g.b_off = s2->offset; g.c_off = so->offset;
+    g.lda = s1->stride; g.ldb = s2->stride; g.ldc = so->stride;
+    g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = so->stride_mat;
+    g.in_dtype = in_dtype;
+    g.out_dtype = out_dtype;
+    DeviceGuard dg(pass->ctx->device);
+    return gemm_dispatch(pass, g, mode);
+}
+
+wgb_status wgb_gemm(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
+                    const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2) {
+    return wgb_gemm_ex(pass, variant, out, so, m1, s1, m2, s2, WGB_F32, WGB_F32, WGB_F32_AUTO);
+}
+
+}  // extern "C"

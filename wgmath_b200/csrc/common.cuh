@@ -1,0 +1,163 @@
+// common.cuh — internal definitions shared by the translation units of libwgebra_b200.so.
+// Handles, error plumbing, view-shape validation, launch accounting and the split-reduction
+// scratch that the bandwidth-bound kernels use.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/wgb200.h"
+
+namespace wgb {
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+
+#define WGB_FAIL(status, ...)          \
+    do {                               \
+        ::wgb::set_error(__VA_ARGS__); \
+        return (status);               \
+    } while (0)
+
+#define WGB_CUDA(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::wgb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                      \
+            return _e == cudaErrorMemoryAllocation ? WGB_ERR_OOM : WGB_ERR_CUDA;             \
+        }                                                                                    \
+    } while (0)
+
+#define WGB_TRY(expr)                      \
+    do {                                   \
+        wgb_status _s = (expr);            \
+        if (_s != WGB_OK) return _s;       \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------
+struct Scratch {
+    float *partials = nullptr;      // split-reduction partial results
+    size_t partials_floats = 0;
+    unsigned int *counters = nullptr;  // last-arriver tickets; always left at zero
+    size_t n_counters = 0;
+};
+
+struct Workspace {  // growable device workspace (3xTF32 operand splits, sharded GEMM panels)
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct CommState;  // comm.cu
+
+}  // namespace wgb
+
+struct wgb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;       // the in-order queue
+    cudaStream_t comm_stream = nullptr;  // side stream for the all-gather of C
+    cudaDeviceProp prop{};
+    std::atomic<uint64_t> launches{0};
+    wgb::Scratch scratch;
+    wgb::Workspace ws[4];
+    wgb::CommState *comm = nullptr;
+    std::mutex mu;
+    void *tmap_cache = nullptr;  // gemm_tc.cu
+};
+
+struct wgb_pass {
+    wgb_ctx *ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    wgb_event *end_ts = nullptr;
+    int last_gemm_path = 0;
+};
+
+struct wgb_buffer {
+    wgb_ctx *ctx = nullptr;
+    void *ptr = nullptr;  // device pointer, or pinned host pointer when host_pinned
+    size_t bytes = 0;
+    bool host_pinned = false;
+    bool owned = true;
+    uint32_t usage = 0;
+};
+
+struct wgb_event {
+    wgb_ctx *ctx = nullptr;
+    cudaEvent_t ev = nullptr;
+};
+
+namespace wgb {
+
+inline void count_launch(wgb_ctx *ctx, uint64_t n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+inline size_t dtype_size(wgb_dtype d) { return d == WGB_BF16 ? 2 : 4; }
+
+// Largest element index (exclusive) touched by a matrix / cube view: offset + extent.
+inline uint64_t view_extent(const wgb_view_shape &s) {
+    if (s.size[0] == 0 || s.size[1] == 0 || s.size[2] == 0) return 0;
+    return (uint64_t)s.offset + (uint64_t)(s.size[2] - 1) * s.stride_mat + (uint64_t)(s.size[1] - 1) * s.stride +
+           s.size[0];
+}
+inline uint64_t vector_extent(const wgb_view_shape &s) { return s.size[0] ? (uint64_t)s.offset + s.size[0] : 0; }
+
+wgb_status check_view(const wgb_buffer *b, const wgb_view_shape &s, size_t elem_size, const char *what,
+                      bool vector_only = false);
+
+// Grow-only device workspace slot; contents are undefined after a grow.
+wgb_status workspace_reserve(wgb_ctx *ctx, int slot, size_t bytes, void **out);
+wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters);
+
+// ---- kernels launched from the dispatch layer (one per .cu) --------------------------------
+wgb_status launch_op_assign(wgb_pass *p, int op, float *a, const float *b, uint64_t n);
+wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, uint64_t n, float *result);
+wgb_status launch_reduce_columns(wgb_pass *p, int op, const float *m, const wgb_view_shape &ms, float *out);
+wgb_status launch_fill_uniform(wgb_pass *p, void *base, const wgb_view_shape &s, wgb_dtype dt, uint64_t seed,
+                               uint32_t row0, uint32_t col0);
+wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
+                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv);
+
+struct GemmProblem {
+    bool tr;               // out = tr(m1) * m2
+    uint32_t M, N, K, nmats;
+    const void *a;         // m1 base (element 0 of the buffer)
+    const void *b;         // m2 base
+    void *c;               // out base
+    uint64_t a_off, b_off, c_off;     // element offsets
+    uint64_t lda, ldb, ldc;           // column strides, elements
+    uint64_t sa, sb, sc;              // matrix strides, elements
+    wgb_dtype in_dtype, out_dtype;
+};
+wgb_status launch_gemm_simt(wgb_pass *p, const GemmProblem &g);
+// tcgen05 path. `passes`: 1 (bf16 or single-pass tf32) or 3 (3xTF32; operands pre-split).
+bool gemm_tc_eligible(const GemmProblem &g);
+wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, int *path_out);
+
+// column-panel range restriction used by the sharded GEMM (compute only n in [n_begin, n_end))
+wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode);
+
+}  // namespace wgb

@@ -1,0 +1,29 @@
+// gemm.cu — path selection for wgb_gemm / wgb_gemm_ex (include/wgb200.h).
+//
+// The reference picks one of four WGSL pipelines by GemmVariant (gemm.rs:102-115); all four compute the
+// same product, so here the variant only selects tr / non-tr and the *kernel family* is chosen from the
+// operand types, the requested f32 mode and whether the views satisfy TMA's alignment rules:
+//   bf16 operands, TMA-eligible          -> tcgen05 kind::f16 (bf16)            path 2
+//   f32 operands, WGB_F32_TF32           -> tcgen05 kind::tf32, single pass      path 3
+//   f32 operands, WGB_F32_AUTO / 3XTF32  -> tcgen05 kind::tf32, 3-pass hi/lo     path 4   (parity-gated default)
+//   anything else (odd strides / offsets, tiny problems, WGB_F32_SIMT, K == 0) -> FFMA kernel, path 1
+#include "common.cuh"
+
+namespace wgb {
+
+wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode) {
+    const uint64_t work = (uint64_t)g.M * g.N * (uint64_t)g.K;
+    // Below ~64^3 per matrix a tensor-core launch (tensor-map encode + 2 helper kernels for 3xTF32) costs more
+    // than the FFMA kernel's whole run time.
+    const bool tiny = work < (uint64_t)96 * 96 * 96 || g.K == 0;
+    const bool want_tc = !tiny && mode != WGB_F32_SIMT && gemm_tc_eligible(g);
+    if (want_tc) {
+        int path = 0;
+        wgb_status s = launch_gemm_tc(p, g, mode, &path);
+        if (s == WGB_OK) p->last_gemm_path = path;
+        return s;
+    }
+    return launch_gemm_simt(p, g);
+}
+
+}  // namespace wgb

@@ -1,0 +1,366 @@
+// gemv.cu — out = m * v and out = tr(m) * v for column-major f32 views.  HBM-bound.
+//
+// Reference kernels replaced (/root/reference/crates/wgebra/src/linalg/gemv.wgsl):
+//   gemv          :68-90   thread owns 4 rows, serial loop over all of K
+//   gemv_fast     :29-65   32 threads per 4 rows + tree reduce
+//   gemv_tr       :93-115  thread owns 4 columns, serial loop over all rows
+//   gemv_tr_fast  :118-154 32 threads per 4 columns + tree reduce
+// and the launch logic of gemv.rs:64-137 (grid = [rows, out_ncols, out_nmats]: m is re-read once
+// per output column).
+//
+// B200 design
+//   gemv    : CTA = 8 warps owns a 128-row tile x a K range.  A warp reads one 512-byte column
+//             segment per instruction (lane = 4 consecutive rows, one 128-bit load), the 8 warps
+//             interleave columns, 4 columns in flight per lane; v is staged in shared memory; up to
+//             4 output columns are produced per pass over m (m is read once, not once per column).
+//             Cross-warp sum through shared memory in warp order.  When M is too small to fill the
+//             machine the K range is split across CTAs (grid.y) and the last CTA of a row tile folds
+//             the split partials in split order (deterministic; no float atomics).
+//   gemv_tr : one warp per column of m (the contiguous axis), 128-bit loads, 4 in flight per lane,
+//             warp-shuffle sum; rows split across CTAs when there are too few columns.
+// Any offset / stride / length is valid: tiles that are not 16-byte aligned or are ragged take a
+// scalar, predicated path inside the same kernels.
+//
+// Algorithmic bytes per launch: 4 * (M*K + K*C + M*C) per matrix.
+#include "common.cuh"
+
+namespace wgb {
+
+static constexpr int kThreads = 256;
+static constexpr int kWarps = 8;
+static constexpr int kTileRows = 128;
+static constexpr int kStage = 512;  // columns of v staged per step
+
+struct GemvArgs {
+    const float *m, *v;
+    float *out;
+    uint32_t M, K;      // out rows, reduction length
+    uint32_t C;         // output columns
+    uint32_t cchunks;   // ceil(C / NV)
+    uint64_t ldm, sm;   // m column / matrix stride
+    uint64_t ldv, sv;
+    uint64_t ldo, so;
+    uint32_t nsplit, chunk;  // reduction split count and length per split
+    uint32_t z_base;
+    float *partials;
+    unsigned int *counters;
+};
+
+__device__ __forceinline__ void fma4(float (&acc)[4], const float4 &x, float s) {
+    acc[0] = fmaf(x.x, s, acc[0]);
+    acc[1] = fmaf(x.y, s, acc[1]);
+    acc[2] = fmaf(x.z, s, acc[2]);
+    acc[3] = fmaf(x.w, s, acc[3]);
+}
+
+template <bool VEC, int NV>
+__global__ void __launch_bounds__(kThreads) gemv_n_kernel(GemvArgs a) {
+    __shared__ float vs[NV][kStage];
+    __shared__ float red[kWarps][NV][kTileRows];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t z = a.z_base + blockIdx.z;
+    const uint32_t t = z / a.cchunks, c0 = (z % a.cchunks) * NV;
+    const uint32_t nv = min((uint32_t)NV, a.C - c0);
+    const uint32_t row0 = blockIdx.x * kTileRows;
+    const uint32_t k0 = blockIdx.y * a.chunk;
+    const uint32_t k1 = min(a.K, k0 + a.chunk);
+    const float *mp = a.m + (uint64_t)t * a.sm;
+    const float *vp = a.v + (uint64_t)t * a.sv + (uint64_t)c0 * a.ldv;
+    const bool full = VEC && (row0 + kTileRows <= a.M);
+
+    float acc[NV][4];
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[c][q] = 0.f;
+
+    for (uint32_t ks = k0; ks < k1; ks += kStage) {
+        const uint32_t kn = min((uint32_t)kStage, k1 - ks);
+        for (uint32_t idx = threadIdx.x; idx < kn * NV; idx += kThreads) {
+            const uint32_t c = idx / kn, kk = idx - c * kn;
+            vs[c][kk] = c < nv ? __ldg(vp + (uint64_t)c * a.ldv + ks + kk) : 0.f;
+        }
+        __syncthreads();
+        if (full) {
+            const float *base = mp + row0 + 4 * lane + (uint64_t)ks * a.ldm;
+            uint32_t kk = w;
+            for (; kk + 3 * kWarps < kn; kk += 4 * kWarps) {
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = __ldcs(reinterpret_cast<const float4 *>(base + (uint64_t)(kk + u * kWarps) * a.ldm));
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < NV; ++c) fma4(acc[c], x[u], vs[c][kk + u * kWarps]);
+            }
+            for (; kk < kn; kk += kWarps) {
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(base + (uint64_t)kk * a.ldm));
+#pragma unroll
+                for (int c = 0; c < NV; ++c) fma4(acc[c], x, vs[c][kk]);
+            }
+        } else {
+            // scalar, predicated: lane owns rows row0 + lane + 32 q (still one coalesced 128-byte request per q)
+            for (uint32_t kk = w; kk < kn; kk += kWarps) {
+                const float *colp = mp + (uint64_t)(ks + kk) * a.ldm;
+                float x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t r = row0 + lane + 32 * q;
+                    x[q] = r < a.M ? __ldcs(colp + r) : 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[c][q] = fmaf(x[q], vs[c][kk], acc[c][q]);
+            }
+        }
+        __syncthreads();
+    }
+
+    // cross-warp sum, fixed warp order
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) red[w][c][full ? 4 * lane + q : lane + 32 * q] = acc[c][q];
+    __syncthreads();
+    const bool split = a.nsplit > 1;
+    const uint64_t tile_id = (uint64_t)z * gridDim.x + blockIdx.x;
+    for (uint32_t idx = threadIdx.x; idx < NV * kTileRows; idx += kThreads) {
+        const uint32_t c = idx / kTileRows, rl = idx % kTileRows;
+        float s = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) s += red[ww][c][rl];
+        if (!split) {
+            if (row0 + rl < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + row0 + rl] = s;
+        } else {
+            a.partials[((tile_id * a.nsplit + blockIdx.y) * NV + c) * kTileRows + rl] = s;
+        }
+    }
+    if (!split) return;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(a.counters + tile_id, 1u);
+        is_last = ticket == a.nsplit - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (uint32_t idx = threadIdx.x; idx < NV * kTileRows; idx += kThreads) {
+        const uint32_t c = idx / kTileRows, rl = idx % kTileRows;
+        float s = 0.f;
+        for (uint32_t y = 0; y < a.nsplit; ++y) s += __ldcg(a.partials + ((tile_id * a.nsplit + y) * NV + c) * kTileRows + rl);
+        if (row0 + rl < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + row0 + rl] = s;
+    }
+    if (threadIdx.x == 0) a.counters[tile_id] = 0u;
+}
+
+__device__ __forceinline__ float dot4(const float4 &x, const float4 &y, float acc) {
+    acc = fmaf(x.x, y.x, acc);
+    acc = fmaf(x.y, y.y, acc);
+    acc = fmaf(x.z, y.z, acc);
+    return fmaf(x.w, y.w, acc);
+}
+
+// out[j] = sum_i m[i, j] * v[i]; here a.M = number of outputs (columns of m), a.K = rows of m.
+template <bool VEC, int NV>
+__global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t z = a.z_base + blockIdx.z;
+    const uint32_t t = z / a.cchunks, c0 = (z % a.cchunks) * NV;
+    const uint32_t nv = min((uint32_t)NV, a.C - c0);
+    const uint32_t j = blockIdx.x * kWarps + w;
+    const bool valid = j < a.M;
+    const uint32_t r0 = blockIdx.y * a.chunk;
+    const uint32_t r1 = min(a.K, r0 + a.chunk);
+    const float *col = a.m + (uint64_t)t * a.sm + (uint64_t)(valid ? j : 0) * a.ldm;
+    const float *vp = a.v + (uint64_t)t * a.sv + (uint64_t)c0 * a.ldv;
+
+    float acc[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) acc[c] = 0.f;
+
+    if (valid) {
+        if (VEC) {
+            const uint32_t nvec = (r1 - r0) >> 2;  // r0 is a multiple of 4 (chunk is)
+            const float *cb = col + r0;
+            const float *vb = vp + r0;
+            uint32_t i = lane;
+            for (; i + 96 < nvec; i += 128) {
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = __ldcs(reinterpret_cast<const float4 *>(cb) + i + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        if (c < nv) acc[c] = dot4(x[u], __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i + 32 * u), acc[c]);
+            }
+            for (; i < nvec; i += 32) {
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(cb) + i);
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c < nv) acc[c] = dot4(x, __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i), acc[c]);
+            }
+            for (uint32_t r = r0 + (nvec << 2) + lane; r < r1; r += 32) {
+                const float x = col[r];
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c < nv) acc[c] = fmaf(x, vp[(uint64_t)c * a.ldv + r], acc[c]);
+            }
+        } else {
+            uint32_t r = r0 + lane;
+            for (; r + 96 < r1; r += 128) {
+                float x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = __ldcs(col + r + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        if (c < nv) acc[c] = fmaf(x[u], __ldg(vp + (uint64_t)c * a.ldv + r + 32 * u), acc[c]);
+            }
+            for (; r < r1; r += 32) {
+                const float x = __ldcs(col + r);
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c < nv) acc[c] = fmaf(x, __ldg(vp + (uint64_t)c * a.ldv + r), acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+
+    const bool split = a.nsplit > 1;
+    if (!split) {
+        if (valid && lane == 0)
+#pragma unroll
+            for (int c = 0; c < NV; ++c)
+                if (c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + j] = acc[c];
+        return;
+    }
+    const uint64_t tile_id = (uint64_t)z * gridDim.x + blockIdx.x;
+    if (lane == 0)
+#pragma unroll
+        for (int c = 0; c < NV; ++c) a.partials[((tile_id * a.nsplit + blockIdx.y) * kWarps + w) * NV + c] = acc[c];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(a.counters + tile_id, 1u);
+        is_last = ticket == a.nsplit - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (threadIdx.x < kWarps * NV) {
+        const uint32_t ww = threadIdx.x / NV, c = threadIdx.x % NV;
+        const uint32_t jj = blockIdx.x * kWarps + ww;
+        float s = 0.f;
+        for (uint32_t y = 0; y < a.nsplit; ++y) s += __ldcg(a.partials + ((tile_id * a.nsplit + y) * kWarps + ww) * NV + c);
+        if (jj < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + jj] = s;
+    }
+    if (threadIdx.x == 0) a.counters[tile_id] = 0u;
+}
+
+template <bool TR, bool VEC, int NV>
+static void launch_one(const GemvArgs &a, dim3 grid, cudaStream_t st) {
+    if (TR) gemv_t_kernel<VEC, NV><<<grid, kThreads, 0, st>>>(a);
+    else gemv_n_kernel<VEC, NV><<<grid, kThreads, 0, st>>>(a);
+}
+
+template <bool TR>
+static void launch_sel(bool vec, int nv, const GemvArgs &a, dim3 grid, cudaStream_t st) {
+    if (vec) {
+        if (nv == 1) launch_one<TR, true, 1>(a, grid, st);
+        else if (nv == 2) launch_one<TR, true, 2>(a, grid, st);
+        else launch_one<TR, true, 4>(a, grid, st);
+    } else {
+        if (nv == 1) launch_one<TR, false, 1>(a, grid, st);
+        else if (nv == 2) launch_one<TR, false, 2>(a, grid, st);
+        else launch_one<TR, false, 4>(a, grid, st);
+    }
+}
+
+wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
+                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv) {
+    wgb_ctx *ctx = p->ctx;
+    GemvArgs a{};
+    a.m = m + sm.offset;
+    a.v = v + sv.offset;
+    a.out = out + so.offset;
+    a.M = so.size[0];
+    a.K = sv.size[0];
+    a.C = so.size[1];
+    const uint32_t nmats = so.size[2];
+    a.ldm = sm.stride; a.sm = sm.stride_mat;
+    a.ldv = sv.stride; a.sv = sv.stride_mat;
+    a.ldo = so.stride; a.so = so.stride_mat;
+    const int nv = a.C == 1 ? 1 : (a.C == 2 ? 2 : 4);
+    a.cchunks = (a.C + nv - 1) / nv;
+    const uint64_t zdim = (uint64_t)a.cchunks * nmats;
+
+    if (a.K == 0) {
+        // empty reduction: the reference's loops do not execute and it stores zeros (gemv.wgsl:74,88)
+        for (uint32_t t = 0; t < nmats; ++t)
+            for (uint32_t c = 0; c < a.C; ++c)
+                WGB_CUDA(cudaMemsetAsync(a.out + (uint64_t)t * a.so + (uint64_t)c * a.ldo, 0, (size_t)a.M * 4, p->stream));
+        return WGB_OK;
+    }
+
+    auto al16 = [](const void *ptr) { return ((uintptr_t)ptr & 15u) == 0; };
+    bool vec;
+    uint64_t tiles_x;
+    if (!tr) {
+        vec = al16(a.m) && a.ldm % 4 == 0 && (nmats == 1 || a.sm % 4 == 0);
+        tiles_x = (a.M + kTileRows - 1) / kTileRows;
+    } else {
+        vec = al16(a.m) && a.ldm % 4 == 0 && (nmats == 1 || a.sm % 4 == 0) && al16(a.v) && (a.C == 1 || a.ldv % 4 == 0) &&
+              (nmats == 1 || a.sv % 4 == 0);
+        tiles_x = (a.M + kWarps - 1) / kWarps;
+    }
+    // split the reduction axis when the output axis alone cannot fill the machine
+    const uint64_t target = (uint64_t)ctx->prop.multiProcessorCount * 16;
+    const uint32_t min_chunk = tr ? 2048 : 256;
+    uint64_t nsplit = 1;
+    if (tiles_x * zdim < target) {
+        nsplit = (target + tiles_x * zdim - 1) / (tiles_x * zdim);
+        const uint64_t max_split = (a.K + min_chunk - 1) / min_chunk;
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit > 65535) nsplit = 65535;
+    }
+    uint32_t chunk = (uint32_t)(((uint64_t)a.K + nsplit - 1) / nsplit);
+    chunk = (chunk + 31u) & ~31u;
+    nsplit = ((uint64_t)a.K + chunk - 1) / chunk;
+    if (nsplit > 1) {
+        const uint64_t per_tile = tr ? (uint64_t)kWarps * nv : (uint64_t)nv * kTileRows;
+        const uint64_t need = tiles_x * zdim * nsplit * per_tile;
+        if (tiles_x * zdim > (1u << 20) || need > ((uint64_t)64 << 20)) {
+            nsplit = 1;
+            chunk = (a.K + 31u) & ~31u;
+        } else {
+            WGB_TRY(scratch_reserve(ctx, need, tiles_x * zdim));
+        }
+    }
+    a.nsplit = (uint32_t)nsplit;
+    a.chunk = chunk;
+    a.partials = ctx->scratch.partials;
+    a.counters = ctx->scratch.counters;
+    if (tiles_x > 0x7fffffffull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemv: too many row tiles");
+
+    for (uint64_t z0 = 0; z0 < zdim; z0 += 65535) {
+        const uint32_t zn = (uint32_t)((zdim - z0) < 65535 ? (zdim - z0) : 65535);
+        a.z_base = (uint32_t)z0;
+        dim3 grid((unsigned)tiles_x, (unsigned)nsplit, zn);
+        if (tr) launch_sel<true>(vec, nv, a, grid, p->stream);
+        else launch_sel<false>(vec, nv, a, grid, p->stream);
+        WGB_CUDA(cudaGetLastError());
+        count_launch(ctx);
+    }
+    return WGB_OK;
+}
+
+}  // namespace wgb
