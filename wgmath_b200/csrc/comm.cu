@@ -1,8 +1,226 @@
+// comm.cu — the one multi-GPU element of the path: a GEMM sharded by output-row block across the GPUs of
+// one box, followed by the all-gather of C over NVLink / NVSwitch (BASELINE configs[4]).
+// The reference has no multi-device code at all (one wgpu::Device, one Queue: wgcore/src/gpu.rs:7-12).
+//
+// One process per GPU; rank p owns rows [p*M/P, (p+1)*M/P) of m1 and of the product, m2 is replicated.
+// Layout choice (SURVEY.md §8(e) option (i)): every rank computes its block into a *contiguous* column-major
+// [M/P x N] panel; the gathered result is P panels back to back, i.e. exactly a reference GpuCube view
+// size = [M/P, N, P], stride = M/P, stride_mat = (M/P)*N (tensor.rs:465-481) — no extra pass over C.
+//
+// Overlap: N is cut into column chunks.  Chunk c's GEMM runs on the queue stream; as soon as it finishes
+// (event), the exchange of chunk c (grouped ncclSend/ncclRecv — an all-gather with arbitrary placement, so
+// the chunk lands directly inside each panel) runs on the context's comm stream while chunk c+1 computes.
+// The GEMM leaves `WGB_COMM_SM_MARGIN` SMs free so the NCCL CTAs can be co-resident instead of queueing
+// behind the persistent GEMM CTAs.
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2: the copy the host framework already loaded, else the
+// system one), so libwgebra_b200.so itself has no link-time NCCL dependency.
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "common.cuh"
-namespace wgb { void comm_destroy(wgb_ctx *) {} }
-extern "C" {
-wgb_status wgb_comm_get_unique_id(void *) { WGB_FAIL(WGB_ERR_UNSUPPORTED, "comm stub"); }
-wgb_status wgb_comm_init_rank(wgb_ctx *, int, int, const void *) { WGB_FAIL(WGB_ERR_UNSUPPORTED, "comm stub"); }
-wgb_status wgb_comm_destroy(wgb_ctx *) { return WGB_OK; }
-wgb_status wgb_gemm_row_sharded(wgb_pass *, wgb_gemm_variant, wgb_buffer *, const wgb_buffer *, const wgb_view_shape *, const wgb_buffer *, const wgb_view_shape *, wgb_dtype, wgb_dtype, wgb_f32_mode, int) { WGB_FAIL(WGB_ERR_UNSUPPORTED, "comm stub"); }
+
+namespace wgb {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t *, int, ncclUniqueId, int, ncclConfig_t *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+static NcclApi &nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *names[] = {getenv("WGB_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char *n : names) {
+            if (!n || !*n) continue;
+            api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (!api.handle) return;
+#define SYM(field, name) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, name))
+        SYM(GetUniqueId, "ncclGetUniqueId");
+        SYM(CommInitRank, "ncclCommInitRank");
+        SYM(CommInitRankConfig, "ncclCommInitRankConfig");
+        SYM(CommDestroy, "ncclCommDestroy");
+        SYM(GroupStart, "ncclGroupStart");
+        SYM(GroupEnd, "ncclGroupEnd");
+        SYM(Send, "ncclSend");
+        SYM(Recv, "ncclRecv");
+        SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
+    });
+    return api;
 }
+
+struct CommState {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0;
+    int sm_margin = 0;
+    std::vector<cudaEvent_t> events;
+    cudaEvent_t done = nullptr;
+};
+
+#define WGB_NCCL(expr)                                                                                          \
+    do {                                                                                                        \
+        ncclResult_t _r = (expr);                                                                               \
+        if (_r != ncclSuccess)                                                                                  \
+            WGB_FAIL(WGB_ERR_NCCL, "%s failed: %s", #expr, nccl().GetErrorString ? nccl().GetErrorString(_r) : "?"); \
+    } while (0)
+
+void comm_destroy(wgb_ctx *ctx) {
+    CommState *c = ctx->comm;
+    if (!c) return;
+    for (auto e : c->events) cudaEventDestroy(e);
+    if (c->done) cudaEventDestroy(c->done);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    delete c;
+    ctx->comm = nullptr;
+}
+
+int comm_sm_margin(const wgb_ctx *ctx) { return ctx->comm && ctx->comm->nranks > 1 ? ctx->comm->sm_margin : 0; }
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace wgb
+
+using namespace wgb;
+
+extern "C" {
+
+wgb_status wgb_comm_get_unique_id(void *id_out) {
+    static_assert(sizeof(ncclUniqueId) == WGB_COMM_ID_BYTES, "ncclUniqueId size changed");
+    if (!id_out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    if (!nccl().ok) WGB_FAIL(WGB_ERR_NCCL, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "symbols missing");
+    ncclUniqueId id;
+    WGB_NCCL(nccl().GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof id);
+    return WGB_OK;
+}
+
+wgb_status wgb_comm_init_rank(wgb_ctx *ctx, int nranks, int rank, const void *id_bytes) {
+    if (!ctx || !id_bytes || nranks < 1 || rank < 0 || rank >= nranks) WGB_FAIL(WGB_ERR_INVALID, "wgb_comm_init_rank: bad argument");
+    if (!nccl().ok) WGB_FAIL(WGB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    if (ctx->comm) comm_destroy(ctx);
+    DeviceGuard g(ctx->device);
+    CommState *c = new CommState();
+    c->nranks = nranks;
+    c->rank = rank;
+    const int max_ctas = env_int("WGB_COMM_MAX_CTAS", 8);
+    c->sm_margin = env_int("WGB_COMM_SM_MARGIN", max_ctas);
+    ncclUniqueId id;
+    memcpy(&id, id_bytes, sizeof id);
+    ncclResult_t r;
+    if (nccl().CommInitRankConfig) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.maxCTAs = max_ctas;   // the exchange needs a sliver of NVLink bandwidth; keep its SM footprint small
+        cfg.minCTAs = 1;
+        r = nccl().CommInitRankConfig(&c->comm, nranks, id, rank, &cfg);
+    } else {
+        r = nccl().CommInitRank(&c->comm, nranks, id, rank);
+    }
+    if (r != ncclSuccess) {
+        delete c;
+        WGB_FAIL(WGB_ERR_NCCL, "ncclCommInitRank failed: %s", nccl().GetErrorString ? nccl().GetErrorString(r) : "?");
+    }
+    cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+    ctx->comm = c;
+    return WGB_OK;
+}
+
+wgb_status wgb_comm_destroy(wgb_ctx *ctx) {
+    if (ctx) {
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->comm_stream);
+        comm_destroy(ctx);
+    }
+    return WGB_OK;
+}
+
+wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_buffer *m1,
+                                const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2, wgb_dtype in_dtype,
+                                wgb_dtype out_dtype, wgb_f32_mode mode, int n_chunks) {
+    if (!pass || !out || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded: null argument");
+    wgb_ctx *ctx = pass->ctx;
+    CommState *cs = ctx->comm;
+    const int P = cs ? cs->nranks : 1, rank = cs ? cs->rank : 0;
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    if (s1->size[2] != 1 || s2->size[2] != 1) WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_row_sharded: batched operands are not supported");
+    const uint32_t Mloc = tr ? s1->size[1] : s1->size[0];
+    const uint32_t K = tr ? s1->size[0] : s1->size[1];
+    const uint32_t N = s2->size[1];
+    if (K != s2->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 cols %u vs m2 rows %u)", K, s2->size[0]);
+    const size_t os = dtype_size(out_dtype), es = dtype_size(in_dtype);
+    const uint64_t panel = (uint64_t)Mloc * N;
+    if (panel * P * os > out->bytes)
+        WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_gemm_row_sharded: gathered output needs %llu bytes, buffer has %zu",
+                 (unsigned long long)(panel * P * os), out->bytes);
+    if (panel > 0xFFFFFFFFull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_row_sharded: panel exceeds u32 indexing");
+    WGB_TRY(check_view(m1, *s1, es, "sharded gemm m1"));
+    WGB_TRY(check_view(m2, *s2, es, "sharded gemm m2"));
+    if (Mloc == 0 || N == 0) return WGB_OK;
+    DeviceGuard dg(ctx->device);
+
+    // column chunks: multiples of 256 columns (whole BLOCK_N tiles), default 8 chunks when exchanging
+    uint32_t nch = n_chunks > 0 ? (uint32_t)n_chunks : (P > 1 ? 8u : 1u);
+    uint32_t width = (N + nch - 1) / nch;
+    width = (width + 255u) & ~255u;
+    nch = (N + width - 1) / width;
+    if (cs)
+        while (cs->events.size() < nch) {
+            cudaEvent_t e;
+            WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            cs->events.push_back(e);
+        }
+
+    for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t n0 = c * width, nc = (N - n0) < width ? (N - n0) : width;
+        GemmProblem g{};
+        g.tr = tr;
+        g.M = Mloc; g.N = nc; g.K = K; g.nmats = 1;
+        g.a = m1->ptr; g.b = m2->ptr; g.c = out->ptr;
+        g.a_off = s1->offset;
+        g.b_off = (uint64_t)s2->offset + (uint64_t)n0 * s2->stride;
+        g.c_off = (uint64_t)rank * panel + (uint64_t)n0 * Mloc;
+        g.lda = s1->stride; g.ldb = s2->stride; g.ldc = Mloc;
+        g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = panel;
+        g.in_dtype = in_dtype; g.out_dtype = out_dtype;
+        WGB_TRY(gemm_dispatch(pass, g, mode));
+        if (P > 1) {
+            WGB_CUDA(cudaEventRecord(cs->events[c], pass->stream));
+            WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, cs->events[c], 0));
+            const size_t bytes = (size_t)nc * Mloc * os;
+            char *base = (char *)out->ptr;
+            const size_t chunk_off = (size_t)n0 * Mloc * os;
+            WGB_NCCL(nccl().GroupStart());
+            for (int d = 1; d < P; ++d) {
+                const int to = (rank + d) % P, from = (rank - d + P) % P;
+                WGB_NCCL(nccl().Send(base + (size_t)rank * panel * os + chunk_off, bytes, ncclInt8, to, cs->comm, ctx->comm_stream));
+                WGB_NCCL(nccl().Recv(base + (size_t)from * panel * os + chunk_off, bytes, ncclInt8, from, cs->comm, ctx->comm_stream));
+            }
+            WGB_NCCL(nccl().GroupEnd());
+            count_launch(ctx);
+        }
+    }
+    if (P > 1) {
+        // later work on the queue sees the gathered panels
+        WGB_CUDA(cudaEventRecord(cs->done, ctx->comm_stream));
+        WGB_CUDA(cudaStreamWaitEvent(pass->stream, cs->done, 0));
+    }
+    return WGB_OK;
+}
+
+}  // extern "C"

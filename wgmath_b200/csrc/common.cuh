@@ -131,6 +131,8 @@ wgb_status check_view(const wgb_buffer *b, const wgb_view_shape &s, size_t elem_
 // Grow-only device workspace slot; contents are undefined after a grow.
 wgb_status workspace_reserve(wgb_ctx *ctx, int slot, size_t bytes, void **out);
 wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters);
+// SMs the persistent GEMM leaves free for the NCCL CTAs of an in-flight exchange (0 without a communicator).
+int comm_sm_margin(const wgb_ctx *ctx);
 
 // ---- kernels launched from the dispatch layer (one per .cu) --------------------------------
 wgb_status launch_op_assign(wgb_pass *p, int op, float *a, const float *b, uint64_t n);

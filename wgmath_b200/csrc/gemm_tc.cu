@@ -1,6 +1,698 @@
+// gemm_tc.cu — the tensor-core GEMM: tcgen05.mma with TMEM accumulators, TMA-staged operand tiles,
+// warp-specialised producer / MMA-issuer / epilogue, persistent tile loop.  sm_100a only.
+//
+// Replaces the four WGSL GEMM kernels of /root/reference/crates/wgebra/src/linalg/gemm.wgsl (:29-199),
+// which are global-memory bound with zero operand reuse.  Same contract as
+// gemm.rs:65-127: out = m1 * m2 or tr(m1) * m2, column-major views, overwrite, batched over size[2].
+//
+// Data layout
+//   column-major m1 [M x K] (non-tr)  -> UMMA operand A, "MN-major": M is the contiguous axis.
+//   column-major m1 [K x M] (tr)      -> UMMA operand A, K-major.  No data transpose: only the major bit.
+//   column-major m2 [K x N]           -> UMMA operand B, K-major (K contiguous).
+//   out [M x N] column-major          <- accumulator rows = TMEM lanes, so a warp's 32 lanes store 32
+//                                        consecutive elements of one output column (coalesced).
+//   Shared-memory tiles use the 128-byte swizzle written by TMA and read by the UMMA descriptors:
+//     K-major tile  : [rows][128 B of K]            SBO = 1024 B, K advance = 32 B per MMA
+//     MN-major tile : [M atom][BLOCK_K][128 B of M] LBO = BLOCK_K*128 B, SBO = 1024 B, K advance = UMMA_K*128 B
+//   BLOCK_K = 128 B of K per stage (64 bf16 / 32 tf32), BLOCK_M = 128 per CTA, BLOCK_N = 128 or 256.
+//
+// Kernel shape (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (tcgen05.ld -> registers -> global).  Three pipelines: smem full/empty
+// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator stages so the epilogue of tile i
+// overlaps the main loop of tile i+1), and the persistent tile loop (grid = #SMs, supertile rasterisation
+// so concurrently running tiles share operand panels in L2).
+// CG = 2 pairs two CTAs (cta_group::2): UMMA M = 256 across the pair, each CTA loads half of the B tile.
+//
+// f32 operands: kind::tf32.  PASSES = 3 is the error-compensated 3xTF32 scheme (hi/lo operand split made
+// by split_tf32_kernel; three MMAs per k-step: lo*hi + hi*lo + hi*hi, f32 accumulation in TMEM), which is
+// what meets the 1e-5 parity bound; PASSES = 1 is plain TF32 (informational fast mode).
+//
+// Roofline: tensor pipe.  Algorithmic work = 2*M*N*K flop per launch (x3 MMA issue for 3xTF32).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace wgb {
-void tmap_cache_destroy(wgb_ctx *) {}
-bool gemm_tc_eligible(const GemmProblem &) { return false; }
-wgb_status launch_gemm_tc(wgb_pass *, const GemmProblem &, wgb_f32_mode, int *) { WGB_FAIL(WGB_ERR_UNSUPPORTED, "tc stub"); }
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
 }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+// Bounded wait: a broken pipeline traps (sticky CUDA error reported to the caller) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 8000000000ll) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// cta_group::2 form: data lands in this CTA's smem, complete_tx is signalled on the *leader* CTA's barrier
+// (peer bit of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+        "[%2];" ::"r"(dst),
+        "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    if (CG == 1) asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_relinquish() {
+    if (CG == 1) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    else asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]
+template <int KIND, int CG>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == 0) {
+        if (CG == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                         : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                         : "memory");
+    } else {
+        if (CG == 1)
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                         : "memory");
+        else
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+                         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                         : "memory");
+    }
+}
+// Arrive on an mbarrier when all previously issued MMAs have completed (implies fence::before_thread_sync).
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    if (CG == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                     "h"((uint16_t)3)
+                     : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// descriptors (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, 16-byte units
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading-dimension byte offset
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride-dimension byte offset
+    d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+    return d;
+}
+
+constexpr uint32_t make_idesc(int kind, bool a_mn_major, int m, int n) {
+    const uint32_t fmt = kind == 0 ? 1u /* BF16 */ : 2u /* TF32 */;
+    return (1u << 4)                      // accumulator format F32
+           | (fmt << 7) | (fmt << 10)     // A / B element format
+           | ((a_mn_major ? 1u : 0u) << 15)  // A major-ness (0 = K-major)
+           | (0u << 16)                   // B is always K-major here
+           | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcArgs {
+    void *c;
+    uint64_t ldc, sc;
+    uint32_t M, N, K, nmats;
+    uint32_t tiles_m, tiles_n, num_kb, total_tiles;
+};
+
+constexpr int kBlockM = 128;        // rows per CTA
+constexpr int kRowBytes = 128;      // bytes of K (K-major) or of M (MN-major) per smem row = swizzle span
+constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KiB, both major-nesses
+constexpr int kNumThreads = 256;
+constexpr int kSuperM = 8;          // m-tiles per rasterisation group
+constexpr int kSmemLimit = 227 * 1024;
+
+template <int BN, int PASSES, int CG>
+struct TcCfg {
+    static constexpr int SETS = PASSES == 3 ? 2 : 1;                  // hi / lo operand copies
+    static constexpr int B_ROWS = BN / CG;                            // rows of the B tile held by one CTA
+    static constexpr int B_TILE_BYTES = B_ROWS * kRowBytes;
+    static constexpr int STAGE_BYTES = SETS * (kATileBytes + B_TILE_BYTES);
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int STAGES_RAW = (kSmemLimit - BAR_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;                          // two accumulator stages (256 or 512: powers of 2)
+    static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+// Tile index -> (batch, m-tile, n-tile); groups of kSuperM m-tiles sweep N together.
+__device__ __forceinline__ void tile_coords(uint32_t t, const TcArgs &a, uint32_t &bt, uint32_t &mt, uint32_t &nt) {
+    const uint32_t per_batch = a.tiles_m * a.tiles_n;
+    bt = t / per_batch;
+    const uint32_t r = t - bt * per_batch;
+    const uint32_t group_span = kSuperM * a.tiles_n;
+    const uint32_t g = r / group_span;
+    const uint32_t first_m = g * kSuperM;
+    const uint32_t gsz = min((uint32_t)kSuperM, a.tiles_m - first_m);
+    const uint32_t rr = r - g * group_span;
+    mt = first_m + rr % gsz;
+    nt = rr / gsz;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_out(T *p, float v);
+template <>
+__device__ __forceinline__ void store_out<float>(float *p, float v) { *p = v; }
+template <>
+__device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+// KIND: 0 = bf16 (kind::f16), 1 = tf32.  A_MN: operand A is MN-major (the non-transposed product).
+template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcArgs args) {
+    using Cfg = TcCfg<BN, PASSES, CG>;
+    constexpr int ES = KIND == 0 ? 2 : 4;                 // operand element size
+    constexpr int BLOCK_K = kRowBytes / ES;               // 64 bf16 / 32 tf32
+    constexpr int UMMA_K = 32 / ES;                       // 16 bf16 / 8 tf32
+    constexpr int K_STEPS = BLOCK_K / UMMA_K;             // 4
+    constexpr int A_ATOMS = A_MN ? (kBlockM * ES) / kRowBytes : 1;   // MN-major: 128-byte atoms along M (2 bf16 / 4 tf32)
+    constexpr int A_ATOM_ELEMS = kRowBytes / ES;
+    constexpr int A_ATOM_BYTES = BLOCK_K * kRowBytes;     // one atom column: BLOCK_K rows of 128 B
+    constexpr uint32_t IDESC = make_idesc(KIND, A_MN, kBlockM * CG, BN);
+    constexpr int STAGES = Cfg::STAGES;
+
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128-byte swizzle
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t *full_bar = bars;                    // [STAGES]
+    uint64_t *empty_bar = bars + STAGES;          // [STAGES]
+    uint64_t *tmem_full_bar = bars + 2 * STAGES;  // [2]
+    uint64_t *tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    const uint32_t cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        if (PASSES == 3) {
+            prefetch_tmap(&tmAlo);
+            prefetch_tmap(&tmBlo);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(full_bar + s), 1);    // one arrive.expect_tx (leader producer) + TMA bytes
+            mbar_init(smem_u32(empty_bar + s), 1);   // one tcgen05.commit
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(tmem_full_bar + s), 1);         // one tcgen05.commit
+            mbar_init(smem_u32(tmem_empty_bar + s), 4 * CG);   // one arrive per epilogue warp (of both CTAs)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc<CG>(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+        tmem_relinquish<CG>();
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0 && lane == 0) {
+        // ===================================== TMA producer =====================================
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+            uint32_t bt, mt, nt;
+            tile_coords(t, args, bt, mt, nt);
+            const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
+            const int n0 = (int)(nt * BN + cta_rank * Cfg::B_ROWS);
+            for (uint32_t kb = 0; kb < args.num_kb; ++kb) {
+                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                const uint32_t fb = smem_u32(full_bar + stage);
+                if (leader) mbar_arrive_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES * CG);
+                uint8_t *sbase = smem + stage * Cfg::STAGE_BYTES;
+                const int k0 = (int)(kb * BLOCK_K);
+#pragma unroll
+                for (int set = 0; set < Cfg::SETS; ++set) {
+                    const CUtensorMap *ta = set == 0 ? &tmA : &tmAlo;
+                    const CUtensorMap *tb = set == 0 ? &tmB : &tmBlo;
+                    const uint32_t sa = smem_u32(sbase + set * kATileBytes);
+                    const uint32_t sb = smem_u32(sbase + Cfg::SETS * kATileBytes + set * Cfg::B_TILE_BYTES);
+                    if (A_MN) {
+#pragma unroll
+                        for (int at = 0; at < A_ATOMS; ++at) {
+                            if (CG == 2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                            else tma_load_3d(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                        }
+                    } else {
+                        if (CG == 2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
+                        else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
+                    }
+                    if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
+                    else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===================================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+                mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (uint32_t kb = 0; kb < args.num_kb; ++kb) {
+                    mbar_wait(smem_u32(full_bar + stage), phase);
+                    tc_fence_after();
+                    const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t sa_hi = sbase, sa_lo = sbase + kATileBytes;
+                    const uint32_t sb_hi = sbase + Cfg::SETS * kATileBytes, sb_lo = sb_hi + Cfg::B_TILE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < K_STEPS; ++j) {
+                        // K advance inside the swizzled tile: 32 B (K-major) or UMMA_K rows of 128 B (MN-major)
+                        const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
+                        const uint32_t b_off = j * 32;
+                        const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
+                        const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, sbo);
+                        const uint64_t db_hi = make_smem_desc(sb_hi + b_off, 16, sbo);
+                        const uint32_t first = (kb | (uint32_t)j) == 0 ? 0u : 1u;
+                        if (PASSES == 3) {
+                            const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, sbo);
+                            const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
+                            umma<KIND, CG>(d_tmem, da_lo, db_hi, IDESC, first);   // small terms first
+                            umma<KIND, CG>(d_tmem, da_hi, db_lo, IDESC, 1u);
+                            umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, 1u);
+                        } else {
+                            umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, first);
+                        }
+                    }
+                    umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
+                    if (kb + 1 == args.num_kb) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================================== epilogue: TMEM -> registers -> global ==============
+        const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
+        TOut *cbase = reinterpret_cast<TOut *>(args.c);
+        uint32_t acc = 0, acc_phase = 0;
+        for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+            uint32_t bt, mt, nt;
+            tile_coords(t, args, bt, mt, nt);
+            const uint32_t row = mt * (kBlockM * CG) + cta_rank * kBlockM + q * 32 + lane;
+            const uint32_t n0 = nt * BN;
+            mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
+            TOut *crow = cbase + (uint64_t)bt * args.sc + row;
+            const bool row_ok = row < args.M;
+            uint32_t v[2][32];
+            tmem_ld32(taddr, v[0]);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                tmem_ld_wait();
+                if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                else {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(smem_u32(tmem_empty_bar + acc), 0);
+                        else mbar_arrive(smem_u32(tmem_empty_bar + acc));
+                    }
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const uint32_t col = n0 + c * 32 + i;
+                        if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                    }
+                }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3xTF32 operand split: x = hi + lo, hi = tf32(x) (round-to-nearest), lo = x - hi (exact in f32; the tensor
+// core truncates lo to its leading 11 bits, leaving a relative error of ~2^-22 per operand).
+// Reads any strided view, writes two dense column-major copies with leading dimension ld_out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, uint32_t rows, uint32_t cols,
+                                                         uint32_t mats, uint64_t ld, uint64_t smat, float *__restrict__ hi,
+                                                         float *__restrict__ lo, uint64_t ld_out, uint64_t smat_out) {
+    const uint64_t total = (uint64_t)ld_out * cols * mats;   // padded rows are written as zeros
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = e % ld_out;
+        const uint64_t jt = e / ld_out;
+        const uint64_t j = jt % cols, t = jt / cols;
+        float x = 0.f;
+        if (i < rows) x = __ldg(src + t * smat + j * ld + i);
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+        const float hf = __uint_as_float(h);
+        const uint64_t o = t * smat_out + j * ld_out + i;
+        hi[o] = hf;
+        lo[o] = x - hf;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct TmapKey {
+    const void *ptr;
+    uint64_t d0, d1, d2, s1, s2;
+    uint32_t b0, b1, es;
+    bool operator==(const TmapKey &o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && s1 == o.s1 && s2 == o.s2 && b0 == o.b0 && b1 == o.b1 &&
+               es == o.es;
+    }
+};
+struct TmapKeyHash {
+    size_t operator()(const TmapKey &k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+        for (uint64_t v : {k.d0, k.d1, k.d2, k.s1, k.s2, (uint64_t)k.b0 << 32 | k.b1, (uint64_t)k.es})
+            h = (h ^ v) * 0xBF58476D1CE4E5B9ull + 0x94D049BB133111EBull;
+        return (size_t)h;
+    }
+};
+using TmapCache = std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>;
+
+// 3-D map: dim0 contiguous (d0 elements), dim1 stride s1 elements, dim2 (batch) stride s2 elements.
+wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                    uint32_t b0, uint32_t b1, CUtensorMap *out) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if (d2 <= 1) {   // single matrix: the batch stride is never used, but must still be a legal (16-byte multiple) stride
+        const uint64_t q = 16 / es;
+        d2 = 1;
+        s2 = d0 > s1 * d1 ? d0 : s1 * d1;
+        s2 = (s2 + q - 1) / q * q;
+    }
+    TmapKey key{ptr, d0, d1, d2, s1, s2, b0, b1, es};
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
+    TmapCache &cache = *static_cast<TmapCache *>(ctx->tmap_cache);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return WGB_OK;
+    }
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1 * es, s2 * es};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu, strides %llu / %llu B, box %u x %u", (int)r,
+                 (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)(s1 * es),
+                 (unsigned long long)(s2 * es), b0, b1);
+    if (cache.size() > 4096) cache.clear();
+    cache.emplace(key, *out);
+    return WGB_OK;
+}
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
+wgb_status launch_cfg(wgb_pass *p, const CUtensorMap &ta, const CUtensorMap &talo, const CUtensorMap &tb, const CUtensorMap &tblo,
+                      TcArgs args) {
+    using Cfg = TcCfg<BN, PASSES, CG>;
+    auto kern = gemm_tc_kernel<KIND, A_MN, BN, PASSES, TOut, CG>;
+    static bool attr_set[64] = {};   // per instantiation, per device
+    const int dev = p->ctx->device & 63;
+    if (!attr_set[dev]) {
+        WGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_set[dev] = true;
+    }
+    uint32_t sms = (uint32_t)p->ctx->prop.multiProcessorCount;
+    const uint32_t margin = (uint32_t)comm_sm_margin(p->ctx);
+    if (margin < sms / 2) sms -= margin;
+    uint32_t clusters = sms / CG;
+    if (clusters > args.total_tiles) clusters = args.total_tiles;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(kNumThreads);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = p->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, talo, tb, tblo, args));
+    count_launch(p->ctx);
+    return WGB_OK;
+}
+
+template <int KIND, bool A_MN, int PASSES, typename TOut>
+wgb_status launch_sel(wgb_pass *p, int bn, int cg, const CUtensorMap &ta, const CUtensorMap &talo, const CUtensorMap &tb,
+                      const CUtensorMap &tblo, const TcArgs &args) {
+    if (cg == 2) {
+        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+    }
+    if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+    return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+}
+
+}  // namespace
+
+void tmap_cache_destroy(wgb_ctx *ctx) {
+    if (ctx->tmap_cache) delete static_cast<TmapCache *>(ctx->tmap_cache);
+    ctx->tmap_cache = nullptr;
+}
+
+static bool aligned_operand(const void *base, uint64_t off, uint64_t ld, uint64_t smat, uint32_t nmats, size_t es) {
+    const uint64_t q = 16 / es;
+    return (((uintptr_t)base + off * es) & 15u) == 0 && ld % q == 0 && (nmats <= 1 || smat % q == 0);
+}
+
+bool gemm_tc_eligible(const GemmProblem &g) {
+    if (g.M == 0 || g.N == 0 || g.K == 0) return false;
+    if (g.in_dtype == WGB_F32) return g.out_dtype == WGB_F32;   // operands are re-materialised dense by the split (any view is fine)
+    const size_t es = 2;
+    return aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, es) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, es);
+}
+
+// Picks BLOCK_N by wave quantisation: time ~ ceil(tiles / clusters) * BLOCK_N (a BLOCK_N = 128 tile moves 1.5x the
+// operand bytes per flop, charged as a small penalty).
+static int pick_bn(uint32_t M, uint32_t N, uint32_t nmats, int cg, uint32_t sms) {
+    const int forced = env_int("WGB_TC_BN", 0);
+    if (forced == 128 || forced == 256) return forced;
+    const uint64_t tm = (M + 128 * cg - 1) / (128 * cg);
+    const uint64_t clusters = sms / cg;
+    auto cost = [&](int bn) {
+        const uint64_t tiles = tm * ((N + bn - 1) / bn) * nmats;
+        const uint64_t waves = (tiles + clusters - 1) / clusters;
+        return (double)waves * bn * (bn == 128 ? 1.06 : 1.0);
+    };
+    return cost(128) < cost(256) ? 128 : 256;
+}
+
+wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, int *path_out) {
+    wgb_ctx *ctx = p->ctx;
+    const bool f32 = g.in_dtype == WGB_F32;
+    int passes = 1;
+    if (f32) passes = (mode == WGB_F32_TF32) ? 1 : 3;
+    if (f32 && passes == 1 &&
+        !(aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)))
+    {   // single-pass TF32 reads the caller's views directly: needs TMA alignment
+        *path_out = 1;
+        return launch_gemm_simt(p, g);
+    }
+    const size_t es = f32 ? 4 : 2;
+    const int cg = env_int("WGB_TC_CG", 1) == 2 ? 2 : 1;
+    const int bn = pick_bn(g.M, g.N, g.nmats, cg, (uint32_t)ctx->prop.multiProcessorCount);
+    const uint32_t block_k = 128 / (uint32_t)es;
+
+    const uint32_t a_rows = g.tr ? g.K : g.M, a_cols = g.tr ? g.M : g.K;
+    const char *a_ptr = (const char *)g.a + g.a_off * es, *b_ptr = (const char *)g.b + g.b_off * es;
+    const char *alo_ptr = a_ptr, *blo_ptr = b_ptr;
+    uint64_t lda = g.lda, ldb = g.ldb, sa = g.sa, sb = g.sb;
+    if (passes == 3) {
+        // dense hi / lo copies in the context workspace (slots 0, 1)
+        const uint64_t lda_d = ((uint64_t)a_rows + 3) & ~3ull, ldb_d = ((uint64_t)g.K + 3) & ~3ull;
+        const uint64_t sa_d = lda_d * a_cols, sb_d = ldb_d * g.N;
+        const size_t a_bytes = sa_d * g.nmats * 4, b_bytes = sb_d * g.nmats * 4;
+        void *wa = nullptr, *wb = nullptr;
+        WGB_TRY(workspace_reserve(ctx, 0, 2 * a_bytes, &wa));
+        WGB_TRY(workspace_reserve(ctx, 1, 2 * b_bytes, &wb));
+        float *ahi = (float *)wa, *alo = (float *)((char *)wa + a_bytes);
+        float *bhi = (float *)wb, *blo = (float *)((char *)wb + b_bytes);
+        const int sgrid = ctx->prop.multiProcessorCount * 8;
+        split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)a_ptr, a_rows, a_cols, g.nmats, g.lda, g.sa, ahi, alo, lda_d, sa_d);
+        split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)b_ptr, g.K, g.N, g.nmats, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
+        WGB_CUDA(cudaGetLastError());
+        count_launch(ctx, 2);
+        a_ptr = (const char *)ahi; alo_ptr = (const char *)alo;
+        b_ptr = (const char *)bhi; blo_ptr = (const char *)blo;
+        lda = lda_d; ldb = ldb_d; sa = sa_d; sb = sb_d;
+    }
+
+    CUtensorMap ta, talo, tb, tblo;
+    const uint32_t a_box0 = g.tr ? block_k : (uint32_t)(128 / es);          // K-major: 128 B of K; MN-major: one 128 B atom of M
+    const uint32_t a_box1 = g.tr ? 128u : block_k;
+    WGB_TRY(get_tmap(ctx, a_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &ta));
+    WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tb));
+    if (passes == 3) {
+        WGB_TRY(get_tmap(ctx, alo_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &talo));
+        WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tblo));
+    } else {
+        talo = ta;
+        tblo = tb;
+    }
+
+    TcArgs args{};
+    args.c = (char *)g.c + g.c_off * dtype_size(g.out_dtype);
+    args.ldc = g.ldc; args.sc = g.sc;
+    args.M = g.M; args.N = g.N; args.K = g.K; args.nmats = g.nmats;
+    args.tiles_m = (g.M + 128 * cg - 1) / (128 * cg);
+    args.tiles_n = (g.N + bn - 1) / bn;
+    args.num_kb = (g.K + block_k - 1) / block_k;
+    const uint64_t total = (uint64_t)args.tiles_m * args.tiles_n * g.nmats;
+    if (total > 0xFFFFFFFFull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: too many output tiles");
+    args.total_tiles = (uint32_t)total;
+
+    wgb_status st;
+    if (!f32) {
+        if (g.out_dtype == WGB_F32)
+            st = g.tr ? launch_sel<0, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<0, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        else
+            st = g.tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args)
+                      : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args);
+        *path_out = 2;
+    } else if (passes == 1) {
+        st = g.tr ? launch_sel<1, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        *path_out = 3;
+    } else {
+        st = g.tr ? launch_sel<1, false, 3, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 3, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        *path_out = 4;
+    }
+    return st;
+}
+
+}  // namespace wgb

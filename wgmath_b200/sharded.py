@@ -1,0 +1,131 @@
+"""Row-sharded GEMM across the GPUs of one box (BASELINE configs[4]).
+
+One process per GPU.  Rank p owns rows [p*M/P, (p+1)*M/P) of m1 and of the product; m2 is
+replicated.  Each rank computes its block into a contiguous column-major [M/P x N] panel and the
+panels are exchanged over NVLink (chunked by column panel, overlapped with the remaining tiles);
+the gathered result is a cube view size=[M/P, N, P], stride=M/P, stride_mat=(M/P)*N.
+
+`torch.distributed` is used only as plumbing (rendezvous, distributing the communicator id,
+barriers); the data path is wgb_gemm_row_sharded in libwgebra_b200.so."""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Tuple
+
+import numpy as np
+
+from ._lib import BF16, COMM_ID_BYTES, F32, check, lib
+from .linalg import F32Mode, GemmVariant
+from .shapes import ViewShape
+from .tensor import GpuTensor, GpuTensorView, as_view
+
+_DTYPE_CODE = {"f32": F32, "bf16": BF16}
+
+
+def row_partition(M: int, P: int) -> List[Tuple[int, int]]:
+    """(first_row, nrows) per rank.  Equal blocks: the gathered panels must all have the same size."""
+    if P < 1 or M % P != 0:
+        raise ValueError(f"row-sharding needs M ({M}) divisible by the number of ranks ({P})")
+    b = M // P
+    return [(p * b, b) for p in range(P)]
+
+
+def column_chunks(N: int, n_chunks: int, P: int) -> List[Tuple[int, int]]:
+    """(first_col, ncols) of each exchange chunk — same rule as wgb_gemm_row_sharded (comm.cu):
+    whole 256-column tiles, default 8 chunks when there is an exchange, 1 otherwise."""
+    if N == 0:
+        return []
+    nch = n_chunks if n_chunks > 0 else (8 if P > 1 else 1)
+    width = -(-N // nch)
+    width = (width + 255) & ~255
+    return [(n0, min(width, N - n0)) for n0 in range(0, N, width)]
+
+
+def gathered_view(out: GpuTensor, m_local: int, N: int, P: int) -> GpuTensorView:
+    """The gathered result as the reference's GpuCubeView (tensor.rs:465-481): matrix p = rows of rank p."""
+    return GpuTensorView(ViewShape((m_local, N, P), m_local, m_local * N, 0), out.buffer(), out.dtype, 3)
+
+
+def panels_to_matrix(flat: np.ndarray, m_local: int, N: int, P: int) -> np.ndarray:
+    """Host-side: [P][N][m_local] gathered panels -> the full (P*m_local) x N matrix."""
+    return np.concatenate([flat[p * m_local * N:(p + 1) * m_local * N].reshape(N, m_local).T for p in range(P)], axis=0)
+
+
+def init_comm(device, dist=None, rank: int = 0, world: int = 1) -> None:
+    """Create the NCCL communicator for this context: rank 0 makes the id, everyone gets it through
+    torch.distributed (any backend), then wgb_comm_init_rank."""
+    idbuf = (ctypes.c_char * COMM_ID_BYTES)()
+    if rank == 0:
+        check(lib().wgb_comm_get_unique_id(idbuf))
+    payload = [bytes(idbuf)]
+    if dist is not None and world > 1:
+        dist.broadcast_object_list(payload, src=0)
+    idbuf = (ctypes.c_char * COMM_ID_BYTES).from_buffer_copy(payload[0])
+    check(lib().wgb_comm_init_rank(device._h, world, rank, idbuf))
+
+
+class RowShardedGemm:
+    """out_gathered[p] = (m1 * m2)[rows of rank p]  for every p, on every rank."""
+
+    def __init__(self, device):
+        self._device = device
+
+    def dispatch(self, device, shapes, pass_, out_gathered: GpuTensor, m1_local, m2, variant=GemmVariant.Gemm,
+                 f32_mode=F32Mode.Auto, n_chunks: int = 0) -> None:
+        m1, b = as_view(m1_local, 3), as_view(m2, 3)
+        s1, s2 = shapes.get(device, m1.shape()).to_c(), shapes.get(device, b.shape()).to_c()
+        check(lib().wgb_gemm_row_sharded(pass_._h, int(variant), out_gathered.buffer()._h, m1.buffer()._h, ctypes.byref(s1),
+                                         b.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out_gathered.dtype],
+                                         int(f32_mode), n_chunks))
+
+
+def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
+    """bench.py's N > 1 leg: bf16 (4096*P)^3, row-sharded, all-gather of C; returns the JSON fields."""
+    dev = gpu.device()
+    n = 4096 * ngpu
+    m_local = n // ngpu
+    ST = w.BufferUsages.STORAGE | w.BufferUsages.COPY_SRC | w.BufferUsages.COPY_DST
+    init_comm(dev, dist, rank, ngpu)
+    a = w.TensorBuilder.matrix(m_local, n, ST).build(dev, "bf16")       # my row block of A
+    b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")             # B replicated
+    c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
+    enc = dev.create_command_encoder()
+    with enc.compute_pass("init", None) as p:
+        w.fill_uniform(dev, p, a, O.SEED_BASE + 1, row0=rank * m_local)  # element (i, j) independent of the sharding
+        w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
+    dev.poll_wait()
+    op = RowShardedGemm(dev)
+    sec, launches = timed(lambda p, i: op.dispatch(dev, shapes, p, c, a, b), args.steps, args.warmup)
+    flops = 2.0 * n * n * n
+    value = flops * args.steps / sec / 1e12
+    ms_step = sec * 1e3 / args.steps
+    long_run = sec > 1.0
+    peak = (peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]) * ngpu
+    comm_bytes = (ngpu - 1) * m_local * n * 2
+    roof = {"bound": "tensor", "kernel": "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)",
+            "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
+            "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
+            "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
+            "nvlink_floor_ms": comm_bytes / 770e9 * 1e3}
+    # e2e: host -> device of this rank's A block and of B, sharded GEMM + gather, device -> host of the gathered C
+    L = lib()
+    abytes, bbytes, cbytes = m_local * n * 2, n * n * 2, n * n * 2
+    ha, hb, hc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    for h, nb in ((ha, abytes), (hb, bbytes), (hc, cbytes)):
+        check(L.wgb_host_alloc(nb, ctypes.byref(h)))
+    check(L.wgb_buffer_read(dev._h, a.buffer()._h, 0, ha, abytes))
+    check(L.wgb_buffer_read(dev._h, b.buffer()._h, 0, hb, bbytes))
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_step(p, i):
+        check(L.wgb_buffer_write(dev._h, a.buffer()._h, 0, ha, abytes))
+        check(L.wgb_buffer_write(dev._h, b.buffer()._h, 0, hb, bbytes))
+        op.dispatch(dev, shapes, p, c, a, b)
+        check(L.wgb_buffer_read(dev._h, c.buffer()._h, 0, hc, cbytes))
+    e2e_sec, _ = timed(e2e_step, e2e_steps, 1)
+    for h in (ha, hb, hc):
+        L.wgb_host_free(h)
+    e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (abytes + bbytes) * ngpu,
+           "d2h_bytes_per_step": cbytes * ngpu, "steps": e2e_steps}
+    lib().wgb_comm_destroy(dev._h)
+    return value, ms_step, launches, roof, e2e, "bf16"
