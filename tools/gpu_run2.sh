@@ -1,12 +1,14 @@
 #!/bin/bash
 # GPU call 2: bring-up of the tcgen05 GEMM + profiles of the level-1 kernels.
 mkdir -p gpurun_out
-echo "=== quick probe (all configs) ==="
-timeout 300 python tools/tc_probe.py quick > gpurun_out/probe_quick.log 2>&1; echo "rc=$?"; grep -c "^OK" gpurun_out/probe_quick.log; grep -E "^FAIL|^EXC|QUICK" gpurun_out/probe_quick.log | head -40
-echo "=== acc ==="
-timeout 200 python tools/tc_probe.py acc > gpurun_out/probe_acc.log 2>&1; cat gpurun_out/probe_acc.log | tail -20
-echo "=== perf ==="
-timeout 300 python tools/tc_probe.py perf > gpurun_out/probe_perf.log 2>&1; cat gpurun_out/probe_perf.log | tail -40
+for cg in 1 2; do
+echo "=== quick probe cg=$cg ==="
+timeout 200 python tools/tc_probe.py quick $cg > gpurun_out/probe_quick$cg.log 2>&1; echo "rc=$?"; grep -c "^OK" gpurun_out/probe_quick$cg.log; grep -E "^FAIL|^EXC|QUICK" gpurun_out/probe_quick$cg.log | head -30
+echo "=== perf cg=$cg ==="
+timeout 200 python tools/tc_probe.py perf $cg > gpurun_out/probe_perf$cg.log 2>&1; tail -20 gpurun_out/probe_perf$cg.log
+echo "=== acc cg=$cg ==="
+timeout 200 python tools/tc_probe.py acc $cg > gpurun_out/probe_acc$cg.log 2>&1; tail -10 gpurun_out/probe_acc$cg.log
+done
 echo "=== pytest gpu (CG=1) ==="
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -25
 echo "=== ncu level-1 ==="

@@ -75,9 +75,9 @@ def set_cfg(cg, bn):
     os.environ["WGB_TC_BN"] = str(bn)
 
 
-def quick():
+def quick(cgs=(1, 2)):
     allok = True
-    for cg in (1, 2):
+    for cg in cgs:
         for bn in (128, 256):
             set_cfg(cg, bn)
             for dtype, mode, tol, name in (("bf16", w.F32Mode.Auto, 1e-4, "bf16"), ("f32", w.F32Mode.Tf32, 3e-3, "tf32"),
@@ -122,8 +122,8 @@ def timed_gemm(n, dtype, mode, steps=10, out_dtype=None, tr=False):
     return ms.value / steps, path
 
 
-def perf():
-    for cg in (1, 2):
+def perf(cgs=(1, 2)):
+    for cg in cgs:
         for bn in (128, 256):
             set_cfg(cg, bn)
             for n in (4096, 8192):
@@ -135,10 +135,10 @@ def perf():
                 print(f"PERF cg{cg} bn{bn} {name} n=4096: {ms:.4f} ms  {2 * 4096 ** 3 / ms / 1e9:.1f} TFLOP/s path={path}", flush=True)
 
 
-def acc():
+def acc(cgs=(1, 2)):
     """Does TMEM accumulation round to nearest?  Long-K 3xTF32 against float64."""
     os.environ.pop("WGB_TC_BN", None)
-    for cg in (1, 2):
+    for cg in cgs:
         os.environ["WGB_TC_CG"] = str(cg)
         for K in (1024, 4096, 16384, 32768):
             got, ref, path = run(256, 256, K, False, "f32", w.F32Mode.X3Tf32)
@@ -152,11 +152,12 @@ def acc():
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "quick"
     t0 = time.time()
+    cgs = (int(sys.argv[2]),) if len(sys.argv) > 2 else (1, 2)
     if what == "quick":
-        ok = quick()
+        ok = quick(cgs)
         print("QUICK", "ALL OK" if ok else "FAILURES", f"{time.time() - t0:.1f}s")
         sys.exit(0 if ok else 1)
     elif what == "perf":
-        perf()
+        perf(cgs)
     elif what == "acc":
-        acc()
+        acc(cgs)
