@@ -1,0 +1,163 @@
+// Replays the reference's four unit tests (gemm.rs:144-202, gemv.rs:153-197, op_assign.rs:109-157,
+// reduce.rs:139-179) through the C++ host mirror (wgmath_b200/host/wgebra_b200.hpp -> C ABI -> CUDA) and
+// checks every result against the CPU oracle (oracle/wgsl_oracle.c) on the same seeded inputs.
+// Exit code 0 = all within tolerance (1e-5 relative; op_assign bit-exact).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../wgmath_b200/host/wgebra_b200.hpp"
+
+extern "C" {
+typedef struct { uint32_t nrows, ncols, nmats, stride, stride_mat, offset; } orc_shape;
+int orc_gemm(int variant, float *out, const orc_shape *so, const float *m1, const orc_shape *s1, const float *m2, const orc_shape *s2);
+int orc_gemv(int variant, float *out, const orc_shape *so, const float *m, const orc_shape *sm, const float *v, const orc_shape *sv, int *ran);
+int orc_op_assign(int op, float *a, const orc_shape *sa, const float *b, const orc_shape *sb);
+int orc_reduce(int op, const float *x, const orc_shape *s, float *result);
+}
+
+static uint64_t splitmix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+static std::vector<float> uniform(uint64_t seed, uint32_t rows, uint32_t cols = 1) {   // == oracle.uniform / wgb_fill_uniform
+    std::vector<float> v((size_t)rows * cols);
+    for (uint32_t j = 0; j < cols; ++j)
+        for (uint32_t i = 0; i < rows; ++i)
+            v[(size_t)j * rows + i] = (float)(splitmix64((seed * 0xD1342543DE82EF95ull) ^ (((uint64_t)j << 32) | i)) >> 40) * 5.9604644775390625e-8f;
+    return v;
+}
+static orc_shape oshape(uint32_t r, uint32_t c = 1) { return orc_shape{r, c, 1, r, r * c, 0}; }
+static double rel_err(const std::vector<float> &got, const std::vector<float> &ref) {
+    double w = 0;
+    for (size_t i = 0; i < ref.size(); ++i) w = std::fmax(w, std::fabs((double)got[i] - ref[i]) / std::fmax(std::fabs((double)ref[i]), 1e-30));
+    return w;
+}
+
+int main() {
+    using namespace wgb;
+    const uint64_t SEED = 0x5EED0000;
+    int failures = 0;
+    try {
+        GpuInstance gpu(0);
+        ViewShapeBuffers shapes;
+        const uint32_t usage = STORAGE | COPY_SRC | COPY_DST;
+        {   // gpu_gemm
+            const uint32_t n = 256;
+            auto m1c = uniform(SEED + 1, n, n), m2c = uniform(SEED + 2, n, n);
+            auto gemm = Gemm::from_device(gpu.device());
+            auto m1 = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), m1c);
+            auto m2 = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), m2c);
+            auto result = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), std::vector<float>(n * n, 0.f));
+            auto staging = Tensors::matrix(n, n, MAP_READ | COPY_DST).build<float>(gpu.device());
+            for (int variant = 0; variant < 4; ++variant) {
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    gemm.dispatch_generic<float>(gpu.device(), shapes, pass, result.as_embedded_view<3>(), m1.as_embedded_view<3>(),
+                                                 m2.as_embedded_view<3>(), (GemmVariant)variant);
+                }
+                staging.copy_from(enc, result);
+                gpu.queue().submit(enc.finish());
+                auto got = staging.read(gpu.device());
+                std::vector<float> ref(n * n, 0.f);
+                orc_shape s = oshape(n, n);
+                orc_gemm(variant, ref.data(), &s, m1c.data(), &s, m2c.data(), &s);
+                const double e = rel_err(got, ref);
+                std::printf("gpu_gemm variant %d: rel err %.3e\n", variant, e);
+                failures += !(e < 1e-5);
+            }
+        }
+        {   // gpu_gemv
+            const uint32_t n = 1024;
+            auto mc = uniform(SEED + 1, n, n), vc = uniform(SEED + 3, n), oc = uniform(SEED + 4, n);
+            auto gemv = Gemv::from_device(gpu.device());
+            auto m = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), mc);
+            auto v = Tensors::vector(n, usage).build_init<float>(gpu.device(), vc);
+            auto result = Tensors::vector(n, usage).build_init<float>(gpu.device(), oc);
+            for (int variant = 0; variant < 4; ++variant) {
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    gemv.dispatch_generic<float>(gpu.device(), shapes, pass, result, m, v, (GemvVariant)variant);
+                }
+                gpu.queue().submit(enc.finish());
+                auto got = result.read(gpu.device());
+                std::vector<float> ref = oc;
+                orc_shape sm = oshape(n, n), sv = oshape(n);
+                int ran = -1;
+                orc_gemv(variant, ref.data(), &sv, mc.data(), &sm, vc.data(), &sv, &ran);
+                const double e = rel_err(got, ref);
+                std::printf("gpu_gemv variant %d: rel err %.3e\n", variant, e);
+                failures += !(e < 1e-5);
+            }
+        }
+        {   // gpu_op_assign
+            const uint32_t n = 1757;
+            std::vector<float> v0(n), v1(n);
+            for (uint32_t i = 0; i < n; ++i) { v0[i] = (float)i + 0.1f; v1[i] = (float)i * 10.0f + 0.1f; }
+            for (int op = 0; op < 5; ++op) {
+                auto a = Tensors::vector(n, usage).build_init<float>(gpu.device(), v0);
+                auto b = Tensors::vector(n, usage).build_init<float>(gpu.device(), v1);
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    OpAssign::make(gpu.device(), (OpAssignVariant)op).dispatch<float>(gpu.device(), shapes, pass, a, b);
+                }
+                gpu.queue().submit(enc.finish());
+                auto got = a.read(gpu.device());
+                std::vector<float> ref = v0;
+                orc_shape s = oshape(n);
+                orc_op_assign(op, ref.data(), &s, v1.data(), &s);
+                const bool same = std::memcmp(got.data(), ref.data(), n * sizeof(float)) == 0;
+                std::printf("gpu_op_assign op %d: %s\n", op, same ? "bit-exact" : "MISMATCH");
+                failures += !same;
+            }
+        }
+        {   // gpu_reduce
+            const uint32_t n = 345;
+            auto x = uniform(SEED + 3, n);
+            auto vec = Tensors::vector(n, usage).build_init<float>(gpu.device(), x);
+            auto res = Tensors::scalar(usage).build<float>(gpu.device());
+            for (int op = 0; op < 5; ++op) {
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    Reduce::make(gpu.device(), (ReduceOp)op).dispatch<float>(gpu.device(), shapes, pass, vec, res);
+                }
+                gpu.queue().submit(enc.finish());
+                const float got = res.read(gpu.device())[0];
+                float ref = 0.f;
+                orc_shape s = oshape(n);
+                orc_reduce(op, x.data(), &s, &ref);
+                const double e = std::fabs((double)got - ref) / std::fmax(std::fabs((double)ref), 1e-30);
+                std::printf("gpu_reduce op %d: got %.8g ref %.8g rel %.3e\n", op, got, ref, e);
+                failures += !(e < 1e-5);
+            }
+        }
+        {   // the reference's panic on mismatched dimensions (gemm.rs:91)
+            auto gemm = Gemm::from_device(gpu.device());
+            auto a = Tensors::matrix(8, 4, usage).build<float>(gpu.device());
+            auto b = Tensors::matrix(8, 8, usage).build<float>(gpu.device());
+            auto o = Tensors::matrix(8, 8, usage).build<float>(gpu.device());
+            bool threw = false;
+            auto enc = gpu.device().create_command_encoder();
+            try {
+                auto pass = enc.compute_pass("test");
+                gemm.dispatch<float>(gpu.device(), shapes, pass, o, a, b);
+            } catch (const DimensionMismatch &e) {
+                threw = std::strstr(e.what(), "Gemm: dimension mismatch") != nullptr;
+            }
+            std::printf("dimension mismatch -> %s\n", threw ? "DimensionMismatch" : "NOT RAISED");
+            failures += !threw;
+        }
+    } catch (const wgb::Error &e) {
+        std::printf("wgb error %d: %s\n", e.status, e.what());
+        return 2;
+    }
+    std::printf("%s (%d failures)\n", failures ? "FAILED" : "ALL OK", failures);
+    return failures ? 1 : 0;
+}

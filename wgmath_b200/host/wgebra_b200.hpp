@@ -1,0 +1,338 @@
+// wgebra_b200.hpp — header-only C++17 host mirror of the reference's Rust surface over the C ABI
+// (include/wgb200.h).  Same names, argument order and error behaviour as
+//   /root/reference/crates/wgcore/src/{gpu,tensor,shapes,kernel,timestamps}.rs and
+//   /root/reference/crates/wgebra/src/linalg/{gemm,gemv,op_assign,reduce}.rs
+// (the reference is Rust; no Rust toolchain exists in this image, so the compiled-language host side is C++).
+//
+//   wgb::GpuInstance gpu;                                   // GpuInstance::new().await
+//   wgb::ViewShapeBuffers shapes;
+//   auto m1 = wgb::TensorBuilder::matrix(r, c, wgb::STORAGE).build_init<float>(gpu.device(), data);
+//   auto enc = gpu.device().create_command_encoder();
+//   { auto pass = enc.compute_pass("test");                 // drop(pass) at scope end
+//     wgb::Gemm::from_device(gpu.device()).dispatch(gpu.device(), shapes, pass, out, m1, m2); }
+//   gpu.queue().submit(enc.finish());
+//   std::vector<float> r = out.read(gpu.device());
+//
+// A dimension mismatch — a panic in the reference (assert_eq!, gemm.rs:91-95 etc.) — throws wgb::DimensionMismatch.
+#pragma once
+
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/wgb200.h"
+
+namespace wgb {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int s, const std::string &m) : std::runtime_error(m), status(s) {}
+};
+struct DimensionMismatch : Error {
+    using Error::Error;
+};
+inline void check(wgb_status s) {
+    if (s == WGB_OK) return;
+    const std::string msg = wgb_last_error_string();
+    if (s == WGB_ERR_DIM_MISMATCH) throw DimensionMismatch(s, msg);
+    throw Error(s, msg);
+}
+
+// wgpu::BufferUsages
+enum : uint32_t { MAP_READ = 1u << 0, MAP_WRITE = 1u << 1, COPY_SRC = 1u << 2, COPY_DST = 1u << 3, UNIFORM = 1u << 6, STORAGE = 1u << 7 };
+
+template <typename T> struct DType;
+template <> struct DType<float> { static constexpr wgb_dtype value = WGB_F32; };
+struct bf16 { uint16_t bits; };
+template <> struct DType<bf16> { static constexpr wgb_dtype value = WGB_BF16; };
+
+using ViewShape = wgb_view_shape;  // shapes.rs:9-21
+
+// shapes.rs:46-116 — a cache of per-shape uniform buffers in the reference; a no-op here (shape = kernel parameter).
+struct ViewShapeBuffers {
+    template <typename Device> const ViewShape &get(const Device &, const ViewShape &s) const { return s; }
+    void clear_tmp() const {}
+};
+
+class Device;
+class ComputePass;
+
+class GpuTimestamps {  // timestamps.rs:9-248
+  public:
+    GpuTimestamps(const Device &dev, uint32_t capacity);
+    ~GpuTimestamps() { for (auto e : ev_) wgb_event_destroy(e); }
+    std::pair<wgb_event *, wgb_event *> next_compute_pass_timestamp_writes() {
+        if (len_ + 2 > ev_.size()) throw std::out_of_range("GpuTimestamps capacity exceeded");
+        len_ += 2;
+        return {ev_[len_ - 2], ev_[len_ - 1]};
+    }
+    void clear() { len_ = 0; }
+    std::vector<float> wait_for_results_ms() const {
+        std::vector<float> out(len_, 0.f);
+        for (size_t i = 1; i < len_; ++i) check(wgb_event_elapsed_ms(ev_[0], ev_[i], &out[i]));
+        return out;
+    }
+  private:
+    std::vector<wgb_event *> ev_;
+    size_t len_ = 0;
+};
+
+class ComputePass {  // kernel.rs:15-26; the destructor is Rust's drop(pass)
+  public:
+    ComputePass(wgb_ctx *ctx, const char *label, GpuTimestamps *ts) {
+        wgb_event *b = nullptr, *e = nullptr;
+        if (ts) std::tie(b, e) = ts->next_compute_pass_timestamp_writes();
+        check(wgb_pass_begin(ctx, label, b, e, &h_));
+    }
+    ComputePass(ComputePass &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    ComputePass(const ComputePass &) = delete;
+    ~ComputePass() { if (h_) wgb_pass_end(h_); }
+    wgb_pass *raw() const { return h_; }
+    int last_gemm_path() const { int p = 0; check(wgb_pass_last_gemm_path(h_, &p)); return p; }
+  private:
+    wgb_pass *h_ = nullptr;
+};
+
+class CommandEncoder {
+  public:
+    explicit CommandEncoder(wgb_ctx *ctx) : ctx_(ctx) {}
+    ComputePass compute_pass(const char *label, GpuTimestamps *timestamps = nullptr) { return ComputePass(ctx_, label, timestamps); }
+    CommandEncoder &finish() { return *this; }
+    wgb_ctx *ctx() const { return ctx_; }
+  private:
+    wgb_ctx *ctx_;
+};
+
+class Device {
+  public:
+    explicit Device(int ordinal) { check(wgb_ctx_create(ordinal, &h_)); }
+    ~Device() { wgb_ctx_destroy(h_); }
+    Device(const Device &) = delete;
+    CommandEncoder create_command_encoder() const { return CommandEncoder(h_); }
+    void poll_wait() const { check(wgb_ctx_sync(h_)); }     // device.poll(PollType::wait())
+    uint64_t launch_count() const { uint64_t n = 0; check(wgb_ctx_launch_count(h_, &n)); return n; }
+    wgb_ctx *raw() const { return h_; }
+  private:
+    wgb_ctx *h_ = nullptr;
+};
+
+inline GpuTimestamps::GpuTimestamps(const Device &dev, uint32_t capacity) {
+    for (uint32_t i = 0; i < capacity; ++i) {
+        wgb_event *e = nullptr;
+        check(wgb_event_create(dev.raw(), &e));
+        ev_.push_back(e);
+    }
+}
+
+class Queue {
+  public:
+    explicit Queue(const Device &d) : d_(d) {}
+    void submit(CommandEncoder &) const { check(wgb_submit(d_.raw())); }   // queue.submit(Some(encoder.finish()))
+  private:
+    const Device &d_;
+};
+
+class GpuInstance {  // gpu.rs:7-79
+  public:
+    explicit GpuInstance(int ordinal = 0) : device_(ordinal), queue_(device_) {}
+    const Device &device() const { return device_; }
+    const Queue &queue() const { return queue_; }
+  private:
+    Device device_;
+    Queue queue_;
+};
+
+struct Buffer {  // wgpu::Buffer
+    wgb_buffer *raw = nullptr;
+    size_t bytes = 0;
+    Buffer(wgb_buffer *r, size_t b) : raw(r), bytes(b) {}
+    Buffer(const Buffer &) = delete;
+    ~Buffer() { wgb_buffer_destroy(raw); }
+    size_t size() const { return bytes; }
+};
+
+template <typename T, int DIM> class GpuTensorView {  // tensor.rs:416-511
+  public:
+    GpuTensorView(ViewShape s, const Buffer *b) : view_shape_(s), buffer_(b) {}
+    ViewShape shape() const { return view_shape_; }
+    const Buffer *buffer() const { return buffer_; }
+    uint32_t len() const { return view_shape_.size[0]; }
+    // GpuVectorView::rows (:445-462) / GpuMatrixView::rows (:498-510)
+    GpuTensorView rows(uint32_t first_row, uint32_t nrows) const {
+        ViewShape s = view_shape_;
+        if (DIM == 1 && first_row + nrows > len()) throw std::out_of_range("Rows slice range out of bounds");
+        s.size[0] = nrows;
+        if (DIM == 1) { s.size[1] = 1; s.size[2] = 1; } else { s.size[2] = 1; }
+        s.offset += first_row;
+        return GpuTensorView(s, buffer_);
+    }
+    GpuTensorView columns(uint32_t first_col, uint32_t ncols) const {   // :484-496
+        ViewShape s = view_shape_;
+        s.size[1] = ncols; s.size[2] = 1;
+        s.offset += s.stride * first_col;
+        return GpuTensorView(s, buffer_);
+    }
+    GpuTensorView<T, 2> matrix(uint32_t matrix_id) const {            // :466-481
+        if (matrix_id >= view_shape_.size[2]) throw std::out_of_range("matrix id out of range");
+        ViewShape s = view_shape_;
+        s.size[2] = 1;
+        s.offset += s.stride_mat * matrix_id;
+        s.stride_mat = 1;
+        return GpuTensorView<T, 2>(s, buffer_);
+    }
+    template <int D2> operator GpuTensorView<T, D2>() const { return GpuTensorView<T, D2>(view_shape_, buffer_); }
+  private:
+    ViewShape view_shape_;
+    const Buffer *buffer_;
+};
+
+template <typename T, int DIM> class GpuTensor {  // tensor.rs:192-399
+  public:
+    GpuTensor(std::array<uint32_t, DIM> shape, std::unique_ptr<Buffer> buf) : shape_(shape), buffer_(std::move(buf)) {}
+    uint64_t len() const { uint64_t n = 1; for (auto s : shape_) n *= s; return n; }
+    uint64_t bytes_len() const { return sizeof(T) * len(); }
+    std::array<uint32_t, DIM> shape() const { return shape_; }
+    const Buffer &buffer() const { return *buffer_; }
+
+    // reshape (:514-541) with default strides, offset 0
+    template <int D2> GpuTensorView<T, D2> reshape(std::array<uint32_t, D2> shape) const {
+        ViewShape s{{1, 1, 1}, 0, 0, 0};
+        for (int i = 0; i < D2 && i < 3; ++i) s.size[i] = shape[i];
+        const uint32_t s0 = D2 > 0 ? shape[0] : 1, s1 = D2 > 1 ? shape[1] : 1;
+        s.stride = s0;
+        s.stride_mat = s0 * s1;
+        return GpuTensorView<T, D2>(s, buffer_.get());
+    }
+    template <int D2 = 3> GpuTensorView<T, D2> as_embedded_view() const {   // :287-297
+        static_assert(D2 >= DIM, "Can only embed into a higher-order tensor view.");
+        std::array<uint32_t, D2> e;
+        e.fill(1);
+        for (int i = 0; i < DIM; ++i) e[i] = shape_[i];
+        return reshape<D2>(e);
+    }
+    GpuTensorView<T, DIM> as_view() const { return as_embedded_view<DIM>(); }
+    template <int D2> operator GpuTensorView<T, D2>() const { return as_embedded_view<(D2 > DIM ? D2 : DIM)>(); }   // :403-409
+
+    GpuTensorView<T, 1> column(uint32_t i) const {                       // GpuMatrix::column :574-585
+        return GpuTensorView<T, 1>(ViewShape{{shape_[0], 1, 1}, 1, 1, shape_[0] * i}, buffer_.get());
+    }
+    GpuTensorView<T, 2> columns(uint32_t first_col, uint32_t ncols) const {   // :600-612
+        return GpuTensorView<T, 2>(ViewShape{{shape_[0], ncols, 1}, shape_[0], shape_[0] * shape_[1], first_col * shape_[0]}, buffer_.get());
+    }
+    GpuTensorView<T, (DIM == 1 ? 1 : 2)> rows(uint32_t first_row, uint32_t nrows) const {   // :614-626 / :669-681
+        if (DIM == 1) return GpuTensorView<T, (DIM == 1 ? 1 : 2)>(ViewShape{{nrows, 1, 1}, shape_[0], shape_[0], first_row}, buffer_.get());
+        return GpuTensorView<T, (DIM == 1 ? 1 : 2)>(ViewShape{{nrows, shape_[DIM > 1 ? 1 : 0], 1}, shape_[0], shape_[0] * shape_[DIM > 1 ? 1 : 0], first_row}, buffer_.get());
+    }
+
+    void copy_from(CommandEncoder &enc, const GpuTensor &src) const {    // :227-233
+        if (len() != src.len()) throw Error(WGB_ERR_DIM_MISMATCH, "copy_from: length mismatch");
+        check(wgb_buffer_copy(enc.ctx(), nullptr, buffer_->raw, 0, src.buffer_->raw, 0, bytes_len()));
+    }
+    std::vector<T> read(const Device &dev) const {                        // :375-384 (blocks like poll(wait))
+        std::vector<T> out(len());
+        check(wgb_buffer_read(dev.raw(), buffer_->raw, 0, out.data(), bytes_len()));
+        return out;
+    }
+  private:
+    std::array<uint32_t, DIM> shape_;
+    std::unique_ptr<Buffer> buffer_;
+};
+template <typename T> using GpuScalar = GpuTensor<T, 0>;
+template <typename T> using GpuVector = GpuTensor<T, 1>;
+template <typename T> using GpuMatrix = GpuTensor<T, 2>;
+template <typename T> using GpuCube = GpuTensor<T, 3>;
+template <typename T> using GpuVectorView = GpuTensorView<T, 1>;
+template <typename T> using GpuMatrixView = GpuTensorView<T, 2>;
+template <typename T> using GpuCubeView = GpuTensorView<T, 3>;
+
+template <int DIM> class TensorBuilder {  // tensor.rs:65-187
+  public:
+    TensorBuilder(std::array<uint32_t, DIM> shape, uint32_t usage) : shape_(shape), usage_(usage) {}
+    uint64_t len() const { uint64_t n = 1; for (auto s : shape_) n *= s; return n; }
+    template <typename T> GpuTensor<T, DIM> build(const Device &dev) const {                     // :112-129
+        wgb_buffer *b = nullptr;
+        check(wgb_buffer_create(dev.raw(), sizeof(T) * len(), usage_, &b));
+        return GpuTensor<T, DIM>(shape_, std::make_unique<Buffer>(b, sizeof(T) * len()));
+    }
+    template <typename T> GpuTensor<T, DIM> build_init(const Device &dev, const std::vector<T> &data) const {   // :175-186
+        if (data.size() < len()) throw Error(WGB_ERR_INVALID, "Incorrect number of elements provided for initializing Tensor.");
+        wgb_buffer *b = nullptr;
+        check(wgb_buffer_create_init(dev.raw(), data.data(), sizeof(T) * len(), usage_, &b));
+        return GpuTensor<T, DIM>(shape_, std::make_unique<Buffer>(b, sizeof(T) * len()));
+    }
+  private:
+    std::array<uint32_t, DIM> shape_;
+    uint32_t usage_;
+};
+struct Tensors {   // TensorBuilder::{scalar, vector, matrix} (:72-90)
+    static TensorBuilder<0> scalar(uint32_t usage) { return TensorBuilder<0>({}, usage); }
+    static TensorBuilder<1> vector(uint32_t dim, uint32_t usage) { return TensorBuilder<1>({dim}, usage); }
+    static TensorBuilder<2> matrix(uint32_t r, uint32_t c, uint32_t usage) { return TensorBuilder<2>({r, c}, usage); }
+};
+
+// ---- wgebra::linalg -------------------------------------------------------------------------
+enum class GemmVariant { Gemm = 0, GemmFast = 1, GemmTr = 2, GemmTrFast = 3 };          // gemm.rs:25-35
+enum class GemvVariant { Gemv = 0, GemvFast = 1, GemvTr = 2, GemvTrFast = 3 };          // gemv.rs:24-34
+enum class OpAssignVariant { Add = 0, Sub = 1, Mul = 2, Div = 3, Copy = 4 };            // op_assign.rs:15-26
+enum class ReduceOp { Min = 0, Max = 1, Sum = 2, Prod = 3, SqNorm = 4 };                // reduce.rs:16-27
+
+class Gemm {  // gemm.rs:9-127
+  public:
+    static Gemm from_device(const Device &) { return Gemm(); }
+    wgb_f32_mode f32_mode = WGB_F32_AUTO;
+    template <typename T> void dispatch(const Device &d, const ViewShapeBuffers &s, ComputePass &p, GpuCubeView<T> out, GpuCubeView<T> m1, GpuCubeView<T> m2) const {
+        dispatch_generic<T>(d, s, p, out, m1, m2, GemmVariant::Gemm);
+    }
+    template <typename T> void dispatch_tr(const Device &d, const ViewShapeBuffers &s, ComputePass &p, GpuCubeView<T> out, GpuCubeView<T> m1, GpuCubeView<T> m2) const {
+        dispatch_generic<T>(d, s, p, out, m1, m2, GemmVariant::GemmTr);
+    }
+    template <typename T> void dispatch_generic(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m1,
+                                                GpuCubeView<T> m2, GemmVariant variant) const {
+        const ViewShape so = shapes.get(d, out.shape()), s1 = shapes.get(d, m1.shape()), s2 = shapes.get(d, m2.shape());   // gemm.rs:98-100
+        check(wgb_gemm_ex(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, m1.buffer()->raw, &s1, m2.buffer()->raw, &s2,
+                          DType<T>::value, DType<T>::value, f32_mode));
+    }
+};
+
+class Gemv {  // gemv.rs:9-137
+  public:
+    static Gemv from_device(const Device &) { return Gemv(); }
+    template <typename T> void dispatch(const Device &d, const ViewShapeBuffers &s, ComputePass &p, GpuCubeView<T> out, GpuCubeView<T> m, GpuCubeView<T> v) const {
+        dispatch_generic<T>(d, s, p, out, m, v, GemvVariant::Gemv);
+    }
+    template <typename T> void dispatch_tr(const Device &d, const ViewShapeBuffers &s, ComputePass &p, GpuCubeView<T> out, GpuCubeView<T> m, GpuCubeView<T> v) const {
+        dispatch_generic<T>(d, s, p, out, m, v, GemvVariant::GemvTr);
+    }
+    template <typename T> void dispatch_generic(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m,
+                                                GpuCubeView<T> v, GemvVariant variant) const {
+        const ViewShape so = shapes.get(d, out.shape()), sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape());
+        check(wgb_gemv(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, v.buffer()->raw, &sv));
+    }
+};
+
+class OpAssign {  // op_assign.rs:43-94
+  public:
+    OpAssignVariant variant;
+    static OpAssign make(const Device &, OpAssignVariant op) { return OpAssign{op}; }   // OpAssign::new
+    template <typename T> void dispatch(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuVectorView<T> in_out_a, GpuVectorView<T> in_b) const {
+        const ViewShape sa = shapes.get(d, in_out_a.shape()), sb = shapes.get(d, in_b.shape());
+        check(wgb_op_assign(pass.raw(), (wgb_op_assign_variant)variant, in_out_a.buffer()->raw, &sa, in_b.buffer()->raw, &sb));
+    }
+};
+
+class Reduce {  // reduce.rs:62-124
+  public:
+    ReduceOp op;
+    static Reduce make(const Device &, ReduceOp op) { return Reduce{op}; }              // Reduce::new
+    template <typename T> void dispatch(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuVectorView<T> value, const GpuScalar<T> &result) const {
+        const ViewShape sv = shapes.get(d, value.shape());
+        check(wgb_reduce(pass.raw(), (wgb_reduce_op)op, value.buffer()->raw, &sv, result.buffer().raw));
+    }
+};
+
+}  // namespace wgb
