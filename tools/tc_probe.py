@@ -83,7 +83,7 @@ def quick(cgs=(1, 2)):
             for dtype, mode, tol, name in (("bf16", w.F32Mode.Auto, 1e-4, "bf16"), ("f32", w.F32Mode.Tf32, 3e-3, "tf32"),
                                            ("f32", w.F32Mode.X3Tf32, 1e-5, "3xtf32")):
                 for tr in (False, True):
-                    for (M, N, K) in ((128, 256, 64), (256, 256, 256), (512, 512, 128), (200, 136, 72), (1024, 768, 520)):
+                    for (M, N, K) in ((128, 256, 64), (256, 256, 256), (512, 512, 128), (200, 136, 72), (1024, 768, 520), (512, 512, 2048)):
                         tag = f"cg{cg} bn{bn} {name} tr={int(tr)} {M}x{N}x{K}"
                         try:
                             got, ref, path = run(M, N, K, tr, dtype, mode)
@@ -124,9 +124,9 @@ def timed_gemm(n, dtype, mode, steps=10, out_dtype=None, tr=False):
 
 def perf(cgs=(1, 2)):
     for cg in cgs:
-        for bn in (128, 256):
+        for bn in (256,):
             set_cfg(cg, bn)
-            for n in (4096, 8192):
+            for n in (1024, 2048, 4096, 8192):
                 for tr in (False, True):
                     ms, path = timed_gemm(n, "bf16", w.F32Mode.Auto, steps=10 if n == 4096 else 4, tr=tr)
                     print(f"PERF cg{cg} bn{bn} bf16 tr={int(tr)} n={n}: {ms:.4f} ms  {2 * n ** 3 / ms / 1e9:.1f} TFLOP/s path={path}", flush=True)
@@ -141,7 +141,7 @@ def acc(cgs=(1, 2)):
     for cg in cgs:
         os.environ["WGB_TC_CG"] = str(cg)
         for K in (1024, 4096, 16384, 32768):
-            got, ref, path = run(256, 256, K, False, "f32", w.F32Mode.X3Tf32)
+            got, ref, path = run(256, 256, K, True, "f32", w.F32Mode.X3Tf32)
             e = (got - ref) / ref
             print(f"ACC cg{cg} 3xtf32 K={K}: max|rel| {np.abs(e).max():.3e} mean rel {e.mean():+.3e} path={path}", flush=True)
             got, ref, path = run(256, 256, K, False, "f32", w.F32Mode.Simt)

@@ -174,13 +174,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ---------------------------------------------------------------------------------------------
 // descriptors (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: required for
+// MN-major 32-bit operands, matching TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address, 16-byte units
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;    // leading-dimension byte offset
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride-dimension byte offset
     d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
-    d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+    d |= (uint64_t)layout_type << 61;
     return d;
 }
 
@@ -198,7 +200,29 @@ struct TcArgs {
     uint64_t ldc, sc;
     uint32_t M, N, K, nmats;
     uint32_t tiles_m, tiles_n, num_kb, total_tiles;
+    // tail split-K: tiles [full_tiles, total_tiles) are each cut into `split` K ranges of `kb_per_split` k-blocks, so the
+    // last, partially filled wave of tiles still occupies every SM.  Work units = full_tiles + (total - full) * split.
+    uint32_t full_tiles, split, kb_per_split, total_units;
+    float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
+    unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
 };
+
+struct WorkUnit {
+    uint32_t tile, kb0, kb1, split_idx;   // split_idx == 0xFFFFFFFF: whole tile
+};
+__device__ __forceinline__ WorkUnit decode_unit(uint32_t u, const TcArgs &a) {
+    WorkUnit w;
+    if (u < a.full_tiles) {
+        w.tile = u; w.kb0 = 0; w.kb1 = a.num_kb; w.split_idx = 0xFFFFFFFFu;
+    } else {
+        const uint32_t v = u - a.full_tiles;
+        w.tile = a.full_tiles + v / a.split;
+        w.split_idx = v % a.split;
+        w.kb0 = w.split_idx * a.kb_per_split;
+        w.kb1 = min(a.num_kb, w.kb0 + a.kb_per_split);
+    }
+    return w;
+}
 
 constexpr int kBlockM = 128;        // rows per CTA
 constexpr int kRowBytes = 128;      // bytes of K (K-major) or of M (MN-major) per smem row = swizzle span
@@ -267,6 +291,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *tmem_full_bar = bars + 2 * STAGES;  // [2]
     uint64_t *tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    volatile uint32_t *split_flag = tmem_ptr_smem + 1;   // epilogue-warps-only broadcast slot
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
@@ -305,12 +330,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         // ===================================== TMA producer =====================================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+        for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
+            const WorkUnit wu = decode_unit(u, args);
             uint32_t bt, mt, nt;
-            tile_coords(t, args, bt, mt, nt);
+            tile_coords(wu.tile, args, bt, mt, nt);
             const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
             const int n0 = (int)(nt * BN + cta_rank * Cfg::B_ROWS);
-            for (uint32_t kb = 0; kb < args.num_kb; ++kb) {
+            for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                 const uint32_t fb = smem_u32(full_bar + stage);
                 if (leader) mbar_arrive_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES * CG);
@@ -342,11 +368,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== MMA issuer (leader CTA only) =====================
         if (leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+            for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
+                const WorkUnit wu = decode_unit(u, args);
                 mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
-                for (uint32_t kb = 0; kb < args.num_kb; ++kb) {
+                for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
                     mbar_wait(smem_u32(full_bar + stage), phase);
                     tc_fence_after();
                     const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -358,11 +385,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
                         const uint32_t b_off = j * 32;
                         const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
-                        const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, sbo);
+                        // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
+                        constexpr bool A32 = A_MN && KIND == 1;
+                        const uint32_t a_sbo = A32 ? 512 : 1024, a_lt = A32 ? 1 : 2;
+                        const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, a_sbo, a_lt);
                         const uint64_t db_hi = make_smem_desc(sb_hi + b_off, 16, sbo);
-                        const uint32_t first = (kb | (uint32_t)j) == 0 ? 0u : 1u;
+                        const uint32_t first = (kb == wu.kb0 && j == 0) ? 0u : 1u;
                         if (PASSES == 3) {
-                            const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, sbo);
+                            const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
                             const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
                             umma<KIND, CG>(d_tmem, da_lo, db_hi, IDESC, first);   // small terms first
                             umma<KIND, CG>(d_tmem, da_hi, db_lo, IDESC, 1u);
@@ -372,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
-                    if (kb + 1 == args.num_kb) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
+                    if (kb + 1 == wu.kb1) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 acc ^= 1;
@@ -384,16 +414,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
         TOut *cbase = reinterpret_cast<TOut *>(args.c);
         uint32_t acc = 0, acc_phase = 0;
-        for (uint32_t t = cluster_id; t < args.total_tiles; t += num_clusters) {
+        for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
+            const WorkUnit wu = decode_unit(u, args);
             uint32_t bt, mt, nt;
-            tile_coords(t, args, bt, mt, nt);
-            const uint32_t row = mt * (kBlockM * CG) + cta_rank * kBlockM + q * 32 + lane;
+            tile_coords(wu.tile, args, bt, mt, nt);
+            const uint32_t row_in_cta = q * 32 + lane;
+            const uint32_t row = mt * (kBlockM * CG) + cta_rank * kBlockM + row_in_cta;
             const uint32_t n0 = nt * BN;
+            const bool split_unit = wu.split_idx != 0xFFFFFFFFu;
             mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
             TOut *crow = cbase + (uint64_t)bt * args.sc + row;
             const bool row_ok = row < args.M;
+            // split units park their f32 partial in the workspace: [slot][split][rank][col][row]
+            const uint32_t slot = wu.tile - args.full_tiles;
+            float *wsp = split_unit ? args.ws + (((uint64_t)slot * args.split + wu.split_idx) * CG + cta_rank) * (uint64_t)(BN * kBlockM) + row_in_cta
+                                    : nullptr;
             uint32_t v[2][32];
             tmem_ld32(taddr, v[0]);
 #pragma unroll
@@ -409,12 +446,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else mbar_arrive(smem_u32(tmem_empty_bar + acc));
                     }
                 }
-                if (row_ok) {
+                if (split_unit) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
+                } else if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         const uint32_t col = n0 + c * 32 + i;
                         if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
                     }
+                }
+            }
+            if (split_unit) {
+                // last CTA to park its partial folds all of them in split order (deterministic) and writes the tile
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (threadIdx.x == 128) *split_flag = atomicAdd(args.counters + slot * CG + cta_rank, 1u);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const bool last = *split_flag == args.split - 1;
+                asm volatile("bar.sync 1, 128;" ::: "memory");   // everyone has read the flag before it can be rewritten
+                if (last) {
+                    __threadfence();
+                    const float *wbase = args.ws + ((uint64_t)slot * args.split * CG + cta_rank) * (uint64_t)(BN * kBlockM) + row_in_cta;
+                    if (row_ok) {
+                        for (uint32_t cc = 0; cc < (uint32_t)BN; ++cc) {
+                            const uint32_t col = n0 + cc;
+                            if (col >= args.N) break;
+                            float sum = 0.f;
+                            for (uint32_t sp = 0; sp < args.split; ++sp)
+                                sum += __ldcg(wbase + (uint64_t)sp * CG * (BN * kBlockM) + (uint64_t)cc * kBlockM);
+                            store_out<TOut>(crow + (uint64_t)col * args.ldc, sum);
+                        }
+                    }
+                    if (threadIdx.x == 128) args.counters[slot * CG + cta_rank] = 0u;
                 }
             }
             acc ^= 1;
@@ -452,6 +516,38 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict
         const uint64_t o = t * smat_out + j * ld_out + i;
         hi[o] = hf;
         lo[o] = x - hf;
+    }
+}
+
+// Same split, but the output is transposed: src is [rows x cols] column-major, hi/lo are [cols x rows] column-major
+// (leading dimension ld_out >= cols).  Used to hand a non-transposed f32 m1 to the K-major kernel variant.
+// lo may be null (plain tf32-rounded transposed copy).  32x32 tiles through shared memory, coalesced both ways.
+__global__ void __launch_bounds__(256) split_tf32_transpose_kernel(const float *__restrict__ src, uint32_t rows, uint32_t cols,
+                                                                   uint64_t ld, uint64_t smat, float *__restrict__ hi,
+                                                                   float *__restrict__ lo, uint64_t ld_out, uint64_t smat_out) {
+    __shared__ float tile[32][33];
+    const uint32_t t = blockIdx.z;
+    const uint32_t r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const float *sp = src + (uint64_t)t * smat;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = r0 + tx, c = c0 + ty + 8 * j;
+        tile[ty + 8 * j][tx] = (r < rows && c < cols) ? __ldg(sp + (uint64_t)c * ld + r) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t r = r0 + ty + 8 * j, c = c0 + tx;   // output element (c, r): c is the contiguous axis
+        if (r < rows && c < cols) {
+            const float x = tile[tx][ty + 8 * j];
+            uint32_t h;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+            const float hf = __uint_as_float(h);
+            const uint64_t o = (uint64_t)t * smat_out + (uint64_t)r * ld_out + c;
+            hi[o] = hf;
+            if (lo) lo[o] = x - hf;
+        }
     }
 }
 
@@ -496,7 +592,7 @@ using TmapCache = std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>;
 
 // 3-D map: dim0 contiguous (d0 elements), dim1 stride s1 elements, dim2 (batch) stride s2 elements.
 wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
-                    uint32_t b0, uint32_t b1, CUtensorMap *out) {
+                    uint32_t b0, uint32_t b1, CUtensorMap *out, bool atom32 = false) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if (d2 <= 1) {   // single matrix: the batch stride is never used, but must still be a legal (16-byte multiple) stride
@@ -505,7 +601,7 @@ wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uin
         s2 = d0 > s1 * d1 ? d0 : s1 * d1;
         s2 = (s2 + q - 1) / q * q;
     }
-    TmapKey key{ptr, d0, d1, d2, s1, s2, b0, b1, es};
+    TmapKey key{ptr, d0, d1, d2, s1, s2, b0, b1, es | (atom32 ? 0x100u : 0u)};
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
     TmapCache &cache = *static_cast<TmapCache *>(ctx->tmap_cache);
@@ -519,7 +615,8 @@ wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uin
     cuuint32_t box[3] = {b0, b1, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(out, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr),
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu, strides %llu / %llu B, box %u x %u", (int)r,
@@ -550,7 +647,7 @@ wgb_status launch_cfg(wgb_pass *p, const CUtensorMap &ta, const CUtensorMap &tal
     const uint32_t margin = (uint32_t)comm_sm_margin(p->ctx);
     if (margin < sms / 2) sms -= margin;
     uint32_t clusters = sms / CG;
-    if (clusters > args.total_tiles) clusters = args.total_tiles;
+    if (clusters > args.total_units) clusters = args.total_units;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CG);
     cfg.blockDim = dim3(kNumThreads);
@@ -598,19 +695,37 @@ bool gemm_tc_eligible(const GemmProblem &g) {
     return aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, es) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, es);
 }
 
-// Picks BLOCK_N by wave quantisation: time ~ ceil(tiles / clusters) * BLOCK_N (a BLOCK_N = 128 tile moves 1.5x the
-// operand bytes per flop, charged as a small penalty).
+// Picks BLOCK_N.  BLOCK_N = 128 moves 1.5x the operand bytes per flop and measured ~0.64x the throughput of 256
+// (probe: 840 vs 1310 TFLOP/s at 4096^3), so it only wins when 256 would leave most of the machine idle; the tail
+// wave of 256-wide tiles is handled by split-K instead (plan_split).
 static int pick_bn(uint32_t M, uint32_t N, uint32_t nmats, int cg, uint32_t sms) {
     const int forced = env_int("WGB_TC_BN", 0);
     if (forced == 128 || forced == 256) return forced;
-    const uint64_t tm = (M + 128 * cg - 1) / (128 * cg);
-    const uint64_t clusters = sms / cg;
-    auto cost = [&](int bn) {
-        const uint64_t tiles = tm * ((N + bn - 1) / bn) * nmats;
-        const uint64_t waves = (tiles + clusters - 1) / clusters;
-        return (double)waves * bn * (bn == 128 ? 1.06 : 1.0);
-    };
-    return cost(128) < cost(256) ? 128 : 256;
+    if (N <= 128) return 128;
+    return 256;
+}
+
+// Tail split-K plan: with T tiles on C clusters, the last T mod C tiles would run alone; cut each into
+// floor(C / tail) K ranges so the last wave is full too (each range keeps >= 4 k-blocks).
+static void plan_split(TcArgs &a, uint32_t clusters) {
+    a.full_tiles = a.total_tiles;
+    a.split = 1;
+    a.kb_per_split = a.num_kb;
+    a.total_units = a.total_tiles;
+    if (env_int("WGB_TC_SPLITK", 1) == 0) return;
+    const uint32_t tail = a.total_tiles % clusters;
+    if (tail == 0) return;
+    uint32_t split = clusters / tail;
+    if (split > 8) split = 8;
+    if (split > a.num_kb / 4) split = a.num_kb / 4;
+    if (split < 2) return;
+    const uint32_t per = (a.num_kb + split - 1) / split;
+    split = (a.num_kb + per - 1) / per;
+    if (split < 2) return;
+    a.full_tiles = a.total_tiles - tail;
+    a.split = split;
+    a.kb_per_split = per;
+    a.total_units = a.full_tiles + tail * split;
 }
 
 wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, int *path_out) {
@@ -618,48 +733,78 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     const bool f32 = g.in_dtype == WGB_F32;
     int passes = 1;
     if (f32) passes = (mode == WGB_F32_TF32) ? 1 : 3;
-    if (f32 && passes == 1 &&
-        !(aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)))
-    {   // single-pass TF32 reads the caller's views directly: needs TMA alignment
+    // A non-transposed f32 m1 is an MN-major 32-bit operand.  "direct": TMA 32-byte-atom swizzle + BASE32B descriptor.
+    // "transpose": the prep kernel writes tr(m1) dense and the K-major kernel variant runs (always valid).
+    const bool mn_direct = env_int("WGB_TF32_MN_DIRECT", 0) != 0;
+    const bool transpose_a = f32 && !g.tr && !mn_direct;
+    if (f32 && passes == 1 && !transpose_a &&
+        !(aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4))) {
+        *path_out = 1;   // single-pass TF32 reads the caller's views directly: needs TMA alignment
+        return launch_gemm_simt(p, g);
+    }
+    if (f32 && passes == 1 && transpose_a && !aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)) {
+        *path_out = 1;
+        return launch_gemm_simt(p, g);
+    }
+    if (g.nmats > 65535 && f32) {
         *path_out = 1;
         return launch_gemm_simt(p, g);
     }
     const size_t es = f32 ? 4 : 2;
-    const int cg = env_int("WGB_TC_CG", 1) == 2 ? 2 : 1;
-    const int bn = pick_bn(g.M, g.N, g.nmats, cg, (uint32_t)ctx->prop.multiProcessorCount);
+    const int cg = env_int("WGB_TC_CG", 2) == 1 ? 1 : 2;
+    const uint32_t sms_total = (uint32_t)ctx->prop.multiProcessorCount;
+    const int bn = pick_bn(g.M, g.N, g.nmats, cg, sms_total);
     const uint32_t block_k = 128 / (uint32_t)es;
 
-    const uint32_t a_rows = g.tr ? g.K : g.M, a_cols = g.tr ? g.M : g.K;
+    bool tr = g.tr;
+    uint32_t a_rows = g.tr ? g.K : g.M, a_cols = g.tr ? g.M : g.K;
     const char *a_ptr = (const char *)g.a + g.a_off * es, *b_ptr = (const char *)g.b + g.b_off * es;
     const char *alo_ptr = a_ptr, *blo_ptr = b_ptr;
     uint64_t lda = g.lda, ldb = g.ldb, sa = g.sa, sb = g.sb;
-    if (passes == 3) {
-        // dense hi / lo copies in the context workspace (slots 0, 1)
-        const uint64_t lda_d = ((uint64_t)a_rows + 3) & ~3ull, ldb_d = ((uint64_t)g.K + 3) & ~3ull;
-        const uint64_t sa_d = lda_d * a_cols, sb_d = ldb_d * g.N;
-        const size_t a_bytes = sa_d * g.nmats * 4, b_bytes = sb_d * g.nmats * 4;
-        void *wa = nullptr, *wb = nullptr;
-        WGB_TRY(workspace_reserve(ctx, 0, 2 * a_bytes, &wa));
-        WGB_TRY(workspace_reserve(ctx, 1, 2 * b_bytes, &wb));
-        float *ahi = (float *)wa, *alo = (float *)((char *)wa + a_bytes);
-        float *bhi = (float *)wb, *blo = (float *)((char *)wb + b_bytes);
+    if (f32 && (passes == 3 || transpose_a)) {
+        // dense re-materialised operands in the context workspace: slot 0 = A (hi, lo), slot 1 = B (hi, lo)
+        const uint32_t oa_rows = transpose_a ? g.K : a_rows, oa_cols = transpose_a ? g.M : a_cols;
+        const uint64_t lda_d = ((uint64_t)oa_rows + 3) & ~3ull;
+        const uint64_t sa_d = lda_d * oa_cols;
+        const size_t a_bytes = sa_d * g.nmats * 4;
+        void *wa = nullptr;
+        WGB_TRY(workspace_reserve(ctx, 0, (passes == 3 ? 2 : 1) * a_bytes, &wa));
+        float *ahi = (float *)wa, *alo = passes == 3 ? (float *)((char *)wa + a_bytes) : nullptr;
         const int sgrid = ctx->prop.multiProcessorCount * 8;
-        split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)a_ptr, a_rows, a_cols, g.nmats, g.lda, g.sa, ahi, alo, lda_d, sa_d);
-        split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)b_ptr, g.K, g.N, g.nmats, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
-        WGB_CUDA(cudaGetLastError());
-        count_launch(ctx, 2);
+        if (transpose_a) {
+            dim3 tg((g.M + 31) / 32, (g.K + 31) / 32, g.nmats);
+            if (tg.y > 65535) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: K too large for the transposing prep");
+            split_tf32_transpose_kernel<<<tg, 256, 0, p->stream>>>((const float *)a_ptr, g.M, g.K, g.lda, g.sa, ahi, alo, lda_d, sa_d);
+            tr = true;
+            a_rows = g.K; a_cols = g.M;
+        } else {
+            split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)a_ptr, a_rows, a_cols, g.nmats, g.lda, g.sa, ahi, alo, lda_d, sa_d);
+        }
+        count_launch(ctx);
         a_ptr = (const char *)ahi; alo_ptr = (const char *)alo;
-        b_ptr = (const char *)bhi; blo_ptr = (const char *)blo;
-        lda = lda_d; ldb = ldb_d; sa = sa_d; sb = sb_d;
+        lda = lda_d; sa = sa_d;
+        if (passes == 3) {
+            const uint64_t ldb_d = ((uint64_t)g.K + 3) & ~3ull, sb_d = ldb_d * g.N;
+            const size_t b_bytes = sb_d * g.nmats * 4;
+            void *wb = nullptr;
+            WGB_TRY(workspace_reserve(ctx, 1, 2 * b_bytes, &wb));
+            float *bhi = (float *)wb, *blo = (float *)((char *)wb + b_bytes);
+            split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)b_ptr, g.K, g.N, g.nmats, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
+            count_launch(ctx);
+            b_ptr = (const char *)bhi; blo_ptr = (const char *)blo;
+            ldb = ldb_d; sb = sb_d;
+        }
+        WGB_CUDA(cudaGetLastError());
     }
 
     CUtensorMap ta, talo, tb, tblo;
-    const uint32_t a_box0 = g.tr ? block_k : (uint32_t)(128 / es);          // K-major: 128 B of K; MN-major: one 128 B atom of M
-    const uint32_t a_box1 = g.tr ? 128u : block_k;
-    WGB_TRY(get_tmap(ctx, a_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &ta));
+    const bool atom32 = f32 && !tr;                                     // MN-major 32-bit operand A
+    const uint32_t a_box0 = tr ? block_k : (uint32_t)(128 / es);       // K-major: 128 B of K; MN-major: one 128 B atom of M
+    const uint32_t a_box1 = tr ? 128u : block_k;
+    WGB_TRY(get_tmap(ctx, a_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &ta, atom32));
     WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tb));
     if (passes == 3) {
-        WGB_TRY(get_tmap(ctx, alo_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &talo));
+        WGB_TRY(get_tmap(ctx, alo_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &talo, atom32));
         WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tblo));
     } else {
         talo = ta;
@@ -674,22 +819,37 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     args.tiles_n = (g.N + bn - 1) / bn;
     args.num_kb = (g.K + block_k - 1) / block_k;
     const uint64_t total = (uint64_t)args.tiles_m * args.tiles_n * g.nmats;
-    if (total > 0xFFFFFFFFull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: too many output tiles");
+    if (total > 0x7FFFFFFFull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: too many output tiles");
     args.total_tiles = (uint32_t)total;
+    uint32_t sms = sms_total;
+    const uint32_t margin = (uint32_t)comm_sm_margin(ctx);
+    if (margin < sms / 2) sms -= margin;
+    plan_split(args, sms / cg);
+    if (args.split > 1) {
+        const uint32_t tail = args.total_tiles - args.full_tiles;
+        if ((uint64_t)tail * cg > ctx->scratch.n_counters) {
+            args.full_tiles = args.total_tiles; args.split = 1; args.kb_per_split = args.num_kb; args.total_units = args.total_tiles;
+        } else {
+            void *w = nullptr;
+            WGB_TRY(workspace_reserve(ctx, 2, (size_t)tail * args.split * cg * bn * 128 * 4, &w));
+            args.ws = (float *)w;
+            args.counters = ctx->scratch.counters;
+        }
+    }
 
     wgb_status st;
     if (!f32) {
         if (g.out_dtype == WGB_F32)
-            st = g.tr ? launch_sel<0, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<0, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+            st = tr ? launch_sel<0, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<0, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
         else
-            st = g.tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args)
-                      : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args);
+            st = tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args)
+                    : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args);
         *path_out = 2;
     } else if (passes == 1) {
-        st = g.tr ? launch_sel<1, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        st = tr ? launch_sel<1, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
         *path_out = 3;
     } else {
-        st = g.tr ? launch_sel<1, false, 3, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 3, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        st = tr ? launch_sel<1, false, 3, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 3, float>(p, bn, cg, ta, talo, tb, tblo, args);
         *path_out = 4;
     }
     return st;

@@ -32,7 +32,7 @@ __device__ __forceinline__ float apply_op(float a, float b) {
 }
 
 template <int OP, bool B_ALIGNED>
-__global__ void __launch_bounds__(kThreads) op_assign_kernel(float *__restrict__ a, const float *__restrict__ b,
+__global__ void __launch_bounds__(kThreads, 4) op_assign_kernel(float *__restrict__ a, const float *__restrict__ b,
                                                              uint64_t n, uint32_t head) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -42,43 +42,54 @@ __global__ void __launch_bounds__(kThreads) op_assign_kernel(float *__restrict__
     if (tid < head) a[tid] = apply_op<OP>(OP == WGB_OP_COPY ? 0.f : a[tid], b[tid]);
     if (tail0 + tid < n) a[tail0 + tid] = apply_op<OP>(OP == WGB_OP_COPY ? 0.f : a[tail0 + tid], b[tail0 + tid]);
 
-    float4 *av = reinterpret_cast<float4 *>(a + head);
-    const float *bb = b + head;
-    constexpr int U = 4;
-    uint64_t i = tid;
-    for (; i + (U - 1) * nthreads < nvec; i += U * nthreads) {
-        float4 x[U], y[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint64_t j = i + u * nthreads;
-            if (OP != WGB_OP_COPY) x[u] = __ldcs(av + j);
-            if (B_ALIGNED) y[u] = ld_stream4(bb + 4 * j);
-            else y[u] = make_float4(__ldcs(bb + 4 * j), __ldcs(bb + 4 * j + 1), __ldcs(bb + 4 * j + 2), __ldcs(bb + 4 * j + 3));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            float4 r;
-            r.x = apply_op<OP>(x[u].x, y[u].x);
-            r.y = apply_op<OP>(x[u].y, y[u].y);
-            r.z = apply_op<OP>(x[u].z, y[u].z);
-            r.w = apply_op<OP>(x[u].w, y[u].w);
-            __stcs(av + i + u * nthreads, r);
-        }
-    }
-    for (; i < nvec; i += nthreads) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y;
-        if (OP != WGB_OP_COPY) x = __ldcs(av + i);
-        if (B_ALIGNED) y = ld_stream4(bb + 4 * i);
-        else y = make_float4(bb[4 * i], bb[4 * i + 1], bb[4 * i + 2], bb[4 * i + 3]);
+    // 2 x (a, b) 16-byte requests in flight per thread; pointer-bumping keeps the loop at ~32 registers
+    float4 *pa = reinterpret_cast<float4 *>(a + head) + tid;
+    const float *pb = b + head + 4 * tid;
+    const uint64_t step = nthreads;
+    auto ldb = [](const float *q) {
+        if (B_ALIGNED) return ld_stream4(q);
+        return make_float4(__ldcs(q), __ldcs(q + 1), __ldcs(q + 2), __ldcs(q + 3));
+    };
+    auto combine = [](const float4 &x, const float4 &y) {
         float4 r;
         r.x = apply_op<OP>(x.x, y.x);
         r.y = apply_op<OP>(x.y, y.y);
         r.z = apply_op<OP>(x.z, y.z);
         r.w = apply_op<OP>(x.w, y.w);
-        __stcs(av + i, r);
+        return r;
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint64_t i = tid;
+    for (; i + step < nvec; i += 2 * step) {
+        const float4 x0 = OP != WGB_OP_COPY ? __ldcs(pa) : zero;
+        const float4 x1 = OP != WGB_OP_COPY ? __ldcs(pa + step) : zero;
+        const float4 y0 = ldb(pb);
+        const float4 y1 = ldb(pb + 4 * step);
+        __stcs(pa, combine(x0, y0));
+        __stcs(pa + step, combine(x1, y1));
+        pa += 2 * step;
+        pb += 8 * step;
+    }
+    if (i < nvec) {
+        const float4 x0 = OP != WGB_OP_COPY ? __ldcs(pa) : zero;
+        __stcs(pa, combine(x0, ldb(pb)));
     }
 }
 
+// Resident CTAs per SM for a kernel (queried once): grids are sized to exactly one wave of resident CTAs, each
+// thread grid-strides over the rest, so there is no partial last wave and no wave hand-over bubble.
+template <typename K>
+static int resident_ctas(K kernel) {
+    static std::mutex mu;
+    static std::unordered_map<const void *, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find((const void *)kernel);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kThreads, 0) != cudaSuccess || n < 1) n = 4;
+    cache[(const void *)kernel] = n;
+    return n;
+}
 static int grid_for(wgb_ctx *ctx, uint64_t work_items_per_thread_unit, int ctas_per_sm) {
     const uint64_t max_ctas = (uint64_t)ctx->prop.multiProcessorCount * ctas_per_sm;
     uint64_t need = (work_items_per_thread_unit + kThreads - 1) / kThreads;
@@ -93,12 +104,16 @@ wgb_status launch_op_assign(wgb_pass *p, int op, float *a, const float *b, uint6
     if (head > n) head = (uint32_t)n;
     const bool b_aligned = (((uintptr_t)(b + head)) & 15u) == 0;
     const uint64_t nvec = (n - head) >> 2;
-    // grid: enough CTAs for >= 4 vectors per thread, capped at 8 resident CTAs per SM (a whole number of waves)
-    const int grid = grid_for(p->ctx, (nvec + 3) / 4 + 8, 8);
+    // grid: enough CTAs for >= 2 vectors per thread, capped at exactly one wave of resident CTAs
 #define LAUNCH(OPV)                                                                                       \
     case OPV:                                                                                             \
-        if (b_aligned) op_assign_kernel<OPV, true><<<grid, kThreads, 0, p->stream>>>(a, b, n, head);      \
-        else op_assign_kernel<OPV, false><<<grid, kThreads, 0, p->stream>>>(a, b, n, head);               \
+        if (b_aligned) {                                                                                  \
+            const int grid = grid_for(p->ctx, (nvec + 1) / 2 + 8, resident_ctas(op_assign_kernel<OPV, true>));   \
+            op_assign_kernel<OPV, true><<<grid, kThreads, 0, p->stream>>>(a, b, n, head);                 \
+        } else {                                                                                          \
+            const int grid = grid_for(p->ctx, (nvec + 1) / 2 + 8, resident_ctas(op_assign_kernel<OPV, false>));  \
+            op_assign_kernel<OPV, false><<<grid, kThreads, 0, p->stream>>>(a, b, n, head);                \
+        }                                                                                                 \
         break;
     switch (op) {
         LAUNCH(WGB_OP_ADD)
@@ -178,43 +193,45 @@ __device__ __forceinline__ float thread_partial(const float *__restrict__ x, con
     for (int q = 0; q < 4; ++q) acc[q] = red_init<OP>();
     if (tid < head) acc[0] = red_elem<OP>(acc[0], x[tid], DOT ? y[tid] : 0.f);
     if (tail0 + tid < n) acc[1] = red_elem<OP>(acc[1], x[tail0 + tid], DOT ? y[tail0 + tid] : 0.f);
-    const float *xb = x + head;
-    const float *yb = DOT ? y + head : nullptr;
-    constexpr int U = 4;
+    // pointer-bumping main loop: U independent 16-byte requests per stream in flight per thread
+    constexpr int U = DOT ? 2 : 4;
+    const float *px = x + head + 4 * tid;
+    const float *py = DOT ? y + head + 4 * tid : nullptr;
+    const uint64_t step4 = 4 * nthreads;
+    auto ldy = [](const float *q) {
+        if (Y_ALIGNED) return ld_stream4(q);
+        return make_float4(__ldcs(q), __ldcs(q + 1), __ldcs(q + 2), __ldcs(q + 3));
+    };
+    auto fold = [&](const float4 &a, const float4 &b) {
+        acc[0] = red_elem<OP>(acc[0], a.x, b.x);
+        acc[1] = red_elem<OP>(acc[1], a.y, b.y);
+        acc[2] = red_elem<OP>(acc[2], a.z, b.z);
+        acc[3] = red_elem<OP>(acc[3], a.w, b.w);
+    };
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
     uint64_t i = tid;
     for (; i + (U - 1) * nthreads < nvec; i += U * nthreads) {
         float4 a[U], b[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const uint64_t j = i + u * nthreads;
-            a[u] = ld_stream4(xb + 4 * j);
-            if (DOT) {
-                if (Y_ALIGNED) b[u] = ld_stream4(yb + 4 * j);
-                else b[u] = make_float4(__ldcs(yb + 4 * j), __ldcs(yb + 4 * j + 1), __ldcs(yb + 4 * j + 2), __ldcs(yb + 4 * j + 3));
-            }
+            a[u] = ld_stream4(px + u * step4);
+            b[u] = DOT ? ldy(py + u * step4) : zero;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            acc[0] = red_elem<OP>(acc[0], a[u].x, DOT ? b[u].x : 0.f);
-            acc[1] = red_elem<OP>(acc[1], a[u].y, DOT ? b[u].y : 0.f);
-            acc[2] = red_elem<OP>(acc[2], a[u].z, DOT ? b[u].z : 0.f);
-            acc[3] = red_elem<OP>(acc[3], a[u].w, DOT ? b[u].w : 0.f);
-        }
+        for (int u = 0; u < U; ++u) fold(a[u], b[u]);
+        px += U * step4;
+        if (DOT) py += U * step4;
     }
     for (; i < nvec; i += nthreads) {
-        const float4 a = ld_stream4(xb + 4 * i);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (DOT) b = make_float4(yb[4 * i], yb[4 * i + 1], yb[4 * i + 2], yb[4 * i + 3]);
-        acc[0] = red_elem<OP>(acc[0], a.x, b.x);
-        acc[1] = red_elem<OP>(acc[1], a.y, b.y);
-        acc[2] = red_elem<OP>(acc[2], a.z, b.z);
-        acc[3] = red_elem<OP>(acc[3], a.w, b.w);
+        fold(ld_stream4(px), DOT ? ldy(py) : zero);
+        px += step4;
+        if (DOT) py += step4;
     }
     return red_comb<OP>(red_comb<OP>(acc[0], acc[1]), red_comb<OP>(acc[2], acc[3]));
 }
 
 template <int OP, bool Y_ALIGNED>
-__global__ void __launch_bounds__(kThreads) reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
+__global__ void __launch_bounds__(kThreads, 4) reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                           uint64_t n, float *__restrict__ partials,
                                                           unsigned int *__restrict__ counter, float *__restrict__ result) {
     __shared__ float red[32];
@@ -251,7 +268,16 @@ wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, ui
     if (((uintptr_t)x & 3u) != 0) WGB_FAIL(WGB_ERR_INVALID, "reduce: buffer is not 4-byte aligned");
     wgb_ctx *ctx = p->ctx;
     const uint64_t nvec = n >> 2;
-    int grid = grid_for(ctx, (nvec + 7) / 8 + 1, 8);  // >= 8 vectors per thread before adding CTAs
+    int occ;
+    switch (op) {
+        case WGB_RED_MIN: occ = resident_ctas(reduce_kernel<WGB_RED_MIN, true>); break;
+        case WGB_RED_MAX: occ = resident_ctas(reduce_kernel<WGB_RED_MAX, true>); break;
+        case WGB_RED_SUM: occ = resident_ctas(reduce_kernel<WGB_RED_SUM, true>); break;
+        case WGB_RED_PROD: occ = resident_ctas(reduce_kernel<WGB_RED_PROD, true>); break;
+        case WGB_RED_SQNORM: occ = resident_ctas(reduce_kernel<WGB_RED_SQNORM, true>); break;
+        default: occ = resident_ctas(reduce_kernel<5, true>); break;
+    }
+    int grid = grid_for(ctx, (nvec + 7) / 8 + 1, occ);  // >= 8 vectors per thread before adding CTAs; one resident wave at most
     if ((size_t)grid > ctx->scratch.partials_floats) grid = (int)ctx->scratch.partials_floats;
     const uint32_t mis = (uint32_t)(((uintptr_t)x & 15u) >> 2);
     const uint64_t head = mis ? 4u - mis : 0u;
