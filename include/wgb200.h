@@ -274,6 +274,26 @@ wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_bu
                                 wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode f32_mode,
                                 int n_chunks);
 
+/* ---- fused GEMM + all-gather over peer memory (NVLink / NVSwitch), no NCCL on the data path ------------
+ * Every rank owns a "gathered" buffer that its peers map through CUDA IPC.  The GEMM epilogue stores each
+ * output element straight into the gathered buffer of every rank (local + P-1 peer stores over NVLink, overlapped
+ * tile by tile with the tensor-core main loop); the last CTA then publishes a completion flag to each peer.
+ * Set-up (once): create on every rank, export the 64-byte handle, exchange all handles through the launcher,
+ * connect.  Every rank must call wgb_gemm_row_sharded_fused the same number of times (it is a collective). */
+#define WGB_IPC_HANDLE_BYTES 64
+typedef struct wgb_peer_gather wgb_peer_gather;
+wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, wgb_peer_gather **out);
+wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out /* WGB_IPC_HANDLE_BYTES */);
+wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles /* nranks x WGB_IPC_HANDLE_BYTES */);
+/* The local gathered buffer as a wgb_buffer (owned by the group; valid until wgb_peer_gather_destroy). */
+wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out);
+wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg);
+/* Same contract and output layout as wgb_gemm_row_sharded, the all-gather fused into the GEMM epilogue. */
+wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg,
+                                      const wgb_buffer *m1_local, const wgb_view_shape *m1_local_shape,
+                                      const wgb_buffer *m2, const wgb_view_shape *m2_shape, wgb_dtype in_dtype,
+                                      wgb_dtype out_dtype, wgb_f32_mode f32_mode);
+
 #ifdef __cplusplus
 }
 #endif

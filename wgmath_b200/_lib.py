@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libwgebra_b200.so")
 OK, ERR_INVALID, ERR_DIM_MISMATCH, ERR_CUDA, ERR_UNSUPPORTED, ERR_OOM, ERR_NCCL, ERR_OOB, ERR_NO_DEVICE = range(9)
 F32, BF16 = 0, 1
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 
 class WgbError(RuntimeError):
@@ -84,6 +85,12 @@ def lib() -> ctypes.CDLL:
         "wgb_comm_init_rank": ([vp, ci, ci, vp], ci),
         "wgb_comm_destroy": ([vp], ci),
         "wgb_gemm_row_sharded": ([vp, ci, vp, vp, sp, vp, sp, ci, ci, ci, ci], ci),
+        "wgb_peer_gather_create": ([vp, ci, ci, sz, pvp], ci),
+        "wgb_peer_gather_export": ([vp, vp], ci),
+        "wgb_peer_gather_connect": ([vp, vp], ci),
+        "wgb_peer_gather_buffer": ([vp, pvp], ci),
+        "wgb_peer_gather_destroy": ([vp], ci),
+        "wgb_gemm_row_sharded_fused": ([vp, ci, vp, vp, sp, vp, sp, ci, ci, ci], ci),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(L, name)  # AttributeError here == the .so does not export what wgb200.h declares
@@ -102,7 +109,9 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemv",
             "wgb_op_assign", "wgb_reduce", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",
-            "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded"]
+            "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded", "wgb_peer_gather_create",
+            "wgb_peer_gather_export", "wgb_peer_gather_connect", "wgb_peer_gather_buffer", "wgb_peer_gather_destroy",
+            "wgb_gemm_row_sharded_fused"]
 
 
 def check(status: int) -> None:

@@ -223,4 +223,178 @@ wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_bu
     return WGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// fused GEMM + all-gather over peer memory
+// ------------------------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct wgb_peer_gather {
+    wgb_ctx *ctx = nullptr;
+    int nranks = 1, rank = 0;
+    size_t data_bytes = 0;          // gathered buffer size (256-byte multiple)
+    char *local = nullptr;          // cudaMalloc: [data_bytes][signal block]
+    char *peer[wgb::kMaxPeers] = {};
+    bool connected = false;
+    unsigned int epoch = 0;
+    wgb_buffer view;                // non-owning wgb_buffer over the local gathered buffer
+};
+
+namespace wgb {
+// signal block layout (u32 words): [0..8) ready[q], [16..24) done[q], [32] cta counter
+constexpr size_t kSignalBytes = 4096;
+constexpr int kReadyOff = 0, kDoneOff = 16, kCtaOff = 32;
+
+__global__ void signal_ready_kernel(FusedGather f) {
+    const int q = threadIdx.x;
+    if (q < f.nranks && q != f.rank) {
+        __threadfence_system();
+        // done_remote[q] points at rank q's done array; its ready array sits kDoneOff words before it
+        unsigned int *ready_q = f.done_remote[q] - kDoneOff + kReadyOff;
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_q + f.rank), "r"(f.epoch) : "memory");
+    }
+}
+__global__ void wait_done_kernel(const unsigned int *done_local, int nranks, int rank, unsigned int epoch) {
+    const int q = threadIdx.x;
+    if (q < nranks && q != rank) {
+        const long long t0 = clock64();
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(done_local + q) : "memory");
+            if (clock64() - t0 > 40000000000ll) __trap();
+        } while ((int)(v - epoch) < 0);
+    }
+    __threadfence_system();
+}
+}  // namespace wgb
+
+extern "C" {
+
+wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, wgb_peer_gather **out) {
+    if (!ctx || !out || nranks < 1 || nranks > wgb::kMaxPeers || rank < 0 || rank >= nranks)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_create: bad argument (at most %d ranks)", wgb::kMaxPeers);
+    DeviceGuard g(ctx->device);
+    wgb_peer_gather *pg = new wgb_peer_gather();
+    pg->ctx = ctx;
+    pg->nranks = nranks;
+    pg->rank = rank;
+    pg->data_bytes = (gathered_bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc((void **)&pg->local, pg->data_bytes + wgb::kSignalBytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete pg;
+        WGB_FAIL(WGB_ERR_OOM, "peer gather: allocation of %zu bytes failed: %s", gathered_bytes, cudaGetErrorString(e));
+    }
+    cudaMemset(pg->local + pg->data_bytes, 0, wgb::kSignalBytes);
+    cudaDeviceSynchronize();
+    pg->peer[rank] = pg->local;
+    pg->connected = nranks == 1;
+    pg->view.ctx = ctx;
+    pg->view.ptr = pg->local;
+    pg->view.bytes = gathered_bytes;
+    pg->view.owned = false;
+    pg->view.usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    *out = pg;
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == WGB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size changed");
+    if (!pg || !handle_out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(pg->ctx->device);
+    cudaIpcMemHandle_t h;
+    WGB_CUDA(cudaIpcGetMemHandle(&h, pg->local));
+    memcpy(handle_out, &h, sizeof h);
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles) {
+    if (!pg || !handles) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(pg->ctx->device);
+    for (int q = 0; q < pg->nranks; ++q) {
+        if (q == pg->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)q * WGB_IPC_HANDLE_BYTES, sizeof h);
+        void *ptr = nullptr;
+        WGB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        pg->peer[q] = (char *)ptr;
+    }
+    pg->connected = true;
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out) {
+    if (!pg || !out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    *out = &pg->view;
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
+    if (!pg) return WGB_OK;
+    DeviceGuard g(pg->ctx->device);
+    cudaStreamSynchronize(pg->ctx->stream);
+    for (int q = 0; q < pg->nranks; ++q)
+        if (q != pg->rank && pg->peer[q]) cudaIpcCloseMemHandle(pg->peer[q]);
+    if (pg->local) cudaFree(pg->local);
+    delete pg;
+    return WGB_OK;
+}
+
+wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg, const wgb_buffer *m1,
+                                      const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2, wgb_dtype in_dtype,
+                                      wgb_dtype out_dtype, wgb_f32_mode mode) {
+    if (!pass || !pg || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused: null argument");
+    if (!pg->connected) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused: peer group is not connected");
+    wgb_ctx *ctx = pass->ctx;
+    const int P = pg->nranks, rank = pg->rank;
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    if (s1->size[2] != 1 || s2->size[2] != 1) WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_row_sharded_fused: batched operands are not supported");
+    const uint32_t Mloc = tr ? s1->size[1] : s1->size[0];
+    const uint32_t K = tr ? s1->size[0] : s1->size[1];
+    const uint32_t N = s2->size[1];
+    if (K != s2->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 cols %u vs m2 rows %u)", K, s2->size[0]);
+    const size_t os = dtype_size(out_dtype), es = dtype_size(in_dtype);
+    const uint64_t panel = (uint64_t)Mloc * N;
+    if (panel * P * os > pg->view.bytes)
+        WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_gemm_row_sharded_fused: gathered output needs %llu bytes, group holds %zu",
+                 (unsigned long long)(panel * P * os), pg->view.bytes);
+    WGB_TRY(check_view(m1, *s1, es, "sharded gemm m1"));
+    WGB_TRY(check_view(m2, *s2, es, "sharded gemm m2"));
+    if (Mloc == 0 || N == 0) return WGB_OK;
+    DeviceGuard dg(ctx->device);
+
+    FusedGather f;
+    f.nranks = P;
+    f.rank = rank;
+    f.epoch = ++pg->epoch;
+    for (int q = 0; q < P; ++q) {
+        f.peer_c[q] = pg->peer[q];
+        f.done_remote[q] = reinterpret_cast<unsigned int *>(pg->peer[q] + pg->data_bytes) + wgb::kDoneOff;
+    }
+    unsigned int *sig = reinterpret_cast<unsigned int *>(pg->local + pg->data_bytes);
+    f.ready_local = sig + wgb::kReadyOff;
+    f.cta_counter = sig + wgb::kCtaOff;
+
+    if (P > 1) {
+        wgb::signal_ready_kernel<<<1, 32, 0, pass->stream>>>(f);   // "my queue has reached step `epoch`: you may overwrite my buffer"
+        count_launch(ctx);
+    }
+    GemmProblem g{};
+    g.fused = &f;
+    g.tr = tr;
+    g.M = Mloc; g.N = N; g.K = K; g.nmats = 1;
+    g.a = m1->ptr; g.b = m2->ptr; g.c = pg->local;
+    g.a_off = s1->offset; g.b_off = s2->offset;
+    g.c_off = (uint64_t)rank * panel;
+    g.lda = s1->stride; g.ldb = s2->stride; g.ldc = Mloc;
+    g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = panel;
+    g.in_dtype = in_dtype; g.out_dtype = out_dtype;
+    WGB_TRY(gemm_dispatch(pass, g, mode));
+    if (P > 1) {
+        wgb::wait_done_kernel<<<1, 32, 0, pass->stream>>>(sig + wgb::kDoneOff, P, rank, f.epoch);   // all panels have landed here
+        count_launch(ctx);
+        WGB_CUDA(cudaGetLastError());
+    }
+    return WGB_OK;
+}
+
 }  // extern "C"

@@ -143,7 +143,20 @@ wgb_status launch_fill_uniform(wgb_pass *p, void *base, const wgb_view_shape &s,
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
                        const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv);
 
+// Fused all-gather of the GEMM output over peer (NVLink-mapped) memory: the epilogue stores every output element
+// into the gathered buffer of every rank, then the last CTA publishes a completion flag to each peer.
+constexpr int kMaxPeers = 8;
+struct FusedGather {
+    int nranks = 1, rank = 0;
+    void *peer_c[kMaxPeers] = {};            // gathered buffer of rank q (peer mapping; [rank] is the local one)
+    unsigned int *ready_local = nullptr;     // ready_local[q]: rank q may be written into for epoch >= value
+    unsigned int *done_remote[kMaxPeers] = {};  // done array of rank q (we write entry [rank])
+    unsigned int *cta_counter = nullptr;     // local: CTAs finished (left at zero)
+    unsigned int epoch = 0;
+};
+
 struct GemmProblem {
+    const FusedGather *fused = nullptr;   // non-null: write C into every rank's gathered buffer (comm.cu)
     bool tr;               // out = tr(m1) * m2
     uint32_t M, N, K, nmats;
     const void *a;         // m1 base (element 0 of the buffer)

@@ -23,6 +23,8 @@ wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode) {
         if (s == WGB_OK) p->last_gemm_path = path;
         return s;
     }
+    if (g.fused && g.fused->nranks > 1)
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "fused all-gather needs the tensor-core GEMM path (TMA-eligible views, problem >= 96^3)");
     return launch_gemm_simt(p, g);
 }
 

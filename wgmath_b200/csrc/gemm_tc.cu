@@ -205,7 +205,22 @@ struct TcArgs {
     uint32_t full_tiles, split, kb_per_split, total_units;
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
+    // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
+    uint32_t npeers, my_rank, epoch;
+    char *dst[kMaxPeers];                     // where this rank's panel lives in rank d's gathered buffer
+    unsigned int *ready_local;                // ready_local[q] >= epoch: rank q's buffer may be overwritten
+    unsigned int *done_remote[kMaxPeers];     // rank q's done array; entry [my_rank] <- epoch when all stores are out
+    unsigned int *cta_counter;
 };
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 struct WorkUnit {
     uint32_t tile, kb0, kb1, split_idx;   // split_idx == 0xFFFFFFFF: whole tile
@@ -412,8 +427,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ===================================== epilogue: TMEM -> registers -> global ==============
         const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
-        TOut *cbase = reinterpret_cast<TOut *>(args.c);
         uint32_t acc = 0, acc_phase = 0;
+        if (args.npeers > 1) {
+            // fused all-gather: do not write into a peer before it has reached this step on its own queue
+            if (threadIdx.x == 128)
+                for (uint32_t r = 0; r < args.npeers; ++r)
+                    if (r != args.my_rank) {
+                        const long long t0 = clock64();
+                        while ((int)(ld_acquire_sys(args.ready_local + r) - args.epoch) < 0)
+                            if (clock64() - t0 > 20000000000ll) __trap();
+                    }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
             const WorkUnit wu = decode_unit(u, args);
             uint32_t bt, mt, nt;
@@ -425,7 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
-            TOut *crow = cbase + (uint64_t)bt * args.sc + row;
+            const uint64_t crow_off = (uint64_t)bt * args.sc + row;   // element offset of (row, col 0) inside a panel
             const bool row_ok = row < args.M;
             // split units park their f32 partial in the workspace: [slot][split][rank][col][row]
             const uint32_t slot = wu.tile - args.full_tiles;
@@ -450,10 +475,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
                 } else if (row_ok) {
+                    for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
+                        TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const uint32_t col = n0 + c * 32 + i;
-                        if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t col = n0 + c * 32 + i;
+                            if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                        }
                     }
                 }
             }
@@ -475,7 +503,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             float sum = 0.f;
                             for (uint32_t sp = 0; sp < args.split; ++sp)
                                 sum += __ldcg(wbase + (uint64_t)sp * CG * (BN * kBlockM) + (uint64_t)cc * kBlockM);
-                            store_out<TOut>(crow + (uint64_t)col * args.ldc, sum);
+                            for (uint32_t d = 0; d < args.npeers; ++d)
+                                store_out<TOut>(reinterpret_cast<TOut *>(args.dst[d]) + crow_off + (uint64_t)col * args.ldc, sum);
                         }
                     }
                     if (threadIdx.x == 128) args.counters[slot * CG + cta_rank] = 0u;
@@ -483,6 +512,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
+        }
+        if (args.npeers > 1) {
+            // all of this CTA's peer stores are out: make them visible system-wide, count the CTA, and let the last CTA of
+            // the grid publish "rank my_rank's panel is complete" to every peer
+            __threadfence_system();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 128) {
+                __threadfence();
+                const unsigned int prev = atomicAdd(args.cta_counter, 1u);
+                if (prev == gridDim.x - 1) {
+                    __threadfence_system();
+                    for (uint32_t r = 0; r < args.npeers; ++r)
+                        if (r != args.my_rank) st_release_sys(args.done_remote[r] + args.my_rank, args.epoch);
+                    *args.cta_counter = 0u;
+                }
+            }
         }
     }
 
@@ -813,6 +858,20 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
 
     TcArgs args{};
     args.c = (char *)g.c + g.c_off * dtype_size(g.out_dtype);
+    args.npeers = 1;
+    args.dst[0] = (char *)args.c;
+    if (g.fused && g.fused->nranks > 1) {
+        const FusedGather &f = *g.fused;
+        args.npeers = (uint32_t)f.nranks;
+        args.my_rank = (uint32_t)f.rank;
+        args.epoch = f.epoch;
+        for (int r = 0; r < f.nranks; ++r) {
+            args.dst[r] = (char *)f.peer_c[r] + g.c_off * dtype_size(g.out_dtype);
+            args.done_remote[r] = f.done_remote[r];
+        }
+        args.ready_local = f.ready_local;
+        args.cta_counter = f.cta_counter;
+    }
     args.ldc = g.ldc; args.sc = g.sc;
     args.M = g.M; args.N = g.N; args.K = g.K; args.nmats = g.nmats;
     args.tiles_m = (g.M + 128 * cg - 1) / (128 * cg);

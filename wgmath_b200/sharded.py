@@ -14,10 +14,10 @@ from typing import List, Tuple
 
 import numpy as np
 
-from ._lib import BF16, COMM_ID_BYTES, F32, check, lib
+from ._lib import BF16, COMM_ID_BYTES, F32, IPC_HANDLE_BYTES, check, lib
 from .linalg import F32Mode, GemmVariant
 from .shapes import ViewShape
-from .tensor import GpuTensor, GpuTensorView, as_view
+from .tensor import Buffer, GpuTensor, GpuTensorView, as_view
 
 _DTYPE_CODE = {"f32": F32, "bf16": BF16}
 
@@ -64,6 +64,50 @@ def init_comm(device, dist=None, rank: int = 0, world: int = 1) -> None:
     check(lib().wgb_comm_init_rank(device._h, world, rank, idbuf))
 
 
+class PeerGather:
+    """The gathered output buffer of every rank, mapped into every other rank through CUDA IPC, plus the flag block
+    the fused GEMM + all-gather kernel signals through (wgb_peer_gather_*).  `tensor` is the local gathered cube
+    [m_local, N, P] as a GpuTensor."""
+
+    def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16"):
+        self._device, self.rank, self.world = device, rank, world
+        nbytes = world * m_local * N * (2 if dtype == "bf16" else 4)
+        h = ctypes.c_void_p()
+        check(lib().wgb_peer_gather_create(device._h, world, rank, nbytes, ctypes.byref(h)))
+        self._h = h
+        mine = (ctypes.c_char * IPC_HANDLE_BYTES)()
+        check(lib().wgb_peer_gather_export(h, mine))
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(mine))
+        else:
+            handles = [bytes(mine)]
+        blob = (ctypes.c_char * (IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
+        check(lib().wgb_peer_gather_connect(h, blob))
+        bh = ctypes.c_void_p()
+        check(lib().wgb_peer_gather_buffer(h, ctypes.byref(bh)))
+        # the group owns the wgb_buffer: never destroyed from the Python side
+        self.tensor = GpuTensor((m_local, N, world), _BorrowedBuffer(device, bh, nbytes), dtype)
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().wgb_peer_gather_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _BorrowedBuffer(Buffer):
+    """A wgb_buffer owned by the library (wgb_peer_gather_buffer): never destroyed from Python."""
+
+    def __del__(self):
+        self._h = None
+
+
 class RowShardedGemm:
     """out_gathered[p] = (m1 * m2)[rows of rank p]  for every p, on every rank."""
 
@@ -78,6 +122,14 @@ class RowShardedGemm:
                                          b.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out_gathered.dtype],
                                          int(f32_mode), n_chunks))
 
+    def dispatch_fused(self, device, shapes, pass_, group: "PeerGather", m1_local, m2, variant=GemmVariant.Gemm,
+                       f32_mode=F32Mode.Auto) -> None:
+        """Same result in group.tensor, the all-gather fused into the GEMM epilogue (peer stores over NVLink)."""
+        m1, b = as_view(m1_local, 3), as_view(m2, 3)
+        s1, s2 = shapes.get(device, m1.shape()).to_c(), shapes.get(device, b.shape()).to_c()
+        check(lib().wgb_gemm_row_sharded_fused(pass_._h, int(variant), group._h, m1.buffer()._h, ctypes.byref(s1), b.buffer()._h,
+                                               ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[group.tensor.dtype], int(f32_mode)))
+
 
 def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
     """bench.py's N > 1 leg: bf16 (4096*P)^3, row-sharded, all-gather of C; returns the JSON fields."""
@@ -85,24 +137,37 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
     n = 4096 * ngpu
     m_local = n // ngpu
     ST = w.BufferUsages.STORAGE | w.BufferUsages.COPY_SRC | w.BufferUsages.COPY_DST
-    init_comm(dev, dist, rank, ngpu)
+    import os
+    mode = os.environ.get("WGB_SHARD_MODE", "fused")                     # "fused" (peer stores) or "nccl"
     a = w.TensorBuilder.matrix(m_local, n, ST).build(dev, "bf16")       # my row block of A
     b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")             # B replicated
-    c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
+    group = None
+    if mode == "fused":
+        group = PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16")
+        c = group.tensor
+    else:
+        init_comm(dev, dist, rank, ngpu)
+        c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
     enc = dev.create_command_encoder()
     with enc.compute_pass("init", None) as p:
         w.fill_uniform(dev, p, a, O.SEED_BASE + 1, row0=rank * m_local)  # element (i, j) independent of the sharding
         w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
     dev.poll_wait()
     op = RowShardedGemm(dev)
-    sec, launches = timed(lambda p, i: op.dispatch(dev, shapes, p, c, a, b), args.steps, args.warmup)
+    if group is not None:
+        step_fn = lambda p, i: op.dispatch_fused(dev, shapes, p, group, a, b)    # noqa: E731
+    else:
+        step_fn = lambda p, i: op.dispatch(dev, shapes, p, c, a, b)             # noqa: E731
+    sec, launches = timed(step_fn, args.steps, args.warmup)
     flops = 2.0 * n * n * n
     value = flops * args.steps / sec / 1e12
     ms_step = sec * 1e3 / args.steps
     long_run = sec > 1.0
     peak = (peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]) * ngpu
     comm_bytes = (ngpu - 1) * m_local * n * 2
-    roof = {"bound": "tensor", "kernel": "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)",
+    kname = ("gemm_tc<bf16> (tcgen05) with the all-gather of C fused into the epilogue (peer stores over NVLink)" if group is not None
+             else "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)")
+    roof = {"bound": "tensor", "kernel": kname,
             "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
             "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
             "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
@@ -120,12 +185,17 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
     def e2e_step(p, i):
         check(L.wgb_buffer_write(dev._h, a.buffer()._h, 0, ha, abytes))
         check(L.wgb_buffer_write(dev._h, b.buffer()._h, 0, hb, bbytes))
-        op.dispatch(dev, shapes, p, c, a, b)
+        step_fn(p, i)
         check(L.wgb_buffer_read(dev._h, c.buffer()._h, 0, hc, cbytes))
     e2e_sec, _ = timed(e2e_step, e2e_steps, 1)
     for h in (ha, hb, hc):
         L.wgb_host_free(h)
     e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (abytes + bbytes) * ngpu,
            "d2h_bytes_per_step": cbytes * ngpu, "steps": e2e_steps}
-    lib().wgb_comm_destroy(dev._h)
+    if dist is not None:
+        dist.barrier()
+    if group is not None:
+        group.close()
+    else:
+        lib().wgb_comm_destroy(dev._h)
     return value, ms_step, launches, roof, e2e, "bf16"
