@@ -212,6 +212,16 @@ wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
                        const wgb_view_shape *m1_shape, const wgb_buffer *m2,
                        const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_dtype out_dtype,
                        wgb_f32_mode f32_mode);
+/* Host-buffer GEMM: out_host = m1_host * m2_host (or tr(m1_host) * m2_host) with dense column-major host matrices
+ * (leading dimensions = row counts).  Equivalent to build_init(m1), build_init(m2), dispatch, read — the sequence of
+ * the reference's own tests (gemm.rs:156-193) — but pipelined: m2 is uploaded and the product downloaded in column
+ * panels, so the PCIe download of panel j overlaps the upload of panel j+1 and the tensor-core work hides under both.
+ * Blocking (returns when out_host is complete).  Pinned host memory (wgb_host_alloc) is needed for the overlap;
+ * pageable memory works but serialises.  n_panels <= 0 selects the default. */
+wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                         const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                         wgb_f32_mode f32_mode, int n_panels);
+
 /* Which kernel family the last wgb_gemm* call on this pass dispatched to:
  * 0 none, 1 SIMT FFMA, 2 tcgen05 bf16, 3 tcgen05 tf32, 4 tcgen05 3xtf32. */
 wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);

@@ -489,6 +489,27 @@ def test_cfg2_f32_gemm_large_sampled(gpu, shapes):
     assert rel_err(got[rows, :], A @ B) < F32_TOL
 
 
+@pytest.mark.parametrize("tr", [False, True])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_gemm_host_buffers_pipelined(gpu, shapes, tr, dtype):
+    """wgb_gemm_host == build_init + dispatch + read (the reference tests' sequence, gemm.rs:156-193)."""
+    M, N, K = 384, 1100, 520          # N spans several column panels, the last one ragged
+    ar, ac = (K, M) if tr else (M, K)
+    A, B = O.uniform(SEED_A, ar, ac), O.uniform(SEED_B, K, N)
+    if dtype == "bf16":
+        A, B = O.to_bf16_rne(A), O.to_bf16_rne(B)
+        ha, hb = O.bf16_bits(A), O.bf16_bits(B)
+    else:
+        ha, hb = A, B
+    out = np.full(M * N, -1.0, np.float32)
+    gemm = w.Gemm.from_device(gpu.device())
+    gemm.dispatch_host(gpu.device(), M, N, K, out, ha, hb, w.GemmVariant.GemmTr if tr else w.GemmVariant.Gemm,
+                       in_dtype=dtype, out_dtype="f32", n_panels=3)
+    a = cm(A, ar, ac).astype(np.float64)
+    ref = (a.T if tr else a) @ cm(B, K, N).astype(np.float64)
+    assert rel_err(cm(out, M, N), ref) < (1e-4 if dtype == "bf16" else F32_TOL)
+
+
 def test_timestamps_and_launch_counter(gpu, shapes):
     dev = gpu.device()
     ts = w.GpuTimestamps.new(dev, 8)

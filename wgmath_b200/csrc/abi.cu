@@ -540,6 +540,61 @@ wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
     return gemm_dispatch(pass, g, mode);
 }
 
+wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                         const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
+                         int n_panels) {
+    if (!ctx || !out_host || !m1_host || !m2_host) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_host: null argument");
+    if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_host: unknown variant");
+    if (M == 0 || N == 0) return WGB_OK;
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    const size_t es = dtype_size(in_dtype), os = dtype_size(out_dtype);
+    const size_t a_bytes = (size_t)M * K * es, b_bytes = (size_t)K * N * es, c_bytes = (size_t)M * N * os;
+    if ((uint64_t)M * K > 0xFFFFFFFFull || (uint64_t)K * N > 0xFFFFFFFFull || (uint64_t)M * N > 0xFFFFFFFFull)
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_host: operands exceed u32 element indexing");
+    DeviceGuard dg(ctx->device);
+    void *w = nullptr;
+    const size_t a_off = 0, b_off = (a_bytes + 255) & ~(size_t)255, c_off = (b_off + b_bytes + 255) & ~(size_t)255;
+    WGB_TRY(workspace_reserve(ctx, 3, c_off + c_bytes, &w));
+    char *dA = (char *)w + a_off, *dB = (char *)w + b_off, *dC = (char *)w + c_off;
+    // column panels: whole 256-column tiles
+    uint32_t np = n_panels > 0 ? (uint32_t)n_panels : 8u;
+    uint32_t width = (N + np - 1) / np;
+    width = (width + 255u) & ~255u;
+    np = (N + width - 1) / width;
+    static thread_local std::vector<cudaEvent_t> evs;
+    while (evs.size() < np + 1) {
+        cudaEvent_t e;
+        WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        evs.push_back(e);
+    }
+    wgb_pass pass;
+    pass.ctx = ctx;
+    pass.stream = ctx->stream;
+    if (K > 0) WGB_CUDA(cudaMemcpyAsync(dA, m1_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t j = 0; j < np; ++j) {
+        const uint32_t n0 = j * width, nc = (N - n0) < width ? (N - n0) : width;
+        if (K > 0)
+            WGB_CUDA(cudaMemcpyAsync(dB + (size_t)n0 * K * es, (const char *)m2_host + (size_t)n0 * K * es, (size_t)nc * K * es,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+        GemmProblem g{};
+        g.tr = tr;
+        g.M = M; g.N = nc; g.K = K; g.nmats = 1;
+        g.a = dA; g.b = dB; g.c = dC;
+        g.a_off = 0; g.b_off = (uint64_t)n0 * K; g.c_off = (uint64_t)n0 * M;
+        g.lda = tr ? K : M; g.ldb = K; g.ldc = M;
+        g.sa = (uint64_t)M * K; g.sb = (uint64_t)K * N; g.sc = (uint64_t)M * N;
+        g.in_dtype = in_dtype; g.out_dtype = out_dtype;
+        WGB_TRY(gemm_dispatch(&pass, g, mode));
+        WGB_CUDA(cudaEventRecord(evs[j], ctx->stream));
+        WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, evs[j], 0));      // download panel j while panel j+1 uploads
+        WGB_CUDA(cudaMemcpyAsync((char *)out_host + (size_t)n0 * M * os, dC + (size_t)n0 * M * os, (size_t)nc * M * os,
+                                 cudaMemcpyDeviceToHost, ctx->comm_stream));
+    }
+    WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return WGB_OK;
+}
+
 wgb_status wgb_gemm(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
                     const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2) {
     return wgb_gemm_ex(pass, variant, out, so, m1, s1, m2, s2, WGB_F32, WGB_F32, WGB_F32_AUTO);

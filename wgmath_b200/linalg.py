@@ -81,6 +81,17 @@ class Gemm:
                                 m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode)))
 
 
+    def dispatch_host(self, device, M: int, N: int, K: int, out_host, m1_host, m2_host, variant=GemmVariant.Gemm,
+                      in_dtype: str = "f32", out_dtype: str = "f32", f32_mode=None, n_panels: int = 0) -> None:
+        """Host-buffer GEMM (wgb_gemm_host): upload, multiply and download pipelined by column panel.  `*_host` are
+        numpy arrays or raw host pointers (ctypes.c_void_p) of dense column-major matrices.  Blocking."""
+        def ptr(x):
+            return x if isinstance(x, ctypes.c_void_p) else x.ctypes.data_as(ctypes.c_void_p)
+        mode = self.f32_mode if f32_mode is None else f32_mode
+        check(lib().wgb_gemm_host(device._h, int(variant), M, N, K, ptr(out_host), ptr(m1_host), ptr(m2_host),
+                                  _DTYPE_CODE[in_dtype], _DTYPE_CODE[out_dtype], int(mode), n_panels))
+
+
 class Gemv:
     """gemv.rs:9-137."""
 
