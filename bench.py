@@ -348,7 +348,7 @@ def run_extras(w, O, gpu, shapes, timed, peaks):
     gemm = w.Gemm.from_device(dev)
     # ---- f32 GEMM sweep
     for n in (256, 512, 1024, 2048, 4096, 8192):
-        nsets = max(1, min(8, int(np.ceil(L2_BYTES * 1.5 / (3 * n * n * 4)))))
+        nsets = max(1, min(256, int(np.ceil(L2_BYTES * 1.5 / (3 * n * n * 4)))))   # rotating operand sets > L2
         sets = []
         enc = dev.create_command_encoder()
         with enc.compute_pass("init", None) as p:

@@ -170,6 +170,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+        "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+        "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // descriptors (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor / InstrDescriptor)
@@ -245,6 +257,10 @@ constexpr int kATileBytes = kBlockM * kRowBytes;  // 16 KiB, both major-nesses
 constexpr int kNumThreads = 256;
 constexpr int kSuperM = 8;          // m-tiles per rasterisation group
 constexpr int kSmemLimit = 227 * 1024;
+// Tensor-core accumulation into TMEM truncates (measured on B200: relative bias ~ -1.1e-8 per k for 3xTF32 on U[0,1)
+// data, i.e. -2.2e-5 at K = 2048).  The parity-gated 3xTF32 path therefore accumulates at most kChunkKb k-blocks
+// (256 k) per TMEM chain and the epilogue adds the chunks in f32 round-to-nearest into a running sum kept in TMEM.
+constexpr int kChunkKb = 8;
 
 template <int BN, int PASSES, int CG>
 struct TcCfg {
@@ -256,7 +272,9 @@ struct TcCfg {
     static constexpr int STAGES_RAW = (kSmemLimit - BAR_BYTES - 1024) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-    static constexpr int TMEM_COLS = 2 * BN;                          // two accumulator stages (256 or 512: powers of 2)
+    // 3xTF32 keeps a third TMEM region: the running f32 sum of K chunks (see CHUNK_KB)
+    static constexpr int TMEM_COLS = PASSES == 3 ? 512 : 2 * BN;      // two accumulator stages (+ running sum); power of 2
+    static_assert(PASSES != 3 || 3 * BN <= 512, "3xTF32 needs two accumulator stages and a running sum in 512 TMEM columns");
     static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
@@ -296,6 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int A_ATOM_BYTES = BLOCK_K * kRowBytes;     // one atom column: BLOCK_K rows of 128 B
     constexpr uint32_t IDESC = make_idesc(KIND, A_MN, kBlockM * CG, BN);
     constexpr int STAGES = Cfg::STAGES;
+    constexpr bool CHUNKED = PASSES == 3;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle
@@ -385,43 +404,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
                 const WorkUnit wu = decode_unit(u, args);
-                mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
-                for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
-                    mbar_wait(smem_u32(full_bar + stage), phase);
+                uint32_t kb = wu.kb0;
+                while (kb < wu.kb1) {
+                    // one TMEM accumulation chain: the whole K range, or kChunkKb k-blocks for 3xTF32
+                    const uint32_t chain_begin = kb;
+                    const uint32_t chain_end = CHUNKED ? min(wu.kb1, kb + (uint32_t)kChunkKb) : wu.kb1;
+                    mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t sa_hi = sbase, sa_lo = sbase + kATileBytes;
-                    const uint32_t sb_hi = sbase + Cfg::SETS * kATileBytes, sb_lo = sb_hi + Cfg::B_TILE_BYTES;
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (; kb < chain_end; ++kb) {
+                        mbar_wait(smem_u32(full_bar + stage), phase);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                        const uint32_t sa_hi = sbase, sa_lo = sbase + kATileBytes;
+                        const uint32_t sb_hi = sbase + Cfg::SETS * kATileBytes, sb_lo = sb_hi + Cfg::B_TILE_BYTES;
 #pragma unroll
-                    for (int j = 0; j < K_STEPS; ++j) {
-                        // K advance inside the swizzled tile: 32 B (K-major) or UMMA_K rows of 128 B (MN-major)
-                        const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
-                        const uint32_t b_off = j * 32;
-                        const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
-                        // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
-                        constexpr bool A32 = A_MN && KIND == 1;
-                        const uint32_t a_sbo = A32 ? 512 : 1024, a_lt = A32 ? 1 : 2;
-                        const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, a_sbo, a_lt);
-                        const uint64_t db_hi = make_smem_desc(sb_hi + b_off, 16, sbo);
-                        const uint32_t first = (kb == wu.kb0 && j == 0) ? 0u : 1u;
-                        if (PASSES == 3) {
-                            const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
-                            const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
-                            umma<KIND, CG>(d_tmem, da_lo, db_hi, IDESC, first);   // small terms first
-                            umma<KIND, CG>(d_tmem, da_hi, db_lo, IDESC, 1u);
-                            umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, 1u);
-                        } else {
-                            umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, first);
+                        for (int j = 0; j < K_STEPS; ++j) {
+                            // K advance inside the swizzled tile: 32 B (K-major) or UMMA_K rows of 128 B (MN-major)
+                            const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
+                            const uint32_t b_off = j * 32;
+                            const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
+                            // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
+                            constexpr bool A32 = A_MN && KIND == 1;
+                            const uint32_t a_sbo = A32 ? 512 : 1024, a_lt = A32 ? 1 : 2;
+                            const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, a_sbo, a_lt);
+                            const uint64_t db_hi = make_smem_desc(sb_hi + b_off, 16, sbo);
+                            const uint32_t first = (kb == chain_begin && j == 0) ? 0u : 1u;
+                            if (PASSES == 3) {
+                                const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
+                                const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
+                                umma<KIND, CG>(d_tmem, da_lo, db_hi, IDESC, first);   // small terms first
+                                umma<KIND, CG>(d_tmem, da_hi, db_lo, IDESC, 1u);
+                                umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, 1u);
+                            } else {
+                                umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, first);
+                            }
                         }
+                        umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
+                        if (kb + 1 == chain_end) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
-                    if (kb + 1 == wu.kb1) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1;
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
             }
         }
     } else if (warp >= 4) {
@@ -439,6 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
+        const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
             const WorkUnit wu = decode_unit(u, args);
             uint32_t bt, mt, nt;
@@ -447,43 +473,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t row = mt * (kBlockM * CG) + cta_rank * kBlockM + row_in_cta;
             const uint32_t n0 = nt * BN;
             const bool split_unit = wu.split_idx != 0xFFFFFFFFu;
-            mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((q * 32u) << 16) + acc * BN;
             const uint64_t crow_off = (uint64_t)bt * args.sc + row;   // element offset of (row, col 0) inside a panel
             const bool row_ok = row < args.M;
             // split units park their f32 partial in the workspace: [slot][split][rank][col][row]
             const uint32_t slot = wu.tile - args.full_tiles;
             float *wsp = split_unit ? args.ws + (((uint64_t)slot * args.split + wu.split_idx) * CG + cta_rank) * (uint64_t)(BN * kBlockM) + row_in_cta
                                     : nullptr;
-            uint32_t v[2][32];
-            tmem_ld32(taddr, v[0]);
+            const uint32_t nkb = wu.kb1 - wu.kb0;
+            const uint32_t nchains = CHUNKED ? (nkb + kChunkKb - 1) / kChunkKb : 1u;
+            for (uint32_t ch = 0; ch < nchains; ++ch) {
+                const bool final_chain = ch + 1 == nchains;
+                mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = lane_base + acc * BN;
+                const uint32_t tsum = lane_base + 2 * BN;   // running sum of the chains (3xTF32 only)
+                uint32_t v[2][32];
+                tmem_ld32(taddr, v[0]);
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) {
-                tmem_ld_wait();
-                if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-                else {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 2) mbar_arrive_cluster(smem_u32(tmem_empty_bar + acc), 0);
-                        else mbar_arrive(smem_u32(tmem_empty_bar + acc));
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t sprev[32];
+                    if (CHUNKED && ch > 0) tmem_ld32(tsum + c * 32, sprev);
+                    tmem_ld_wait();
+                    if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    else {
+                        // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_cluster(smem_u32(tmem_empty_bar + acc), 0);
+                            else mbar_arrive(smem_u32(tmem_empty_bar + acc));
+                        }
                     }
-                }
-                if (split_unit) {
+                    if (CHUNKED && ch > 0) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
-                } else if (row_ok) {
-                    for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
-                        TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
+                        for (int i = 0; i < 32; ++i) v[c & 1][i] = __float_as_uint(__uint_as_float(v[c & 1][i]) + __uint_as_float(sprev[i]));
+                    }
+                    if (CHUNKED && !final_chain) {
+                        tmem_st32(tsum + c * 32, v[c & 1]);
+                    } else if (split_unit) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const uint32_t col = n0 + c * 32 + i;
-                            if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                        for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
+                    } else if (row_ok) {
+                        for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
+                            TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const uint32_t col = n0 + c * 32 + i;
+                                if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                            }
                         }
                     }
                 }
+                if (CHUNKED && !final_chain) tmem_st_wait();
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
             }
             if (split_unit) {
                 // last CTA to park its partial folds all of them in split order (deterministic) and writes the tile
@@ -496,22 +539,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (last) {
                     __threadfence();
                     const float *wbase = args.ws + ((uint64_t)slot * args.split * CG + cta_rank) * (uint64_t)(BN * kBlockM) + row_in_cta;
-                    if (row_ok) {
-                        for (uint32_t cc = 0; cc < (uint32_t)BN; ++cc) {
-                            const uint32_t col = n0 + cc;
-                            if (col >= args.N) break;
-                            float sum = 0.f;
-                            for (uint32_t sp = 0; sp < args.split; ++sp)
-                                sum += __ldcg(wbase + (uint64_t)sp * CG * (BN * kBlockM) + (uint64_t)cc * kBlockM);
-                            for (uint32_t d = 0; d < args.npeers; ++d)
-                                store_out<TOut>(reinterpret_cast<TOut *>(args.dst[d]) + crow_off + (uint64_t)col * args.ldc, sum);
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        float sum[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[i] = 0.f;
+                        for (uint32_t sp = 0; sp < args.split; ++sp) {
+                            const float *src = wbase + (uint64_t)sp * CG * (BN * kBlockM) + (uint64_t)(c * 32) * kBlockM;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) sum[i] += __ldcg(src + (uint64_t)i * kBlockM);   // 32 loads in flight
                         }
+                        if (row_ok)
+                            for (uint32_t d = 0; d < args.npeers; ++d) {
+                                TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const uint32_t col = n0 + c * 32 + i;
+                                    if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, sum[i]);
+                                }
+                            }
                     }
                     if (threadIdx.x == 128) args.counters[slot * CG + cta_rank] = 0u;
                 }
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
         }
         if (args.npeers > 1) {
             // all of this CTA's peer stores are out: make them visible system-wide, count the CTA, and let the last CTA of
@@ -713,12 +763,17 @@ wgb_status launch_cfg(wgb_pass *p, const CUtensorMap &ta, const CUtensorMap &tal
 template <int KIND, bool A_MN, int PASSES, typename TOut>
 wgb_status launch_sel(wgb_pass *p, int bn, int cg, const CUtensorMap &ta, const CUtensorMap &talo, const CUtensorMap &tb,
                       const CUtensorMap &tblo, const TcArgs &args) {
-    if (cg == 2) {
-        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
-        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+    if constexpr (PASSES == 3) {   // 3xTF32: BLOCK_N = 128 only (two accumulator stages + running sum in TMEM)
+        if (cg == 2) return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+    } else {
+        if (cg == 2) {
+            if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+            return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+        }
+        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
     }
-    if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
-    return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
 }
 
 }  // namespace
@@ -780,7 +835,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     if (f32) passes = (mode == WGB_F32_TF32) ? 1 : 3;
     // A non-transposed f32 m1 is an MN-major 32-bit operand.  "direct": TMA 32-byte-atom swizzle + BASE32B descriptor.
     // "transpose": the prep kernel writes tr(m1) dense and the K-major kernel variant runs (always valid).
-    const bool mn_direct = env_int("WGB_TF32_MN_DIRECT", 0) != 0;
+    const bool mn_direct = env_int("WGB_TF32_MN_DIRECT", 1) != 0;   // validated on B200: direct is the default
     const bool transpose_a = f32 && !g.tr && !mn_direct;
     if (f32 && passes == 1 && !transpose_a &&
         !(aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4))) {
@@ -798,7 +853,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     const size_t es = f32 ? 4 : 2;
     const int cg = env_int("WGB_TC_CG", 2) == 1 ? 1 : 2;
     const uint32_t sms_total = (uint32_t)ctx->prop.multiProcessorCount;
-    const int bn = pick_bn(g.M, g.N, g.nmats, cg, sms_total);
+    const int bn = passes == 3 ? 128 : pick_bn(g.M, g.N, g.nmats, cg, sms_total);
     const uint32_t block_k = 128 / (uint32_t)es;
 
     bool tr = g.tr;
