@@ -58,8 +58,11 @@ def main():
                 w.lib().wgb_comm_destroy(dev._h)
             else:
                 group.close()
-        same = np.array_equal(results["nccl"], results["fused"])
-        full = sharded.panels_to_matrix(O.bf16_from_bits(results["fused"]).astype(np.float64), m_local, N, world)
+        # the two paths may pick different split-K / chunk shapes, so they agree to rounding, not bitwise
+        fa, fb = O.bf16_from_bits(results["nccl"]).astype(np.float64), O.bf16_from_bits(results["fused"]).astype(np.float64)
+        same = bool(np.max(np.abs(fa - fb) / np.abs(fb)) < 1e-2)
+        full = sharded.panels_to_matrix(fb, m_local, N, world)
+        full_nccl = sharded.panels_to_matrix(fa, m_local, N, world)
         # float64 reference on sampled rows of the *global* product (every rank checks rows owned by every rank)
         rows = np.array(sorted({0, 1, m_local - 1, m_local % M, M // 2, M - 1, (7 * m_local + 13) % M}))
         if tr:
@@ -67,10 +70,10 @@ def main():
         else:
             a_rows = np.stack([O.to_bf16_rne(O.uniform(O.SEED_BASE + 1, 1, K, row0=int(r))) for r in rows]).astype(np.float64)
         ref = a_rows @ b_all.reshape(N, K).T.astype(np.float64)
-        err = float(np.max(np.abs(full[rows] - ref) / np.abs(ref)))
+        err = max(float(np.max(np.abs(full[rows] - ref) / np.abs(ref))), float(np.max(np.abs(full_nccl[rows] - ref) / np.abs(ref))))
         good = same and err < 1e-2
         ok &= good
-        print(f"[rank {rank}] {M}x{N}x{K} tr={int(tr)} world={world}: nccl==fused {same}, rel err vs f64 {err:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}] {M}x{N}x{K} tr={int(tr)} world={world}: nccl~fused {same}, rel err vs f64 {err:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
