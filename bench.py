@@ -241,6 +241,32 @@ def main_gpu(args):
             sec = float(t.item())
         return sec, dev.launch_count() - n0
 
+    def timed_graph(fn, steps, warmup):
+        """Like timed(), but the `steps` dispatches are recorded once into a CUDA graph (wgb_graph_*) and replayed with one
+        launch, so kernels of a few microseconds are not hidden behind the Python/ctypes cost of issuing them."""
+        e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+        check(L.wgb_event_create(dev._h, ctypes.byref(e0)))
+        check(L.wgb_event_create(dev._h, ctypes.byref(e1)))
+        enc = dev.create_command_encoder()
+        with enc.compute_pass("warm", None) as p:
+            for i in range(warmup):
+                fn(p, i)
+        with dev.capture() as cap:
+            with enc.compute_pass("rec", None) as p:
+                for i in range(steps):
+                    fn(p, warmup + i)
+        barrier_sync()
+        with sampler:
+            check(L.wgb_event_record(e0, None))
+            cap.graph.launch()
+            check(L.wgb_event_record(e1, None))
+            barrier_sync()
+        ms = ctypes.c_float()
+        check(L.wgb_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+        L.wgb_event_destroy(e0)
+        L.wgb_event_destroy(e1)
+        return ms.value / 1e3, 0
+
     gemm = w.Gemm.from_device(dev)
     extra = {}
 
@@ -316,7 +342,7 @@ def main_gpu(args):
                                   "call": "wgb_buffer_write x2 + wgb_gemm_ex + wgb_buffer_read"}}
         if not args.no_extras:
             sets.clear()
-            extra = run_extras(w, O, gpu, shapes, timed, peaks)
+            extra = run_extras(w, O, gpu, shapes, timed, peaks, timed_graph)
         cpu_tf, cores, desc, _, _ = cpu_gemm_sample(10.0)
         cpu = {"value": cpu_tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": desc}
     else:
@@ -341,7 +367,7 @@ def main_gpu(args):
     return 0
 
 
-def run_extras(w, O, gpu, shapes, timed, peaks):
+def run_extras(w, O, gpu, shapes, timed, peaks, timed_graph):
     """The other BASELINE configs, each timed like the headline: configs[1] f32 GEMM sweep, configs[3] GEMV +
     level-1 GB/s.  Operands larger than L2 (or rotated) so no run is served from cache."""
     dev = gpu.device()
@@ -370,7 +396,7 @@ def run_extras(w, O, gpu, shapes, timed, peaks):
                 gemm.dispatch_generic(dev, shapes, p, c, a, b, w.GemmVariant.Gemm, f32_mode=mode)
                 if not path:
                     path.append(p.last_gemm_path())
-            sec, _ = timed(step, steps, 3)
+            sec, _ = timed_graph(step, steps, 3)          # device time of `steps` back-to-back GEMMs, one graph launch
             tf = 2.0 * n ** 3 * steps / sec / 1e12
             # TF32 dense peak is half the bf16 peak; 3xTF32 issues three MMAs per product
             peak = peaks["bf16_tflops"] / 2 / (3 if name == "3xtf32" else 1)

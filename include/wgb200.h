@@ -170,6 +170,16 @@ wgb_status wgb_pass_end(wgb_pass *pass);
 /* queue.submit(encoder.finish()): CUDA work is already in flight, this only flushes. */
 wgb_status wgb_submit(wgb_ctx *ctx);
 
+/* Record-once / replay-many (CUDA graphs): between capture_begin and capture_end every dispatch on the context's
+ * queue is recorded instead of executed (like recording a wgpu command buffer); wgb_graph_launch replays the whole
+ * recorded sequence with one launch, removing per-dispatch host cost for chains of small kernels.  Workspaces
+ * must be warm (run the same sequence once before capturing): an allocation during capture fails with WGB_ERR_CUDA. */
+typedef struct wgb_graph wgb_graph;
+wgb_status wgb_graph_capture_begin(wgb_ctx *ctx);
+wgb_status wgb_graph_capture_end(wgb_ctx *ctx, wgb_graph **out);
+wgb_status wgb_graph_launch(wgb_graph *graph);
+wgb_status wgb_graph_destroy(wgb_graph *graph);
+
 /* ------------------------------------------------------------------ buffers ---------- */
 /* tensor.rs:112-129 TensorBuilder::build: uninitialised buffer of `bytes` bytes. */
 wgb_status wgb_buffer_create(wgb_ctx *ctx, size_t bytes, uint32_t usage, wgb_buffer **out);

@@ -510,6 +510,34 @@ def test_gemm_host_buffers_pipelined(gpu, shapes, tr, dtype):
     assert rel_err(cm(out, M, N), ref) < (1e-4 if dtype == "bf16" else F32_TOL)
 
 
+def test_graph_capture_replays_a_dispatch_chain(gpu, shapes):
+    """wgb_graph_*: record gemm -> op_assign -> reduce once, replay it, same result as the eager sequence."""
+    dev = gpu.device()
+    n = 256
+    A, B, bias = O.uniform(SEED_A, n, n), O.uniform(SEED_B, n, n), O.uniform(SEED_V, n * n)
+    ta, tb, tbias = upload(gpu, A, (n, n)), upload(gpu, B, (n, n)), upload(gpu, bias, (n * n,))
+    tc = w.TensorBuilder.matrix(n, n, STORAGE).build(dev)
+    res = w.TensorBuilder.scalar(STORAGE).build(dev)
+    gemm, add, rsum = w.Gemm.from_device(dev), w.OpAssign.new(dev, w.OpAssignVariant.Add), w.Reduce.new(dev, w.ReduceOp.Sum)
+
+    def chain(p):
+        gemm.dispatch(dev, shapes, p, tc, ta, tb)
+        add.dispatch(dev, shapes, p, tc.reshape((n * n,)), tbias)
+        rsum.dispatch(dev, shapes, p, tc.reshape((n * n,)), res)
+    run_pass(gpu, chain)                       # eager (also warms the workspaces)
+    eager_c, eager_r = tc.read(), res.read()[0]
+    with dev.capture() as cap:
+        run_pass(gpu, chain)
+    run_pass(gpu, lambda p: w.OpAssign.new(dev, w.OpAssignVariant.Copy).dispatch(dev, shapes, p, tc.reshape((n * n,)), tbias))  # clobber
+    n0 = dev.launch_count()
+    cap.graph.launch()
+    np.testing.assert_array_equal(tc.read(), eager_c)
+    assert res.read()[0] == eager_r
+    assert dev.launch_count() - n0 >= 3
+    ref = (cm(A, n, n).astype(np.float64) @ cm(B, n, n).astype(np.float64)).T.reshape(-1) + bias
+    assert rel_err(eager_c, ref) < F32_TOL
+
+
 def test_timestamps_and_launch_counter(gpu, shapes):
     dev = gpu.device()
     ts = w.GpuTimestamps.new(dev, 8)

@@ -4,7 +4,7 @@ The package holds only what the hot path needs: `csrc/` (CUDA kernels + the C AB
 include/wgb200.h, built into libwgebra_b200.so) and this host-side mirror of the reference's
 Rust interface (wgcore::{gpu,tensor,shapes,kernel,timestamps} + wgebra::linalg)."""
 from ._lib import DimensionMismatch, WgbError, lib  # noqa: F401
-from .gpu import CommandEncoder, ComputePass, Device, GpuInstance, Queue  # noqa: F401
+from .gpu import CommandEncoder, ComputePass, Device, GpuInstance, Graph, Queue  # noqa: F401
 from .linalg import (Dot, F32Mode, Gemm, GemmVariant, Gemv, GemvVariant, OpAssign, OpAssignVariant, Reduce,  # noqa: F401
                      ReduceOp, fill_uniform)
 from .shapes import ViewShape, ViewShapeBuffers  # noqa: F401

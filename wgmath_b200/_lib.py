@@ -58,6 +58,10 @@ def lib() -> ctypes.CDLL:
         "wgb_pass_end": ([vp], ci),
         "wgb_submit": ([vp], ci),
         "wgb_pass_last_gemm_path": ([vp, ctypes.POINTER(ci)], ci),
+        "wgb_graph_capture_begin": ([vp], ci),
+        "wgb_graph_capture_end": ([vp, pvp], ci),
+        "wgb_graph_launch": ([vp], ci),
+        "wgb_graph_destroy": ([vp], ci),
         "wgb_buffer_create": ([vp, sz, u32, pvp], ci),
         "wgb_buffer_create_init": ([vp, vp, sz, u32, pvp], ci),
         "wgb_buffer_wrap": ([vp, vp, sz, pvp], ci),
@@ -105,7 +109,8 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_ctx_destroy", "wgb_ctx_sync",
             "wgb_ctx_device_info", "wgb_ctx_launch_count", "wgb_ctx_stream", "wgb_pass_begin", "wgb_pass_end",
-            "wgb_submit", "wgb_pass_last_gemm_path", "wgb_buffer_create", "wgb_buffer_create_init", "wgb_buffer_wrap",
+            "wgb_submit", "wgb_pass_last_gemm_path", "wgb_graph_capture_begin", "wgb_graph_capture_end", "wgb_graph_launch",
+            "wgb_graph_destroy", "wgb_buffer_create", "wgb_buffer_create_init", "wgb_buffer_wrap",
             "wgb_buffer_destroy", "wgb_buffer_size", "wgb_buffer_device_ptr", "wgb_buffer_write", "wgb_buffer_copy",
             "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_host", "wgb_gemv",
             "wgb_op_assign", "wgb_reduce", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",

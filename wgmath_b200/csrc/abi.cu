@@ -218,6 +218,8 @@ wgb_status wgb_submit(wgb_ctx *ctx) {
     // Kernels were enqueued at dispatch time; cudaStreamQuery nudges the driver to flush (WDDM-style batching
     // does not exist on Linux, so this is effectively free).
     DeviceGuard g(ctx->device);
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone) return WGB_OK;  // recording
     cudaError_t e = cudaStreamQuery(ctx->stream);
     if (e != cudaSuccess && e != cudaErrorNotReady) WGB_FAIL(WGB_ERR_CUDA, "queue error: %s", cudaGetErrorString(e));
     return WGB_OK;
@@ -226,6 +228,70 @@ wgb_status wgb_submit(wgb_ctx *ctx) {
 wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path) {
     if (!pass || !path) WGB_FAIL(WGB_ERR_INVALID, "null argument");
     *path = pass->last_gemm_path;
+    return WGB_OK;
+}
+
+// --------------------------------------------------------------------------- graphs
+}  // extern "C"
+struct wgb_graph {
+    wgb_ctx *ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t launches_per_replay = 0;
+    uint64_t launches_at_begin = 0;
+};
+static thread_local uint64_t g_capture_launch_mark = 0;
+extern "C" {
+
+wgb_status wgb_graph_capture_begin(wgb_ctx *ctx) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "null context");
+    DeviceGuard g(ctx->device);
+    WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g_capture_launch_mark = ctx->launches.load();
+    WGB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    return WGB_OK;
+}
+
+wgb_status wgb_graph_capture_end(wgb_ctx *ctx, wgb_graph **out) {
+    if (!ctx || !out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(ctx->device);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (e != cudaSuccess || !graph) {
+        (void)cudaGetLastError();
+        WGB_FAIL(WGB_ERR_CUDA, "graph capture failed (%s): a dispatch synchronised or allocated during capture — warm the "
+                               "workspaces by running the sequence once before capturing", cudaGetErrorString(e));
+    }
+    wgb_graph *gr = new wgb_graph();
+    gr->ctx = ctx;
+    gr->graph = graph;
+    gr->launches_per_replay = ctx->launches.load() - g_capture_launch_mark;
+    ctx->launches.store(g_capture_launch_mark);   // recorded, not executed
+    e = cudaGraphInstantiate(&gr->exec, graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        delete gr;
+        WGB_FAIL(WGB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    *out = gr;
+    return WGB_OK;
+}
+
+wgb_status wgb_graph_launch(wgb_graph *graph) {
+    if (!graph) WGB_FAIL(WGB_ERR_INVALID, "null graph");
+    DeviceGuard g(graph->ctx->device);
+    WGB_CUDA(cudaGraphLaunch(graph->exec, graph->ctx->stream));
+    count_launch(graph->ctx, graph->launches_per_replay);
+    return WGB_OK;
+}
+
+wgb_status wgb_graph_destroy(wgb_graph *graph) {
+    if (!graph) return WGB_OK;
+    DeviceGuard g(graph->ctx->device);
+    cudaStreamSynchronize(graph->ctx->stream);
+    if (graph->exec) cudaGraphExecDestroy(graph->exec);
+    if (graph->graph) cudaGraphDestroy(graph->graph);
+    delete graph;
     return WGB_OK;
 }
 

@@ -32,6 +32,10 @@ class Device:
     def create_command_encoder(self, desc=None) -> "CommandEncoder":
         return CommandEncoder(self)
 
+    def capture(self) -> "_Capture":
+        """`with device.capture() as cap: <dispatches>` records them; `cap.graph.launch()` replays (wgb_graph_*)."""
+        return _Capture(self)
+
     def poll_wait(self) -> None:
         """device.poll(PollType::wait()) (tensor.rs:304-312)."""
         check(lib().wgb_ctx_sync(self._h))
@@ -47,6 +51,41 @@ class Device:
         n = ctypes.c_uint64()
         check(lib().wgb_ctx_launch_count(self._h, ctypes.byref(n)))
         return n.value
+
+
+class Graph:
+    """A recorded dispatch sequence (CUDA graph): `Device.capture()` ... `with` body ... then `.launch()` replays it."""
+
+    def __init__(self, device: "Device", handle):
+        self._device, self._h = device, handle
+
+    def launch(self) -> None:
+        check(lib().wgb_graph_launch(self._h))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().wgb_graph_destroy(h)
+            except Exception:
+                pass
+
+
+class _Capture:
+    def __init__(self, device: "Device"):
+        self._device, self.graph = device, None
+
+    def __enter__(self):
+        check(lib().wgb_graph_capture_begin(self._device._h))
+        return self
+
+    def __exit__(self, et, ev, tb):
+        h = ctypes.c_void_p()
+        st = lib().wgb_graph_capture_end(self._device._h, ctypes.byref(h))
+        if et is None:
+            check(st)
+            self.graph = Graph(self._device, h)
+        return False
 
 
 class Queue:
