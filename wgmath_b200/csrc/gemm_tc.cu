@@ -215,6 +215,9 @@ struct TcArgs {
     // tail split-K: tiles [full_tiles, total_tiles) are each cut into `split` K ranges of `kb_per_split` k-blocks, so the
     // last, partially filled wave of tiles still occupies every SM.  Work units = full_tiles + (total - full) * split.
     uint32_t full_tiles, split, kb_per_split, total_units;
+    // tail N-split (default): tiles [full_tiles, total_tiles) are instead cut into `nsplit` column strips of `tail_bn`
+    // columns, each a complete (narrower) output tile: the last wave fills the machine and needs no fix-up.
+    uint32_t nsplit, tail_bn, idesc_tail;
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
@@ -235,12 +238,22 @@ __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) 
 }
 
 struct WorkUnit {
-    uint32_t tile, kb0, kb1, split_idx;   // split_idx == 0xFFFFFFFF: whole tile
+    uint32_t tile, kb0, kb1, split_idx;   // split_idx == 0xFFFFFFFF: whole K range
+    uint32_t n_off, bn;                   // column strip inside the tile (n_off = 0, bn = BLOCK_N for a whole tile)
+    bool narrow;
 };
-__device__ __forceinline__ WorkUnit decode_unit(uint32_t u, const TcArgs &a) {
+__device__ __forceinline__ WorkUnit decode_unit(uint32_t u, const TcArgs &a, uint32_t block_n) {
     WorkUnit w;
+    w.n_off = 0; w.bn = block_n; w.narrow = false;
     if (u < a.full_tiles) {
         w.tile = u; w.kb0 = 0; w.kb1 = a.num_kb; w.split_idx = 0xFFFFFFFFu;
+    } else if (a.nsplit > 1) {
+        const uint32_t v = u - a.full_tiles;
+        w.tile = a.full_tiles + v / a.nsplit;
+        w.kb0 = 0; w.kb1 = a.num_kb; w.split_idx = 0xFFFFFFFFu;
+        w.n_off = (v % a.nsplit) * a.tail_bn;
+        w.bn = a.tail_bn;
+        w.narrow = true;
     } else {
         const uint32_t v = u - a.full_tiles;
         w.tile = a.full_tiles + v / a.split;
@@ -303,7 +316,8 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16 *p, float
 template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcArgs args) {
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmBlot, const TcArgs args) {
     using Cfg = TcCfg<BN, PASSES, CG>;
     constexpr int ES = KIND == 0 ? 2 : 4;                 // operand element size
     constexpr int BLOCK_K = kRowBytes / ES;               // 64 bf16 / 32 tf32
@@ -335,9 +349,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        prefetch_tmap(&tmBt);
         if (PASSES == 3) {
             prefetch_tmap(&tmAlo);
             prefetch_tmap(&tmBlo);
+            prefetch_tmap(&tmBlot);
         }
     }
     if (warp == 1 && lane == 0) {
@@ -365,21 +381,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== TMA producer =====================================
         uint32_t stage = 0, phase = 0;
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
-            const WorkUnit wu = decode_unit(u, args);
+            const WorkUnit wu = decode_unit(u, args, BN);
             uint32_t bt, mt, nt;
             tile_coords(wu.tile, args, bt, mt, nt);
             const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
-            const int n0 = (int)(nt * BN + cta_rank * Cfg::B_ROWS);
+            const uint32_t b_rows = wu.bn / CG;      // rows of the B tile this CTA loads
+            const int n0 = (int)(nt * BN + wu.n_off + cta_rank * b_rows);
+            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (kATileBytes + b_rows * kRowBytes) * CG;
             for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                 const uint32_t fb = smem_u32(full_bar + stage);
-                if (leader) mbar_arrive_expect_tx(fb, (uint32_t)Cfg::STAGE_BYTES * CG);
+                if (leader) mbar_arrive_expect_tx(fb, stage_tx);
                 uint8_t *sbase = smem + stage * Cfg::STAGE_BYTES;
                 const int k0 = (int)(kb * BLOCK_K);
 #pragma unroll
                 for (int set = 0; set < Cfg::SETS; ++set) {
                     const CUtensorMap *ta = set == 0 ? &tmA : &tmAlo;
-                    const CUtensorMap *tb = set == 0 ? &tmB : &tmBlo;
+                    const CUtensorMap *tb = wu.narrow ? (set == 0 ? &tmBt : &tmBlot) : (set == 0 ? &tmB : &tmBlo);
                     const uint32_t sa = smem_u32(sbase + set * kATileBytes);
                     const uint32_t sb = smem_u32(sbase + Cfg::SETS * kATileBytes + set * Cfg::B_TILE_BYTES);
                     if (A_MN) {
@@ -403,7 +421,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) {
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
-                const WorkUnit wu = decode_unit(u, args);
+                const WorkUnit wu = decode_unit(u, args, BN);
+                const uint32_t idesc = wu.narrow ? args.idesc_tail : IDESC;
                 uint32_t kb = wu.kb0;
                 while (kb < wu.kb1) {
                     // one TMEM accumulation chain: the whole K range, or kChunkKb k-blocks for 3xTF32
@@ -433,11 +452,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             if (PASSES == 3) {
                                 const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
                                 const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
-                                umma<KIND, CG>(d_tmem, da_lo, db_hi, IDESC, first);   // small terms first
-                                umma<KIND, CG>(d_tmem, da_hi, db_lo, IDESC, 1u);
-                                umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, 1u);
+                                umma<KIND, CG>(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
+                                umma<KIND, CG>(d_tmem, da_hi, db_lo, idesc, 1u);
+                                umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, 1u);
                             } else {
-                                umma<KIND, CG>(d_tmem, da_hi, db_hi, IDESC, first);
+                                umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, first);
                             }
                         }
                         umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
@@ -466,12 +485,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
-            const WorkUnit wu = decode_unit(u, args);
+            const WorkUnit wu = decode_unit(u, args, BN);
             uint32_t bt, mt, nt;
             tile_coords(wu.tile, args, bt, mt, nt);
             const uint32_t row_in_cta = q * 32 + lane;
             const uint32_t row = mt * (kBlockM * CG) + cta_rank * kBlockM + row_in_cta;
-            const uint32_t n0 = nt * BN;
+            const uint32_t n0 = nt * BN + wu.n_off;
+            const int nblk = (int)(wu.bn / 32);      // 32-column blocks in this unit's accumulator
             const bool split_unit = wu.split_idx != 0xFFFFFFFFu;
             const uint64_t crow_off = (uint64_t)bt * args.sc + row;   // element offset of (row, col 0) inside a panel
             const bool row_ok = row < args.M;
@@ -491,10 +511,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tmem_ld32(taddr, v[0]);
 #pragma unroll
                 for (int c = 0; c < BN / 32; ++c) {
+                    if (c >= nblk) break;
                     uint32_t sprev[32];
                     if (CHUNKED && ch > 0) tmem_ld32(tsum + c * 32, sprev);
                     tmem_ld_wait();
-                    if (c + 1 < BN / 32) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (c + 1 < nblk) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
                     else {
                         // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
                         tc_fence_before();
@@ -727,9 +748,12 @@ int env_int(const char *name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+struct TcMaps {
+    CUtensorMap a, alo, b, blo, bt, blot;   // operands (hi / lo), and B with the narrow box of the tail strips
+};
+
 template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
-wgb_status launch_cfg(wgb_pass *p, const CUtensorMap &ta, const CUtensorMap &talo, const CUtensorMap &tb, const CUtensorMap &tblo,
-                      TcArgs args) {
+wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     using Cfg = TcCfg<BN, PASSES, CG>;
     auto kern = gemm_tc_kernel<KIND, A_MN, BN, PASSES, TOut, CG>;
     static bool attr_set[64] = {};   // per instantiation, per device
@@ -755,24 +779,23 @@ wgb_status launch_cfg(wgb_pass *p, const CUtensorMap &ta, const CUtensorMap &tal
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, talo, tb, tblo, args));
+    WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.alo, m.b, m.blo, m.bt, m.blot, args));
     count_launch(p->ctx);
     return WGB_OK;
 }
 
 template <int KIND, bool A_MN, int PASSES, typename TOut>
-wgb_status launch_sel(wgb_pass *p, int bn, int cg, const CUtensorMap &ta, const CUtensorMap &talo, const CUtensorMap &tb,
-                      const CUtensorMap &tblo, const TcArgs &args) {
+wgb_status launch_sel(wgb_pass *p, int bn, int cg, const TcMaps &m, const TcArgs &args) {
     if constexpr (PASSES == 3) {   // 3xTF32: BLOCK_N = 128 only (two accumulator stages + running sum in TMEM)
-        if (cg == 2) return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
-        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+        if (cg == 2) return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, m, args);
+        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, m, args);
     } else {
         if (cg == 2) {
-            if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
-            return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, ta, talo, tb, tblo, args);
+            if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, m, args);
+            return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, m, args);
         }
-        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
-        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, ta, talo, tb, tblo, args);
+        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, m, args);
+        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, m, args);
     }
 }
 
@@ -805,29 +828,49 @@ static int pick_bn(uint32_t M, uint32_t N, uint32_t nmats, int cg, uint32_t sms)
     return 256;
 }
 
-// Tail split-K plan: with T tiles on C clusters, the last T mod C tiles would run alone; cut each into
-// floor(C / tail) K ranges so the last wave is full too (each range keeps >= 4 k-blocks).
-static void plan_split(TcArgs &a, uint32_t clusters) {
+// Tail plan.  With T tiles on C clusters the last T mod C tiles would run alone while the other clusters idle.
+// Default: cut each tail tile into 2 or 4 column strips (narrower complete tiles, no fix-up) when that still fits one wave:
+// a 128- / 64-column strip costs ~0.75 / ~0.63 of a 256-column tile (the A tile is loaded either way).
+// WGB_TC_SPLITK=1 selects the K split with a workspace fix-up instead (measured slower, kept for reference).
+static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bool a_mn) {
     a.full_tiles = a.total_tiles;
     a.split = 1;
     a.kb_per_split = a.num_kb;
+    a.nsplit = 1;
+    a.tail_bn = (uint32_t)bn;
+    a.idesc_tail = 0;
     a.total_units = a.total_tiles;
-    // Measured on B200 (profiles/README.md): the workspace fix-up (park partials, last CTA re-reads them from L2) costs as
-    // much as the half wave it saves at 4096^3 and more at small sizes, so the tail split is opt-in for now.
-    if (env_int("WGB_TC_SPLITK", 0) == 0) return;
     const uint32_t tail = a.total_tiles % clusters;
     if (tail == 0) return;
-    uint32_t split = clusters / tail;
-    if (split > 8) split = 8;
-    if (split > a.num_kb / 4) split = a.num_kb / 4;
-    if (split < 2) return;
-    const uint32_t per = (a.num_kb + split - 1) / split;
-    split = (a.num_kb + per - 1) / per;
-    if (split < 2) return;
+    if (env_int("WGB_TC_SPLITK", 0) != 0) {
+        uint32_t split = clusters / tail;
+        if (split > 8) split = 8;
+        if (split > a.num_kb / 4) split = a.num_kb / 4;
+        if (split < 2) return;
+        const uint32_t per = (a.num_kb + split - 1) / split;
+        split = (a.num_kb + per - 1) / per;
+        if (split < 2) return;
+        a.full_tiles = a.total_tiles - tail;
+        a.split = split;
+        a.kb_per_split = per;
+        a.total_units = a.full_tiles + tail * split;
+        return;
+    }
+    if (env_int("WGB_TC_NSPLIT", 1) == 0) return;
+    uint32_t nsplit = 1;
+    for (uint32_t cand : {4u, 2u}) {
+        const uint32_t w = (uint32_t)bn / cand;
+        if ((uint64_t)tail * cand <= clusters && w >= 32 && (w / cg) % 8 == 0) {
+            nsplit = cand;
+            break;
+        }
+    }
+    if (nsplit == 1) return;
     a.full_tiles = a.total_tiles - tail;
-    a.split = split;
-    a.kb_per_split = per;
-    a.total_units = a.full_tiles + tail * split;
+    a.nsplit = nsplit;
+    a.tail_bn = (uint32_t)bn / nsplit;
+    a.idesc_tail = make_idesc(kind, a_mn, kBlockM * cg, (int)a.tail_bn);
+    a.total_units = a.full_tiles + tail * nsplit;
 }
 
 wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, int *path_out) {
@@ -899,7 +942,8 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         WGB_CUDA(cudaGetLastError());
     }
 
-    CUtensorMap ta, talo, tb, tblo;
+    TcMaps maps;
+    CUtensorMap &ta = maps.a, &talo = maps.alo, &tb = maps.b, &tblo = maps.blo;
     const bool atom32 = f32 && !tr;                                     // MN-major 32-bit operand A
     const uint32_t a_box0 = tr ? block_k : (uint32_t)(128 / es);       // K-major: 128 B of K; MN-major: one 128 B atom of M
     const uint32_t a_box1 = tr ? 128u : block_k;
@@ -940,7 +984,14 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     uint32_t sms = sms_total;
     const uint32_t margin = (uint32_t)comm_sm_margin(ctx);
     if (margin < sms / 2) sms -= margin;
-    plan_split(args, sms / cg);
+    plan_tail(args, sms / cg, bn, cg, f32 ? 1 : 0, !tr);
+    maps.bt = tb;
+    maps.blot = tblo;
+    if (args.nsplit > 1) {
+        WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.bt));
+        if (passes == 3) WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.blot));
+        else maps.blot = maps.bt;
+    }
     if (args.split > 1) {
         const uint32_t tail = args.total_tiles - args.full_tiles;
         if ((uint64_t)tail * cg > ctx->scratch.n_counters) {
@@ -956,16 +1007,16 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     wgb_status st;
     if (!f32) {
         if (g.out_dtype == WGB_F32)
-            st = tr ? launch_sel<0, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<0, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+            st = tr ? launch_sel<0, false, 1, float>(p, bn, cg, maps, args) : launch_sel<0, true, 1, float>(p, bn, cg, maps, args);
         else
-            st = tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args)
-                    : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, ta, talo, tb, tblo, args);
+            st = tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, maps, args)
+                    : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, maps, args);
         *path_out = 2;
     } else if (passes == 1) {
-        st = tr ? launch_sel<1, false, 1, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 1, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        st = tr ? launch_sel<1, false, 1, float>(p, bn, cg, maps, args) : launch_sel<1, true, 1, float>(p, bn, cg, maps, args);
         *path_out = 3;
     } else {
-        st = tr ? launch_sel<1, false, 3, float>(p, bn, cg, ta, talo, tb, tblo, args) : launch_sel<1, true, 3, float>(p, bn, cg, ta, talo, tb, tblo, args);
+        st = tr ? launch_sel<1, false, 3, float>(p, bn, cg, maps, args) : launch_sel<1, true, 3, float>(p, bn, cg, maps, args);
         *path_out = 4;
     }
     return st;
