@@ -222,6 +222,15 @@ wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
                        const wgb_view_shape *m1_shape, const wgb_buffer *m2,
                        const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_dtype out_dtype,
                        wgb_f32_mode f32_mode);
+/* GEMM with the caller's next element-wise step fused into the epilogue: out = (m1 * m2) (op) operand,
+ * i.e. Gemm::dispatch followed by OpAssign::dispatch(out, operand) (op_assign.rs:71-94) without the extra round trip of
+ * `out` through HBM.  `operand` is a matrix view of out's element type with out's [rows, cols, mats]; its strides are free.
+ * op == WGB_OP_COPY is rejected (it would discard the product). */
+wgb_status wgb_gemm_op(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *out_shape,
+                       const wgb_buffer *m1, const wgb_view_shape *m1_shape, const wgb_buffer *m2,
+                       const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode f32_mode,
+                       wgb_op_assign_variant op, const wgb_buffer *operand, const wgb_view_shape *operand_shape);
+
 /* Host-buffer GEMM: out_host = m1_host * m2_host (or tr(m1_host) * m2_host) with dense column-major host matrices
  * (leading dimensions = row counts).  Equivalent to build_init(m1), build_init(m2), dispatch, read — the sequence of
  * the reference's own tests (gemm.rs:156-193) — but pipelined: m2 is uploaded and the product downloaded in column

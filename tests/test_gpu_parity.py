@@ -510,6 +510,50 @@ def test_gemm_host_buffers_pipelined(gpu, shapes, tr, dtype):
     assert rel_err(cm(out, M, N), ref) < (1e-4 if dtype == "bf16" else F32_TOL)
 
 
+@pytest.mark.parametrize("op", [w.OpAssignVariant.Add, w.OpAssignVariant.Sub, w.OpAssignVariant.Mul, w.OpAssignVariant.Div])
+@pytest.mark.parametrize("M,N,K,mode", [(256, 384, 192, None), (100, 60, 52, w.F32Mode.Simt), (512, 512, 1024, w.F32Mode.Tf32)])
+def test_gemm_fused_op_assign_equals_the_two_dispatch_chain(gpu, shapes, op, M, N, K, mode):
+    """wgb_gemm_op == Gemm::dispatch then OpAssign::dispatch(out, operand) (the reference's separate dispatches)."""
+    dev = gpu.device()
+    A, B = O.uniform(SEED_A, M, K), O.uniform(SEED_B, K, N)
+    E = O.uniform(SEED_V, M * N) + np.float32(0.5)
+    ta, tb, te = upload(gpu, A, (M, K)), upload(gpu, B, (K, N)), upload(gpu, E, (M, N))
+    fused = upload(gpu, np.zeros(M * N, np.float32), (M, N))
+    chain = upload(gpu, np.zeros(M * N, np.float32), (M, N))
+    gemm = w.Gemm.from_device(dev)
+    opk = w.OpAssign.new(dev, op)
+
+    def go(p):
+        gemm.dispatch_op(dev, shapes, p, fused, ta, tb, op, te, f32_mode=mode)
+        gemm.dispatch_generic(dev, shapes, p, chain, ta, tb, w.GemmVariant.Gemm, f32_mode=mode)
+        opk.dispatch(dev, shapes, p, chain.reshape((M * N,)), te.reshape((M * N,)))
+    run_pass(gpu, go)
+    np.testing.assert_array_equal(fused.read(), chain.read())          # same kernel arithmetic, then the same IEEE op
+    if mode != w.F32Mode.Tf32:
+        ref = np.zeros(M * N, np.float32)
+        if M % 4 == 0 and N % 4 == 0 and K % 4 == 0:
+            assert O.gemm(O.GEMM, ref, O.shape(M, N), A, O.shape(M, K), B, O.shape(K, N)) == O.ORC_OK
+        else:
+            ref = (cm(A, M, K).astype(np.float64) @ cm(B, K, N).astype(np.float64)).T.reshape(-1).astype(np.float32)
+        assert O.op_assign(int(op), ref, O.shape(M * N), E, O.shape(M * N)) == O.ORC_OK
+        assert rel_err(fused.read(), ref) < F32_TOL
+
+
+def test_gemm_fused_accumulate_in_place(gpu, shapes):
+    """operand == out: out += m1 * m2 (bf16 operands, f32 accumulate / output), twice."""
+    dev = gpu.device()
+    n = 256
+    A, B = O.to_bf16_rne(O.uniform(SEED_A, n, n)), O.to_bf16_rne(O.uniform(SEED_B, n, n))
+    ta, tb = upload(gpu, O.bf16_bits(A), (n, n), "bf16"), upload(gpu, O.bf16_bits(B), (n, n), "bf16")
+    out = upload(gpu, np.ones(n * n, np.float32), (n, n))
+    gemm = w.Gemm.from_device(dev)
+    run_pass(gpu, lambda p: [gemm.dispatch_op(dev, shapes, p, out, ta, tb, w.OpAssignVariant.Add, out) for _ in range(2)])
+    ref = 1.0 + 2.0 * (cm(A, n, n).astype(np.float64) @ cm(B, n, n).astype(np.float64))
+    assert rel_err(cm(out.read(), n, n), ref) < 1e-4
+    with pytest.raises(w.WgbError):
+        run_pass(gpu, lambda p: gemm.dispatch_op(dev, shapes, p, out, ta, tb, w.OpAssignVariant.Copy, out))
+
+
 def test_graph_capture_replays_a_dispatch_chain(gpu, shapes):
     """wgb_graph_*: record gemm -> op_assign -> reduce once, replay it, same result as the eager sequence."""
     dev = gpu.device()

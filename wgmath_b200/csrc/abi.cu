@@ -568,9 +568,10 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, c
     return launch_gemv(pass, tr, (float *)out->ptr, *so, (const float *)m->ptr, sm_used, (const float *)v->ptr, sv_used);
 }
 
-wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
-                       const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
-                       wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode) {
+static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
+                              const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
+                              wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode, int ep_op, const wgb_buffer *e,
+                              const wgb_view_shape *se) {
     if (!pass || !out || !so || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: null argument");
     if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown variant %d", (int)variant);
     if ((in_dtype != WGB_F32 && in_dtype != WGB_BF16) || (out_dtype != WGB_F32 && out_dtype != WGB_BF16))
@@ -602,9 +603,41 @@ wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
     g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = so->stride_mat;
     g.in_dtype = in_dtype;
     g.out_dtype = out_dtype;
+    if (ep_op >= 0) {
+        if (!e || !se) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_op: null operand");
+        if (ep_op == WGB_OP_COPY || ep_op > WGB_OP_COPY) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_op: op must be Add, Sub, Mul or Div");
+        if (se->size[0] != so->size[0] || se->size[1] != so->size[1] || se->size[2] != so->size[2])
+            WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Op-assign: dimension mismatch. (operand %u x %u x %u vs out %u x %u x %u)", se->size[0],
+                     se->size[1], se->size[2], so->size[0], so->size[1], so->size[2]);
+        if (e->bytes == 0) return WGB_OK;
+        WGB_TRY(check_view(e, *se, dtype_size(out_dtype), "gemm_op operand"));
+        g.ep_op = ep_op;
+        g.e = e->ptr;
+        g.e_off = se->offset;
+        g.lde = se->stride;
+        g.se = se->stride_mat;
+    }
     DeviceGuard dg(pass->ctx->device);
     return gemm_dispatch(pass, g, mode);
 }
+
+}  // extern "C"  (gemm_common is internal)
+extern "C" {
+
+wgb_status wgb_gemm_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
+                       const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
+                       wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode) {
+    return gemm_common(pass, variant, out, so, m1, s1, m2, s2, in_dtype, out_dtype, mode, -1, nullptr, nullptr);
+}
+
+wgb_status wgb_gemm_op(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so, const wgb_buffer *m1,
+                       const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2, wgb_dtype in_dtype,
+                       wgb_dtype out_dtype, wgb_f32_mode mode, wgb_op_assign_variant op, const wgb_buffer *operand,
+                       const wgb_view_shape *operand_shape) {
+    if ((int)op < 0) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_op: unknown op");
+    return gemm_common(pass, variant, out, so, m1, s1, m2, s2, in_dtype, out_dtype, mode, (int)op, operand, operand_shape);
+}
+
 
 wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
                          const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,

@@ -166,7 +166,24 @@ struct GemmProblem {
     uint64_t lda, ldb, ldc;           // column strides, elements
     uint64_t sa, sb, sc;              // matrix strides, elements
     wgb_dtype in_dtype, out_dtype;
+    // fused element-wise epilogue: out = (m1 * m2) (ep_op) e, e a view of out's element type (ep_op < 0: none)
+    int ep_op = -1;
+    const void *e = nullptr;
+    uint64_t e_off = 0, lde = 0, se = 0;
 };
+// out-of-line helper shared by both GEMM kernels
+template <typename T>
+__device__ __forceinline__ float epilogue_apply(int op, float v, const T *e);
+template <>
+__device__ __forceinline__ float epilogue_apply<float>(int op, float v, const float *e) {
+    const float x = *e;
+    return op == WGB_OP_ADD ? v + x : op == WGB_OP_SUB ? v - x : op == WGB_OP_MUL ? v * x : v / x;
+}
+template <>
+__device__ __forceinline__ float epilogue_apply<__nv_bfloat16>(int op, float v, const __nv_bfloat16 *e) {
+    const float x = __bfloat162float(*e);
+    return op == WGB_OP_ADD ? v + x : op == WGB_OP_SUB ? v - x : op == WGB_OP_MUL ? v * x : v / x;
+}
 wgb_status launch_gemm_simt(wgb_pass *p, const GemmProblem &g);
 // tcgen05 path. `passes`: 1 (bf16 or single-pass tf32) or 3 (3xTF32; operands pre-split).
 bool gemm_tc_eligible(const GemmProblem &g);

@@ -36,6 +36,9 @@ struct SimtArgs {
     uint32_t M, N, K;
     uint64_t lda, ldb, ldc, sa, sb, sc;
     uint32_t z_base;
+    int ep_op;
+    const void *e;
+    uint64_t lde, se;
 };
 
 template <bool TR, typename TIn, typename TOut>
@@ -114,7 +117,12 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const uint32_t m = m0 + (i < 4 ? tx * 4 + i : 64 + tx * 4 + (i - 4));
-            if (m < g.M) C[(uint64_t)n * g.ldc + m] = from_f32<TOut>(acc[i][j]);
+            if (m < g.M) {
+                float val = acc[i][j];
+                if (g.ep_op >= 0)
+                    val = epilogue_apply<TOut>(g.ep_op, val, reinterpret_cast<const TOut *>(g.e) + (uint64_t)t * g.se + (uint64_t)n * g.lde + m);
+                C[(uint64_t)n * g.ldc + m] = from_f32<TOut>(val);
+            }
         }
     }
 }
@@ -138,6 +146,9 @@ wgb_status launch_gemm_simt(wgb_pass *p, const GemmProblem &g) {
     a.M = g.M; a.N = g.N; a.K = g.K;
     a.lda = g.lda; a.ldb = g.ldb; a.ldc = g.ldc;
     a.sa = g.sa; a.sb = g.sb; a.sc = g.sc;
+    a.ep_op = g.ep_op;
+    a.e = g.e ? (const char *)g.e + g.e_off * os : nullptr;
+    a.lde = g.lde; a.se = g.se;
     const uint32_t gx = (g.M + BM - 1) / BM, gy = (g.N + BN - 1) / BN;
     if (gy > 65535) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm (SIMT path): N = %u needs more than 65535 column tiles", g.N);
     for (uint32_t z0 = 0; z0 < g.nmats; z0 += 65535) {

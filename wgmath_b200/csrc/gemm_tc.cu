@@ -218,6 +218,10 @@ struct TcArgs {
     // tail N-split (default): tiles [full_tiles, total_tiles) are instead cut into `nsplit` column strips of `tail_bn`
     // columns, each a complete (narrower) output tile: the last wave fills the machine and needs no fix-up.
     uint32_t nsplit, tail_bn, idesc_tail;
+    int ep_op;               // fused element-wise epilogue (-1: none): out = acc (op) e
+    const void *ep;          // operand view base (element 0 of the view), element type = TOut
+    uint64_t ep_ld, ep_sm;
+    uint32_t debug_skip;     // diagnostics only (WGB_TC_DEBUG_SKIP): bit 0 = do not load A tiles, bit 1 = do not load B tiles
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
@@ -376,6 +380,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap the
+    // tail of the previous kernel on the queue; nothing below may touch global memory before that kernel has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0 && lane == 0) {
         // ===================================== TMA producer =====================================
@@ -387,7 +395,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
             const uint32_t b_rows = wu.bn / CG;      // rows of the B tile this CTA loads
             const int n0 = (int)(nt * BN + wu.n_off + cta_rank * b_rows);
-            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (kATileBytes + b_rows * kRowBytes) * CG;
+            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (((args.debug_skip & 1u) ? 0u : (uint32_t)kATileBytes) +
+                                                             ((args.debug_skip & 2u) ? 0u : b_rows * kRowBytes)) * CG;
             for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
                 const uint32_t fb = smem_u32(full_bar + stage);
@@ -400,7 +409,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const CUtensorMap *tb = wu.narrow ? (set == 0 ? &tmBt : &tmBlot) : (set == 0 ? &tmB : &tmBlo);
                     const uint32_t sa = smem_u32(sbase + set * kATileBytes);
                     const uint32_t sb = smem_u32(sbase + Cfg::SETS * kATileBytes + set * Cfg::B_TILE_BYTES);
-                    if (A_MN) {
+                    if (args.debug_skip & 1u) {
+                    } else if (A_MN) {
 #pragma unroll
                         for (int at = 0; at < A_ATOMS; ++at) {
                             if (CG == 2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
@@ -410,9 +420,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (CG == 2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
                         else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
                     }
-                    if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
+                    if (args.debug_skip & 2u) {
+                    } else if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
                     else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
                 }
+                if (args.debug_skip == 3u && leader) {}   // (both skipped: expect_tx(0) completes on the arrive alone)
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -535,6 +547,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
                     } else if (row_ok) {
+                        if (args.ep_op >= 0) {   // fused OpAssign: out = acc (op) e, e read coalesced like the store
+                            const TOut *erow = reinterpret_cast<const TOut *>(args.ep) + (uint64_t)bt * args.ep_sm + row;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const uint32_t col = n0 + c * 32 + i;
+                                if (col < args.N)
+                                    v[c & 1][i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(v[c & 1][i]), erow + (uint64_t)col * args.ep_ld));
+                            }
+                        }
                         for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
                             TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
 #pragma unroll
@@ -570,7 +591,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 32; ++i) sum[i] += __ldcg(src + (uint64_t)i * kBlockM);   // 32 loads in flight
                         }
-                        if (row_ok)
+                        if (row_ok) {
+                            if (args.ep_op >= 0) {
+                                const TOut *erow = reinterpret_cast<const TOut *>(args.ep) + (uint64_t)bt * args.ep_sm + row;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) {
+                                    const uint32_t col = n0 + c * 32 + i;
+                                    if (col < args.N) sum[i] = epilogue_apply<TOut>(args.ep_op, sum[i], erow + (uint64_t)col * args.ep_ld);
+                                }
+                            }
                             for (uint32_t d = 0; d < args.npeers; ++d) {
                                 TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
 #pragma unroll
@@ -579,6 +608,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, sum[i]);
                                 }
                             }
+                        }
                     }
                     if (threadIdx.x == 128) args.counters[slot * CG + cta_rank] = 0u;
                 }
@@ -772,13 +802,15 @@ wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     cfg.blockDim = dim3(kNumThreads);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = p->stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = env_int("WGB_TC_PDL", 1) != 0 ? 2 : 1;
     WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.alo, m.b, m.blo, m.bt, m.blot, args));
     count_launch(p->ctx);
     return WGB_OK;
@@ -984,6 +1016,11 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     uint32_t sms = sms_total;
     const uint32_t margin = (uint32_t)comm_sm_margin(ctx);
     if (margin < sms / 2) sms -= margin;
+    args.ep_op = g.ep_op;
+    args.ep = g.e ? (const char *)g.e + g.e_off * dtype_size(g.out_dtype) : nullptr;
+    args.ep_ld = g.lde;
+    args.ep_sm = g.se;
+    args.debug_skip = (uint32_t)env_int("WGB_TC_DEBUG_SKIP", 0) & 3u;   // timing diagnostics only: results are garbage
     plan_tail(args, sms / cg, bn, cg, f32 ? 1 : 0, !tr);
     maps.bt = tb;
     maps.blot = tblo;

@@ -81,6 +81,16 @@ class Gemm:
                                 m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode)))
 
 
+    def dispatch_op(self, device, shapes, pass_, out, m1, m2, op: "OpAssignVariant", operand, variant=GemmVariant.Gemm, f32_mode=None):
+        """out = (m1 * m2) (op) operand in one launch (wgb_gemm_op): Gemm::dispatch + OpAssign::dispatch(out, operand) fused
+        into the GEMM epilogue.  `operand` may be `out` itself (accumulate into out)."""
+        out, m1, m2, e = as_view(out, 3), as_view(m1, 3), as_view(m2, 3), as_view(operand, 3)
+        so, s1, s2, se = (shapes.get(device, v.shape()).to_c() for v in (out, m1, m2, e))
+        mode = self.f32_mode if f32_mode is None else f32_mode
+        check(lib().wgb_gemm_op(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m1.buffer()._h, ctypes.byref(s1),
+                                m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode), int(op),
+                                e.buffer()._h, ctypes.byref(se)))
+
     def dispatch_host(self, device, M: int, N: int, K: int, out_host, m1_host, m2_host, variant=GemmVariant.Gemm,
                       in_dtype: str = "f32", out_dtype: str = "f32", f32_mode=None, n_panels: int = 0) -> None:
         """Host-buffer GEMM (wgb_gemm_host): upload, multiply and download pipelined by column panel.  `*_host` are
