@@ -1,0 +1,42 @@
+//! crates/wgebra/src/linalg/gemm.rs:9-127 — same struct, enum and `dispatch*` signatures; one FFI call underneath.
+use super::{B200Scalar, ComposerError};
+use wgcore::shapes::ViewShapeBuffers;
+use wgcore::tensor::GpuCubeView;
+use wgpu::{sys, ComputePass, ComputePipeline, Device};
+
+/// Shader for computing the product of two matrices.
+pub struct Gemm {
+    pub gemm: ComputePipeline,
+    pub gemm_fast: ComputePipeline,
+    pub gemm_tr: ComputePipeline,
+    pub gemm_tr_fast: ComputePipeline,
+}
+
+#[derive(Copy, Clone, Debug, PartialEq, Eq, Hash)]
+pub enum GemmVariant { Gemm, GemmFast, GemmTr, GemmTrFast }   // discriminants == wgb_gemm_variant
+
+impl Gemm {
+    /// `#[derive(Shader)]`'s `from_device` (wgcore-derive/src/lib.rs:138-140): nothing to compile at run time.
+    pub fn from_device(_device: &Device) -> Result<Self, ComposerError> {
+        Ok(Self { gemm: ComputePipeline("gemm"), gemm_fast: ComputePipeline("gemm_fast"), gemm_tr: ComputePipeline("gemm_tr"), gemm_tr_fast: ComputePipeline("gemm_tr_fast") })
+    }
+
+    /// `out = m1 * m2`
+    pub fn dispatch<'a, 'b, T: B200Scalar>(&'a self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass,
+        out: impl Into<GpuCubeView<'b, T>>, m1: impl Into<GpuCubeView<'b, T>>, m2: impl Into<GpuCubeView<'b, T>>) {
+        self.dispatch_generic(device, shapes, pass, out, m1, m2, GemmVariant::Gemm)
+    }
+    /// `out = tr(m1) * m2`
+    pub fn dispatch_tr<'a, 'b, T: B200Scalar>(&'a self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass,
+        out: impl Into<GpuCubeView<'b, T>>, m1: impl Into<GpuCubeView<'b, T>>, m2: impl Into<GpuCubeView<'b, T>>) {
+        self.dispatch_generic(device, shapes, pass, out, m1, m2, GemmVariant::GemmTr)
+    }
+    pub fn dispatch_generic<'a, 'b, T: B200Scalar>(&'a self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass,
+        out: impl Into<GpuCubeView<'b, T>>, m1: impl Into<GpuCubeView<'b, T>>, m2: impl Into<GpuCubeView<'b, T>>, variant: GemmVariant) {
+        let (out, m1, m2) = (out.into(), m1.into(), m2.into());
+        // the dimension asserts of gemm.rs:81-96 live in the library: status 2 -> panic!("Gemm: dimension mismatch. …")
+        let (so, s1, s2) = (shapes.get(device, out.shape()), shapes.get(device, m1.shape()), shapes.get(device, m2.shape()));
+        sys::check(unsafe { sys::wgb_gemm_ex(pass.raw(), variant as i32, out.buffer().raw(), &so, m1.buffer().raw(), &s1,
+                                             m2.buffer().raw(), &s2, T::DTYPE, T::DTYPE, /* WGB_F32_AUTO: parity-gated 3xTF32 */ 0) });
+    }
+}
