@@ -112,7 +112,7 @@ def cpu_gemm_sample(target_s: float, n: int = 4096, repeat: int = 1):
     """Times the oracle's restatement of gemm.wgsl:81-113 on a row strip of the n^3 product (f32: the reference
     has no bf16).  Returns (tflops, cores, description, seconds_per_run)."""
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = O.use_all_cores()
     b = O.uniform(O.SEED_BASE + 2, n, n)
     # calibrate on 64 rows
     rows = 64
@@ -142,7 +142,7 @@ def run_reference_arm(args):
         return 0
     n = 4096
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = O.use_all_cores()
     # size the per-step sample so that (steps + warmup) steps finish in ~2 minutes at most
     budget = 100.0 / max(1, args.steps + args.warmup)
     tf, cores, desc, dt, rows = cpu_gemm_sample(min(2.0, budget), n, repeat=1)

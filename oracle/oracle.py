@@ -67,6 +67,8 @@ def lib():
                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, fp, sp, fp, sp]
         L.orc_gemm_f64.restype = None
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_set_num_threads.argtypes = [ctypes.c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
@@ -107,6 +109,17 @@ def gemm_f64(tr, M, N, K, nmats, m1, s1, m2, s2) -> np.ndarray:
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def use_all_cores() -> int:
+    """Overrides an inherited OMP_NUM_THREADS (torchrun sets it to 1): the CPU baseline uses every core the process may
+    run on.  Returns the thread count now in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().orc_set_num_threads(n)
+    return num_threads()
 
 
 # ---- seeded inputs -------------------------------------------------------------------

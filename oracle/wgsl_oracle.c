@@ -393,6 +393,15 @@ void orc_gemm_f64(int tr, double *out /* dense col-major M x N per mat */, uint3
     }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core it can. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
