@@ -138,6 +138,34 @@ int main() {
                 failures += !(e < 1e-5);
             }
         }
+        {   // extensions through the C++ mirror: fused Gemm + OpAssign(Add) epilogue, recorded into a graph and replayed
+            const uint32_t n = 256;
+            auto a = uniform(SEED + 1, n, n), b = uniform(SEED + 2, n, n), e = uniform(SEED + 3, n * n);
+            auto gemm = Gemm::from_device(gpu.device());
+            auto ta = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), a);
+            auto tb = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), b);
+            auto te = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), e);
+            auto out = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), std::vector<float>(n * n, 0.f));
+            auto run = [&]() {
+                auto enc = gpu.device().create_command_encoder();
+                auto pass = enc.compute_pass("fused");
+                gemm.dispatch_op<float>(gpu.device(), shapes, pass, out.as_embedded_view<3>(), ta.as_embedded_view<3>(), tb.as_embedded_view<3>(),
+                                        (int)OpAssignVariant::Add, te.as_embedded_view<3>());
+            };
+            run();   // eager (warms the workspaces)
+            Graph::capture_begin(gpu.device());
+            run();
+            Graph g = Graph::capture_end(gpu.device());
+            g.launch();
+            auto got = out.read(gpu.device());
+            std::vector<float> ref(n * n, 0.f);
+            orc_shape s = oshape(n, n), sv = oshape(n * n);
+            orc_gemm(0, ref.data(), &s, a.data(), &s, b.data(), &s);
+            orc_op_assign(0, ref.data(), &sv, e.data(), &sv);
+            const double err = rel_err(got, ref);
+            std::printf("fused gemm+add via graph replay: rel err %.3e\n", err);
+            failures += !(err < 1e-5);
+        }
         {   // the reference's panic on mismatched dimensions (gemm.rs:91)
             auto gemm = Gemm::from_device(gpu.device());
             auto a = Tensors::matrix(8, 4, usage).build<float>(gpu.device());

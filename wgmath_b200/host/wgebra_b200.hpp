@@ -297,6 +297,29 @@ class Gemm {  // gemm.rs:9-127
         check(wgb_gemm_ex(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, m1.buffer()->raw, &s1, m2.buffer()->raw, &s2,
                           DType<T>::value, DType<T>::value, f32_mode));
     }
+
+    // Extension (wgb_gemm_op): out = (m1 * m2) (op) operand — Gemm::dispatch + OpAssign::dispatch in one launch.
+    template <typename T> void dispatch_op(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m1,
+                                           GpuCubeView<T> m2, int op /* OpAssignVariant */, GpuCubeView<T> operand,
+                                           GemmVariant variant = GemmVariant::Gemm) const {
+        const ViewShape so = shapes.get(d, out.shape()), s1 = shapes.get(d, m1.shape()), s2 = shapes.get(d, m2.shape()), se = shapes.get(d, operand.shape());
+        check(wgb_gemm_op(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, m1.buffer()->raw, &s1, m2.buffer()->raw, &s2,
+                          DType<T>::value, DType<T>::value, f32_mode, (wgb_op_assign_variant)op, operand.buffer()->raw, &se));
+    }
+};
+
+// Extension (wgb_graph_*): record a dispatch chain once, replay it with one launch.
+class Graph {
+  public:
+    static void capture_begin(const Device &d) { check(wgb_graph_capture_begin(d.raw())); }
+    static Graph capture_end(const Device &d) { Graph g; check(wgb_graph_capture_end(d.raw(), &g.h_)); return g; }
+    Graph(Graph &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Graph(const Graph &) = delete;
+    ~Graph() { if (h_) wgb_graph_destroy(h_); }
+    void launch() const { check(wgb_graph_launch(h_)); }
+  private:
+    Graph() = default;
+    wgb_graph *h_ = nullptr;
 };
 
 class Gemv {  // gemv.rs:9-137
