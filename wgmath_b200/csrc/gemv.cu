@@ -272,24 +272,6 @@ static void launch_one(const GemvArgs &a, dim3 grid, cudaStream_t st) {
     else gemv_n_kernel<VEC, NV><<<grid, kThreads, 0, st>>>(a);
 }
 
-// Resident CTAs per SM of the kernel that launch_sel would pick (queried once per instantiation).
-template <bool TR, bool VEC, int NV>
-static int occ_one() {
-    static int occ = 0;
-    if (occ == 0) {
-        int n = 0;
-        cudaError_t e = TR ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<VEC, NV>, kThreads, 0)
-                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_n_kernel<VEC, NV>, kThreads, 0);
-        occ = (e == cudaSuccess && n > 0) ? n : 4;
-    }
-    return occ;
-}
-template <bool TR>
-static int occ_sel(bool vec, int nv) {
-    if (vec) return nv == 1 ? occ_one<TR, true, 1>() : nv == 2 ? occ_one<TR, true, 2>() : occ_one<TR, true, 4>();
-    return nv == 1 ? occ_one<TR, false, 1>() : nv == 2 ? occ_one<TR, false, 2>() : occ_one<TR, false, 4>();
-}
-
 template <bool TR>
 static void launch_sel(bool vec, int nv, const GemvArgs &a, dim3 grid, cudaStream_t st) {
     if (vec) {
@@ -340,29 +322,17 @@ wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &s
               (nmats == 1 || a.sv % 4 == 0);
         tiles_x = (a.M + kWarps - 1) / kWarps;
     }
-    // Split the reduction axis when the output axis alone cannot fill the machine, and pick the split count whose CTA total
-    // is closest to a whole number of resident waves (a 3.46-wave grid measured 8 % slower than a 9.0-wave one).
-    const uint64_t resident = (uint64_t)ctx->prop.multiProcessorCount * (tr ? occ_sel<true>(vec, nv) : occ_sel<false>(vec, nv));
-    const uint64_t target = 2 * resident;
+    // Split the reduction axis when the output axis alone cannot fill the machine: aim at ~16 CTAs per SM in total.
+    // (A split count tuned to a whole number of resident waves — 13 splits for 65536 x 4096 gemv_tr — measured *slower*,
+    // 5742 vs 6072-6155 GB/s: more partials to fold and shorter streams per warp outweigh the fuller last wave.)
+    const uint64_t target = (uint64_t)ctx->prop.multiProcessorCount * 16;
     const uint32_t min_chunk = tr ? 2048 : 256;
     uint64_t nsplit = 1;
     if (tiles_x * zdim < target) {
-        uint64_t max_split = (a.K + min_chunk - 1) / min_chunk;
-        if (max_split > 65535) max_split = 65535;
-        if (max_split > 64) max_split = 64;
-        double best = -1.0;
-        for (uint64_t sp = 1; sp <= max_split; ++sp) {
-            const double waves = (double)(tiles_x * zdim * sp) / (double)resident;
-            const double full = waves < 1.0 ? 1.0 : (double)(uint64_t)(waves + 0.999999);
-            // efficiency of the last wave, slightly favouring >= 2 waves (more bytes in flight) and fewer splits
-            double eff = waves / full;
-            if (waves < 1.0) eff *= 0.9;
-            eff -= 0.002 * (double)sp;
-            if (eff > best) {
-                best = eff;
-                nsplit = sp;
-            }
-        }
+        nsplit = (target + tiles_x * zdim - 1) / (tiles_x * zdim);
+        const uint64_t max_split = (a.K + min_chunk - 1) / min_chunk;
+        if (nsplit > max_split) nsplit = max_split;
+        if (nsplit > 65535) nsplit = 65535;
     }
     uint32_t chunk = (uint32_t)(((uint64_t)a.K + nsplit - 1) / nsplit);
     chunk = (chunk + 31u) & ~31u;
