@@ -30,7 +30,6 @@ static constexpr int kThreads = 256;
 static constexpr int kWarps = 8;
 static constexpr int kTileRows = 128;
 static constexpr int kStage = 512;  // columns of v staged per step
-static constexpr int kVStage = 2048; // rows of v staged per step in gemv_tr
 
 struct GemvArgs {
     const float *m, *v;
@@ -183,48 +182,35 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc[c] = 0.f;
 
-    if (VEC) {
-        // v is shared by the 8 columns of this CTA: stage it through shared memory in 2048-row pieces so that only m streams
-        // from L2 (with long columns v does not stay in L1 and every m load used to be matched by an equal-sized v load).
-        __shared__ float4 vs4[NV][kVStage / 4];
-        for (uint32_t rs = r0; rs < r1; rs += kVStage) {
-            const uint32_t rn = min((uint32_t)kVStage, r1 - rs);
-            const uint32_t nvec = rn >> 2;               // rs is a multiple of 4 (r0 and kVStage are)
-            for (uint32_t idx = threadIdx.x; idx < NV * (kVStage / 4); idx += kThreads) {
-                const uint32_t c = idx / (kVStage / 4), i = idx % (kVStage / 4);
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (c < nv && i < nvec) val = __ldg(reinterpret_cast<const float4 *>(vp + (uint64_t)c * a.ldv + rs) + i);
-                vs4[c][i] = val;
-            }
-            __syncthreads();
-            if (valid) {
-                const float4 *cb = reinterpret_cast<const float4 *>(col + rs);
-                uint32_t i = lane;
-                for (; i + 96 < nvec; i += 128) {
-                    float4 x[4];
+    if (valid) {
+        if (VEC) {
+            const uint32_t nvec = (r1 - r0) >> 2;  // r0 is a multiple of 4 (chunk is)
+            const float *cb = col + r0;
+            const float *vb = vp + r0;
+            uint32_t i = lane;
+            for (; i + 96 < nvec; i += 128) {
+                float4 x[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = __ldcs(cb + i + 32 * u);
+                for (int u = 0; u < 4; ++u) x[u] = __ldcs(reinterpret_cast<const float4 *>(cb) + i + 32 * u);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-#pragma unroll
-                        for (int c = 0; c < NV; ++c) acc[c] = dot4(x[u], vs4[c][i + 32 * u], acc[c]);
-                }
-                for (; i < nvec; i += 32) {
-                    const float4 x = __ldcs(cb + i);
-#pragma unroll
-                    for (int c = 0; c < NV; ++c) acc[c] = dot4(x, vs4[c][i], acc[c]);
-                }
-                for (uint32_t r = rs + (nvec << 2) + lane; r < rs + rn; r += 32) {   // ragged last rows of the range
-                    const float x = col[r];
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
                     for (int c = 0; c < NV; ++c)
-                        if (c < nv) acc[c] = fmaf(x, vp[(uint64_t)c * a.ldv + r], acc[c]);
-                }
+                        if (c < nv) acc[c] = dot4(x[u], __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i + 32 * u), acc[c]);
             }
-            __syncthreads();
-        }
-    } else if (valid) {
-        {
+            for (; i < nvec; i += 32) {
+                const float4 x = __ldcs(reinterpret_cast<const float4 *>(cb) + i);
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c < nv) acc[c] = dot4(x, __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i), acc[c]);
+            }
+            for (uint32_t r = r0 + (nvec << 2) + lane; r < r1; r += 32) {
+                const float x = col[r];
+#pragma unroll
+                for (int c = 0; c < NV; ++c)
+                    if (c < nv) acc[c] = fmaf(x, vp[(uint64_t)c * a.ldv + r], acc[c]);
+            }
+        } else {
             uint32_t r = r0 + lane;
             for (; r + 96 < r1; r += 128) {
                 float x[4];
