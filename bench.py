@@ -108,22 +108,32 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- CPU baseline (oracle)
+def _cpu_operand(O, seed, rows, cols):
+    """Seeded U[0,1) operand; beyond 4096 x 4096 the seeded 4096-square block is tiled (values do not affect CPU timing and
+    generating 10^9 hashed elements in numpy would take longer than the measurement)."""
+    if rows <= 4096 and cols <= 4096:
+        return O.uniform(seed, rows, cols)
+    blk = O.uniform(seed, min(rows, 4096), min(cols, 4096)).reshape(min(cols, 4096), min(rows, 4096))
+    reps = (-(-cols // blk.shape[0]), -(-rows // blk.shape[1]))
+    return np.ascontiguousarray(np.tile(blk, reps)[:cols, :rows]).reshape(-1)
+
+
 def cpu_gemm_sample(target_s: float, n: int = 4096, repeat: int = 1):
     """Times the oracle's restatement of gemm.wgsl:81-113 on a row strip of the n^3 product (f32: the reference
-    has no bf16).  Returns (tflops, cores, description, seconds_per_run)."""
+    has no bf16).  Returns (tflops, cores, description, seconds_per_run, rows)."""
     from oracle import oracle as O
     cores = O.use_all_cores()
-    b = O.uniform(O.SEED_BASE + 2, n, n)
+    b = _cpu_operand(O, O.SEED_BASE + 2, n, n)
     # calibrate on 64 rows
     rows = 64
-    a = O.uniform(O.SEED_BASE + 1, rows, n)
+    a = _cpu_operand(O, O.SEED_BASE + 1, rows, n)
     out = np.zeros(rows * n, np.float32)
     t0 = time.perf_counter()
     O.gemm(O.GEMM, out, O.shape(rows, n), a, O.shape(rows, n), b, O.shape(n, n))
     dt = time.perf_counter() - t0
     rate = 2.0 * rows * n * n / dt
     rows = int(min(n, max(64, (target_s * rate / (2.0 * n * n)) // 64 * 64)))
-    a = O.uniform(O.SEED_BASE + 1, rows, n)
+    a = _cpu_operand(O, O.SEED_BASE + 1, rows, n)
     out = np.zeros(rows * n, np.float32)
     times = []
     for _ in range(repeat):
@@ -140,14 +150,13 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    n = 4096
+    n = 4096 * max(1, args.gpus)          # the same cube as the native arm's config at this N
     from oracle import oracle as O
-    cores = O.use_all_cores()
     # size the per-step sample so that (steps + warmup) steps finish in ~2 minutes at most
     budget = 100.0 / max(1, args.steps + args.warmup)
     tf, cores, desc, dt, rows = cpu_gemm_sample(min(2.0, budget), n, repeat=1)
-    b = O.uniform(O.SEED_BASE + 2, n, n)
-    a = O.uniform(O.SEED_BASE + 1, rows, n)
+    b = _cpu_operand(O, O.SEED_BASE + 2, n, n)
+    a = _cpu_operand(O, O.SEED_BASE + 1, rows, n)
     out = np.zeros(rows * n, np.float32)
     for _ in range(args.warmup):
         O.gemm(O.GEMM, out, O.shape(rows, n), a, O.shape(rows, n), b, O.shape(n, n))
