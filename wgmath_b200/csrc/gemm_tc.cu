@@ -225,7 +225,7 @@ struct TcArgs {
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
-    uint32_t npeers, my_rank, epoch;
+    uint32_t npeers, my_rank, epoch, handshake;
     char *dst[kMaxPeers];                     // where this rank's panel lives in rank d's gathered buffer
     unsigned int *ready_local;                // ready_local[q] >= epoch: rank q's buffer may be overwritten
     unsigned int *done_remote[kMaxPeers];     // rank q's done array; entry [my_rank] <- epoch when all stores are out
@@ -484,7 +484,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===================================== epilogue: TMEM -> registers -> global ==============
         const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
         uint32_t acc = 0, acc_phase = 0;
-        if (args.npeers > 1) {
+        if (args.handshake) {
             // fused all-gather: do not write into a peer before it has reached this step on its own queue
             if (threadIdx.x == 128)
                 for (uint32_t r = 0; r < args.npeers; ++r)
@@ -614,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
-        if (args.npeers > 1) {
+        if (args.handshake) {
             // all of this CTA's peer stores are out: make them visible system-wide, count the CTA, and let the last CTA of
             // the grid publish "rank my_rank's panel is complete" to every peer
             __threadfence_system();
@@ -996,6 +996,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     if (g.fused && g.fused->nranks > 1) {
         const FusedGather &f = *g.fused;
         args.npeers = (uint32_t)f.nranks;
+        args.handshake = 1;
         args.my_rank = (uint32_t)f.rank;
         args.epoch = f.epoch;
         for (int r = 0; r < f.nranks; ++r) {
@@ -1016,6 +1017,15 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     uint32_t sms = sms_total;
     const uint32_t margin = (uint32_t)comm_sm_margin(ctx);
     if (margin < sms / 2) sms -= margin;
+    if (args.npeers == 1) {
+        // diagnostics only (WGB_TC_DEBUG_FAKE_PEERS=n): issue the epilogue stores n times (all to the local buffer) to measure the
+        // SM-side cost of the fused all-gather's extra stores without NVLink
+        const int fake = env_int("WGB_TC_DEBUG_FAKE_PEERS", 0);
+        if (fake > 1 && fake <= kMaxPeers) {
+            args.npeers = (uint32_t)fake;
+            for (int r = 0; r < fake; ++r) args.dst[r] = (char *)args.c;
+        }
+    }
     args.ep_op = g.ep_op;
     args.ep = g.e ? (const char *)g.e + g.e_off * dtype_size(g.out_dtype) : nullptr;
     args.ep_ld = g.lde;
