@@ -1022,8 +1022,13 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         // SM-side cost of the fused all-gather's extra stores without NVLink
         const int fake = env_int("WGB_TC_DEBUG_FAKE_PEERS", 0);
         if (fake > 1 && fake <= kMaxPeers) {
-            args.npeers = (uint32_t)fake;
-            for (int r = 0; r < fake; ++r) args.dst[r] = (char *)args.c;
+            // replicas 1..n-1 go to distinct scratch panels (like distinct peers), replica 0 is the real output
+            const size_t c_bytes = ((size_t)(g.nmats - 1) * g.sc + (size_t)(g.N - 1) * g.ldc + g.M) * dtype_size(g.out_dtype);
+            void *scratch = nullptr;
+            if (workspace_reserve(ctx, 3, (size_t)(fake - 1) * c_bytes, &scratch) == WGB_OK) {
+                args.npeers = (uint32_t)fake;
+                for (int r = 1; r < fake; ++r) args.dst[r] = (char *)scratch + (size_t)(r - 1) * c_bytes;
+            }
         }
     }
     args.ep_op = g.ep_op;
