@@ -27,6 +27,7 @@
  *   wgb_reduce_columns     one launch for Reduce over every column of a matrix view
  *                          (reference: one Reduce dispatch per GpuMatrix::column(j))
  *   wgb_comm_*, wgb_gemm_row_sharded   8-GPU row-sharded GEMM + all-gather of C (NCCL / NVLink)
+ *   wgb_gemm_ord, wgb_gemv_ord   per-operand RowMajor / ColumnMajor ordering (tensor.rs:17-39, shape.wgsl:49-57)
  *   wgb_fill_uniform       seeded synthetic inputs generated in HBM (bench / tests)
  *
  * Conventions
@@ -231,6 +232,23 @@ wgb_status wgb_gemm_op(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
                        const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode f32_mode,
                        wgb_op_assign_variant op, const wgb_buffer *operand, const wgb_view_shape *operand_shape);
 
+/* Matrix ordering of a view: wgcore/src/tensor.rs:17-39 (ColumnMajor / RowMajor: MatrixOrdering, the type parameter of
+ * GpuTensorView) and the ROW_MAJOR branch of wgebra/src/linalg/shape.wgsl:49-57 switched on by row_major_shader_defs()
+ * (shape.rs:13-15): element (i, j) of a row-major view lives at offset + i * stride + j, `stride` being the distance between
+ * consecutive ROWS; size[] stays [rows, cols, mats] and stride_mat the distance between matrices.  No linalg shader of the
+ * reference enables the define, so these entry points are the defined-by-shape.wgsl superset: every
+ * combination of orderings is computed in place (no copy of a bf16 operand; an N-contiguous f32 m2 is transposed by the
+ * 3xTF32 split that re-materialises it anyway). */
+typedef enum wgb_ordering { WGB_COLUMN_MAJOR = 0, WGB_ROW_MAJOR = 1 } wgb_ordering;
+
+/* wgb_gemm_ex / wgb_gemm_op with an ordering per operand.  op < 0: no fused element-wise step (operand ignored); otherwise
+ * `operand` is a view ordered like `out`. */
+wgb_status wgb_gemm_ord(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *out_shape,
+                        wgb_ordering out_ordering, const wgb_buffer *m1, const wgb_view_shape *m1_shape,
+                        wgb_ordering m1_ordering, const wgb_buffer *m2, const wgb_view_shape *m2_shape,
+                        wgb_ordering m2_ordering, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode f32_mode, int op,
+                        const wgb_buffer *operand, const wgb_view_shape *operand_shape);
+
 /* Host-buffer GEMM: out_host = m1_host * m2_host (or tr(m1_host) * m2_host) with dense column-major host matrices
  * (leading dimensions = row counts).  Equivalent to build_init(m1), build_init(m2), dispatch, read — the sequence of
  * the reference's own tests (gemm.rs:156-193) — but pipelined: m2 is uploaded and the product downloaded in column
@@ -250,6 +268,11 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out,
                     const wgb_view_shape *out_shape, const wgb_buffer *m,
                     const wgb_view_shape *m_shape, const wgb_buffer *v,
                     const wgb_view_shape *v_shape);
+
+/* wgb_gemv with a row- or column-major m (v and out stay column-major: a contiguous vector is the same in both). */
+wgb_status wgb_gemv_ord(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *out_shape,
+                        const wgb_buffer *m, const wgb_view_shape *m_shape, wgb_ordering m_ordering, const wgb_buffer *v,
+                        const wgb_view_shape *v_shape);
 
 /* op_assign.rs:71-94.  a[i] = a[i] (op) b[i]; only size[0] and offset of the shapes are used
  * (shape.wgsl:36-38 iv()). */

@@ -66,6 +66,8 @@ def lib():
         L.orc_gemm_f64.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_uint32,
                                    ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, fp, sp, fp, sp]
         L.orc_gemm_f64.restype = None
+        L.orc_gemm_ord.argtypes = [ctypes.c_int, fp, sp, ctypes.c_int, fp, sp, ctypes.c_int, fp, sp, ctypes.c_int]
+        L.orc_gemv_ord.argtypes = [ctypes.c_int, fp, sp, fp, sp, ctypes.c_int, fp, sp]
         L.orc_num_threads.restype = ctypes.c_int
         L.orc_set_num_threads.argtypes = [ctypes.c_int]
         L.orc_set_num_threads.restype = None
@@ -88,6 +90,17 @@ def gemv(variant, out, so, m, sm, v, sv):
     rc = lib().orc_gemv(variant, _fp(out), ctypes.byref(so), _fp(m), ctypes.byref(sm), _fp(v), ctypes.byref(sv),
                         ctypes.byref(ran))
     return rc, ran.value
+
+
+def gemm_ord(variant, out, so, out_rm, m1, s1, m1_rm, m2, s2, m2_rm) -> int:
+    """gemm on views that are each column-major (0) or row-major (1): shape.wgsl:49-57 addressing."""
+    return lib().orc_gemm_ord(variant, _fp(out), ctypes.byref(so), int(out_rm), _fp(m1), ctypes.byref(s1), int(m1_rm),
+                              _fp(m2), ctypes.byref(s2), int(m2_rm))
+
+
+def gemv_ord(variant, out, so, m, sm, m_rm, v, sv) -> int:
+    return lib().orc_gemv_ord(variant, _fp(out), ctypes.byref(so), _fp(m), ctypes.byref(sm), int(m_rm), _fp(v),
+                              ctypes.byref(sv))
 
 
 def op_assign(op, a, sa, b, sb) -> int:

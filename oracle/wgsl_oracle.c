@@ -7,7 +7,8 @@
  * imports or calls anything in oracle/.
  *
  * What it restates (all paths relative to /root/reference/crates/wgebra/src/linalg/):
- *   shape.wgsl:36-66      iv / im / it / div_ceil4 / with_vec4_elts (column-major branch)
+ *   shape.wgsl:36-66      iv / im / it / div_ceil4 / with_vec4_elts (column-major branch; the ROW_MAJOR
+ *                         addressing of :49-53 is restated by orc_gemm_ord / orc_gemv_ord)
  *   gemm.wgsl:81-113      gemm           (thread owns 4 rows x all N, 4x4 blocks over K)
  *   gemm.wgsl:29-78       gemm_fast      (64 threads split K by 256, 6-step mat4x4 tree)
  *   gemm.wgsl:116-148     gemm_tr
@@ -391,6 +392,57 @@ void orc_gemm_f64(int tr, double *out /* dense col-major M x N per mat */, uint3
                 out[((size_t)t * N + (size_t)n) * M + i] = acc;
             }
     }
+}
+
+/* ---- row-major views (shape.wgsl:49-57, the ROW_MAJOR branch) ----------------------- */
+/* No linalg shader of the reference is compiled with row_major_shader_defs() (shape.rs:13-15), so there is no vec4 kernel
+ * body to restate for it: what the reference defines is the ADDRESS of element (i, j, t) of a row-major view
+ * (im(): offset + i * stride + j, it(): t * stride_mat + im).  These two functions are gemm.wgsl:81-148 / gemv.wgsl:68-115
+ * written per scalar element on top of that addressing, with an ordering flag (0 column-major, 1 row-major) per operand:
+ * f32 products summed over k in increasing order, no contraction.  They are the checker for wgb_gemm_ord / wgb_gemv_ord. */
+static inline uint32_t it_ord(shape_t v, int row_major, uint32_t i, uint32_t j, uint32_t t) {
+    return t * v.stride_mat + v.offset + (row_major ? i * v.stride + j : i + j * v.stride);
+}
+
+int orc_gemm_ord(int variant, float *out, const shape_t *so, int out_rm, const float *m1, const shape_t *s1, int m1_rm,
+                 const float *m2, const shape_t *s2, int m2_rm) {
+    int rc = gemm_check(*so, *s1, *s2, variant);
+    if (rc) return rc;
+    const int tr = variant == GEMM_TR || variant == GEMM_TR_FAST;
+    const uint32_t K = s2->nrows;
+    for (uint32_t t = 0; t < so->nmats; ++t) {
+#pragma omp parallel for schedule(static)
+        for (int64_t n = 0; n < (int64_t)so->ncols; ++n)
+            for (uint32_t i = 0; i < so->nrows; ++i) {
+                float acc = 0.f;
+                for (uint32_t k = 0; k < K; ++k) {
+                    const float a = tr ? m1[it_ord(*s1, m1_rm, k, i, t)] : m1[it_ord(*s1, m1_rm, i, k, t)];
+                    acc = acc + a * m2[it_ord(*s2, m2_rm, k, (uint32_t)n, t)];
+                }
+                out[it_ord(*so, out_rm, i, (uint32_t)n, t)] = acc;
+            }
+    }
+    return ORC_OK;
+}
+
+int orc_gemv_ord(int variant, float *out, const shape_t *so, const float *m, const shape_t *sm, int m_rm, const float *v,
+                 const shape_t *sv) {
+    const int tr = variant == 2 || variant == 3;
+    const uint32_t rows = tr ? sm->ncols : sm->nrows, cols = tr ? sm->nrows : sm->ncols;
+    if (cols != sv->nrows || rows != so->nrows) return ORC_DIM_MISMATCH;   /* gemv.rs:89-90 */
+    for (uint32_t t = 0; t < so->nmats; ++t)
+        for (uint32_t c = 0; c < so->ncols; ++c) {
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < (int64_t)rows; ++i) {
+                float acc = 0.f;
+                for (uint32_t k = 0; k < cols; ++k) {
+                    const float a = tr ? m[it_ord(*sm, m_rm, k, (uint32_t)i, t)] : m[it_ord(*sm, m_rm, (uint32_t)i, k, t)];
+                    acc = acc + a * v[it_ord(*sv, 0, k, c, t)];
+                }
+                out[it_ord(*so, 0, (uint32_t)i, c, t)] = acc;
+            }
+        }
+    return ORC_OK;
 }
 
 /* torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core it can. */

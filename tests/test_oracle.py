@@ -154,3 +154,50 @@ def test_golden_fixtures():
     for op, key in [(O.RED_MIN, "min"), (O.RED_MAX, "max"), (O.RED_SUM, "sum"), (O.RED_PROD, "prod"), (O.RED_SQNORM, "sqnorm")]:
         got = O.reduce(op, l1["x345"], O.shape(345))
         assert abs(got - l1[key]) <= 1e-5 * abs(l1[key]) + 1e-37
+
+
+@pytest.mark.parametrize("tr", [0, 2])
+def test_row_major_addressing_restatement(tr):
+    """orc_gemm_ord / orc_gemv_ord (shape.wgsl:49-57): every ordering combination equals the float64 product, equals the
+    literal vec4 restatement when everything is column-major, and never writes outside the output view."""
+    rng = np.random.default_rng(7)
+    M, N, K, T = 12, 20, 16, 2
+    for ro in (0, 1):
+        for r1 in (0, 1):
+            for r2 in (0, 1):
+                a_dims = (K, M) if tr else (M, K)
+                A, B = rng.random((T,) + a_dims, dtype=np.float32), rng.random((T, K, N), dtype=np.float32)
+
+                def pack(X, rm, pad, off):
+                    r, c = X.shape[1:]
+                    ld = (c if rm else r) + pad
+                    smat = ld * (r if rm else c) + 4
+                    buf = np.full(off + smat * T, np.float32(-7.0))
+                    for t in range(T):
+                        for i in range(r):
+                            for j in range(c):
+                                buf[off + t * smat + (i * ld + j if rm else i + j * ld)] = X[t, i, j]
+                    return buf, O.Shape(r, c, T, ld, smat, off)
+                a, sa = pack(A, r1, 4, 8)
+                b, sb = pack(B, r2, 0, 4)
+                c0, sc = pack(np.zeros((T, M, N), np.float32), ro, 4, 4)
+                out = np.full_like(c0, np.float32(-7.0))
+                assert O.gemm_ord(tr, out, sc, ro, a, sa, r1, b, sb, r2) == O.ORC_OK
+                ref = np.einsum("tkm,tkn->tmn" if tr else "tmk,tkn->tmn", A.astype(np.float64), B.astype(np.float64))
+                want, _ = pack(ref.astype(np.float32), ro, 4, 4)
+                live = c0 == 0
+                np.testing.assert_allclose(out[live], want[live], rtol=2e-6)
+                assert np.all(out[~live] == np.float32(-7.0))
+                if (ro, r1, r2) == (0, 0, 0):
+                    lit = np.full_like(c0, np.float32(-7.0))
+                    assert O.gemm(tr, lit, sc, a, sa, b, sb) == O.ORC_OK
+                    np.testing.assert_allclose(lit[live], out[live], rtol=2e-6)
+    # gemv with a row-major matrix == gemv_tr / gemv on the transposed column-major memory
+    R, C = 24, 40
+    Mx, v = rng.random((R, C), dtype=np.float32), rng.random(R if tr else C, dtype=np.float32)
+    out = np.zeros(C if tr else R, np.float32)
+    sm = O.Shape(R, C, 1, C, R * C, 0)
+    assert O.gemv_ord(tr, out, O.shape(out.size), np.ascontiguousarray(Mx).reshape(-1), sm, 1, v, O.shape(v.size)) == O.ORC_OK
+    np.testing.assert_allclose(out, (Mx.T if tr else Mx).astype(np.float64) @ v.astype(np.float64), rtol=2e-6)
+    bad = np.zeros(3, np.float32)
+    assert O.gemv_ord(tr, bad, O.shape(3), np.ascontiguousarray(Mx).reshape(-1), sm, 1, v, O.shape(v.size)) == O.ORC_DIM_MISMATCH

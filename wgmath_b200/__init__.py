@@ -8,6 +8,6 @@ from .gpu import CommandEncoder, ComputePass, Device, GpuInstance, Graph, Queue 
 from .linalg import (Dot, F32Mode, Gemm, GemmVariant, Gemv, GemvVariant, OpAssign, OpAssignVariant, Reduce,  # noqa: F401
                      ReduceOp, fill_uniform)
 from .shapes import ViewShape, ViewShapeBuffers  # noqa: F401
-from .tensor import (BufferUsages, GpuCube, GpuCubeView, GpuMatrix, GpuMatrixView, GpuScalar, GpuTensor,  # noqa: F401
+from .tensor import (BufferUsages, ColumnMajor, RowMajor, GpuCube, GpuCubeView, GpuMatrix, GpuMatrixView, GpuScalar, GpuTensor,  # noqa: F401
                      GpuTensorView, GpuVector, GpuVectorView, TensorBuilder, as_view)
 from .timestamps import GpuTimestamps  # noqa: F401

@@ -534,11 +534,27 @@ wgb_status wgb_fill_uniform(wgb_pass *pass, wgb_buffer *buf, const wgb_view_shap
     return launch_fill_uniform(pass, buf->ptr, *s, dt, seed, row0, col0);
 }
 
+// A row-major [r x c] view (shape.wgsl:49-53: element (i, j) at offset + i * stride + j) addresses the same memory as the
+// column-major [c x r] view with the same stride / stride_mat / offset, i.e. its transpose.
+static wgb_view_shape transposed_shape(const wgb_view_shape &s) {
+    wgb_view_shape t = s;
+    t.size[0] = s.size[1];
+    t.size[1] = s.size[0];
+    return t;
+}
+static bool bad_ordering(wgb_ordering o) { return (int)o != WGB_COLUMN_MAJOR && (int)o != WGB_ROW_MAJOR; }
+
 wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *so,
                     const wgb_buffer *m, const wgb_view_shape *sm, const wgb_buffer *v, const wgb_view_shape *sv) {
+    return wgb_gemv_ord(pass, variant, out, so, m, sm, WGB_COLUMN_MAJOR, v, sv);
+}
+
+wgb_status wgb_gemv_ord(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *so, const wgb_buffer *m,
+                        const wgb_view_shape *sm, wgb_ordering m_ord, const wgb_buffer *v, const wgb_view_shape *sv) {
     if (!pass || !out || !so || !m || !sm || !v || !sv) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: null argument");
     if ((int)variant < 0 || (int)variant > WGB_GEMV_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: unknown variant %d", (int)variant);
-    const bool tr = variant == WGB_GEMV_TR || variant == WGB_GEMV_TR_FAST;
+    if (bad_ordering(m_ord)) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: unknown ordering %d", (int)m_ord);
+    bool tr = variant == WGB_GEMV_TR || variant == WGB_GEMV_TR_FAST;
     const uint32_t m_rows = tr ? sm->size[1] : sm->size[0];
     const uint32_t m_cols = tr ? sm->size[0] : sm->size[1];
     if (m_cols != sv->size[0])  // gemv.rs:89
@@ -558,6 +574,10 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, c
                  so->size[1], so->size[2], sv->size[1], sv->size[2], sm->size[2]);
     if (any_zero_buffer({out, m, v}) || view_extent(*so) == 0) return WGB_OK;
     wgb_view_shape sv_used = *sv, sm_used = *sm;
+    if (m_ord == WGB_ROW_MAJOR) {   // the same memory read as the column-major transpose
+        sm_used = transposed_shape(*sm);
+        tr = !tr;
+    }
     sv_used.size[1] = so->size[1];
     sv_used.size[2] = so->size[2];
     sm_used.size[2] = so->size[2];
@@ -571,12 +591,15 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, c
 static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
                               const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
                               wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode, int ep_op, const wgb_buffer *e,
-                              const wgb_view_shape *se) {
+                              const wgb_view_shape *se, wgb_ordering out_ord = WGB_COLUMN_MAJOR,
+                              wgb_ordering m1_ord = WGB_COLUMN_MAJOR, wgb_ordering m2_ord = WGB_COLUMN_MAJOR) {
     if (!pass || !out || !so || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: null argument");
     if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown variant %d", (int)variant);
     if ((in_dtype != WGB_F32 && in_dtype != WGB_BF16) || (out_dtype != WGB_F32 && out_dtype != WGB_BF16))
         WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm: unsupported dtype");
     if ((int)mode < 0 || (int)mode > WGB_F32_SIMT) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown f32 mode %d", (int)mode);
+    if (bad_ordering(out_ord) || bad_ordering(m1_ord) || bad_ordering(m2_ord)) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm: unknown ordering");
+    const bool ro = out_ord == WGB_ROW_MAJOR, r1 = m1_ord == WGB_ROW_MAJOR, r2 = m2_ord == WGB_ROW_MAJOR;
     const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
     const uint32_t m_rows = tr ? s1->size[1] : s1->size[0];
     const uint32_t m_cols = tr ? s1->size[0] : s1->size[1];
@@ -588,19 +611,35 @@ static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buff
     if (so->size[2] != s2->size[2]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (out mats %u vs m2 mats %u)", so->size[2], s2->size[2]);
     pass->last_gemm_path = 0;
     if (any_zero_buffer({out, m1, m2}) || view_extent(*so) == 0) return WGB_OK;
-    WGB_TRY(check_view(out, *so, dtype_size(out_dtype), "gemm out"));
-    WGB_TRY(check_view(m1, *s1, dtype_size(in_dtype), "gemm m1"));
-    WGB_TRY(check_view(m2, *s2, dtype_size(in_dtype), "gemm m2"));
+    WGB_TRY(check_view(out, ro ? transposed_shape(*so) : *so, dtype_size(out_dtype), "gemm out"));
+    WGB_TRY(check_view(m1, r1 ? transposed_shape(*s1) : *s1, dtype_size(in_dtype), "gemm m1"));
+    WGB_TRY(check_view(m2, r2 ? transposed_shape(*s2) : *s2, dtype_size(in_dtype), "gemm m2"));
+    // Canonical device problem: C (column-major) = A * B with "K contiguous in A's memory" (tr) and "N contiguous in B's
+    // memory" (b_nmajor) as the only layout facts.  A row-major out is computed as out^T = m2^T * op(m1)^T.
+    const bool a_k = tr != r1;   // K is the contiguous axis of m1's memory
+    const bool b_n = r2;         // N is the contiguous axis of m2's memory
     GemmProblem g{};
-    g.tr = tr;
-    g.M = so->size[0];
-    g.N = so->size[1];
     g.K = m_cols;
     g.nmats = so->size[2];
-    g.a = m1->ptr; g.b = m2->ptr; g.c = out->ptr;
-    g.a_off = s1->offset; g.b_off = s2->offset; g.c_off = so->offset;
-    g.lda = s1->stride; g.ldb = s2->stride; g.ldc = so->stride;
-    g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = so->stride_mat;
+    g.c = out->ptr;
+    g.c_off = so->offset;
+    g.ldc = so->stride;
+    g.sc = so->stride_mat;
+    if (!ro) {
+        g.tr = a_k;
+        g.b_nmajor = b_n;
+        g.M = so->size[0];
+        g.N = so->size[1];
+        g.a = m1->ptr; g.a_off = s1->offset; g.lda = s1->stride; g.sa = s1->stride_mat;
+        g.b = m2->ptr; g.b_off = s2->offset; g.ldb = s2->stride; g.sb = s2->stride_mat;
+    } else {
+        g.tr = !b_n;
+        g.b_nmajor = !a_k;
+        g.M = so->size[1];
+        g.N = so->size[0];
+        g.a = m2->ptr; g.a_off = s2->offset; g.lda = s2->stride; g.sa = s2->stride_mat;
+        g.b = m1->ptr; g.b_off = s1->offset; g.ldb = s1->stride; g.sb = s1->stride_mat;
+    }
     g.in_dtype = in_dtype;
     g.out_dtype = out_dtype;
     if (ep_op >= 0) {
@@ -610,7 +649,7 @@ static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buff
             WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Op-assign: dimension mismatch. (operand %u x %u x %u vs out %u x %u x %u)", se->size[0],
                      se->size[1], se->size[2], so->size[0], so->size[1], so->size[2]);
         if (e->bytes == 0) return WGB_OK;
-        WGB_TRY(check_view(e, *se, dtype_size(out_dtype), "gemm_op operand"));
+        WGB_TRY(check_view(e, ro ? transposed_shape(*se) : *se, dtype_size(out_dtype), "gemm_op operand"));   // e is ordered like out
         g.ep_op = ep_op;
         g.e = e->ptr;
         g.e_off = se->offset;
@@ -638,6 +677,14 @@ wgb_status wgb_gemm_op(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
     return gemm_common(pass, variant, out, so, m1, s1, m2, s2, in_dtype, out_dtype, mode, (int)op, operand, operand_shape);
 }
 
+
+wgb_status wgb_gemm_ord(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so, wgb_ordering out_ord,
+                        const wgb_buffer *m1, const wgb_view_shape *s1, wgb_ordering m1_ord, const wgb_buffer *m2,
+                        const wgb_view_shape *s2, wgb_ordering m2_ord, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
+                        int op, const wgb_buffer *operand, const wgb_view_shape *operand_shape) {
+    return gemm_common(pass, variant, out, so, m1, s1, m2, s2, in_dtype, out_dtype, mode, op < 0 ? -1 : op, operand, operand_shape,
+                       out_ord, m1_ord, m2_ord);
+}
 
 wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
                          const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,

@@ -157,7 +157,8 @@ struct FusedGather {
 
 struct GemmProblem {
     const FusedGather *fused = nullptr;   // non-null: write C into every rank's gathered buffer (comm.cu)
-    bool tr;               // out = tr(m1) * m2
+    bool tr;               // K is the contiguous axis of m1 (out = tr(m1) * m2 on column-major views)
+    bool b_nmajor = false; // N is the contiguous axis of m2 (a row-major m2); false: K contiguous (column-major m2)
     uint32_t M, N, K, nmats;
     const void *a;         // m1 base (element 0 of the buffer)
     const void *b;         // m2 base

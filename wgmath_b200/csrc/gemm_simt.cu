@@ -3,7 +3,8 @@
 //
 // Semantics follow gemm.wgsl:81-113 (out = m1 * m2) and :116-148 (out = tr(m1) * m2) of
 // /root/reference/crates/wgebra/src/linalg/, for any M, N, K (the reference requires multiples of 4),
-// any column / matrix stride and offset, batched over size[2] (gemm.rs:126 grid.y).
+// any column / matrix stride and offset, batched over size[2] (gemm.rs:126 grid.y).  BT: m2 is N-contiguous
+// (a row-major m2, shape.wgsl:49-53), the product is unchanged.
 //
 // Shape: 128x128 output tile per CTA, K step 8, 256 threads x (8x8) register tile, operands staged in
 // shared memory K-major so the inner loop reads two float4 per operand per k; global loads are
@@ -41,7 +42,7 @@ struct SimtArgs {
     uint64_t lde, se;
 };
 
-template <bool TR, typename TIn, typename TOut>
+template <bool TR, bool BT, typename TIn, typename TOut>
 __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g) {
     __shared__ __align__(16) float As[2][BK][BM + PAD];
     __shared__ __align__(16) float Bs[2][BK][BN + PAD];
@@ -64,8 +65,13 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g) {
                 const uint32_t k = k0 + (idx % BK), m = m0 + (idx / BK);
                 ra[e] = (m < g.M && k < g.K) ? to_f32<TIn>(A[(uint64_t)m * g.lda + k]) : 0.f;
             }
-            const uint32_t k = k0 + (idx % BK), n = n0 + (idx / BK);
-            rb[e] = (n < g.N && k < g.K) ? to_f32<TIn>(B[(uint64_t)n * g.ldb + k]) : 0.f;
+            if (!BT) {  // B is K x N, K contiguous
+                const uint32_t k = k0 + (idx % BK), n = n0 + (idx / BK);
+                rb[e] = (n < g.N && k < g.K) ? to_f32<TIn>(B[(uint64_t)n * g.ldb + k]) : 0.f;
+            } else {    // B is N x K in memory, N contiguous
+                const uint32_t n = n0 + (idx % BN), k = k0 + (idx / BN);
+                rb[e] = (n < g.N && k < g.K) ? to_f32<TIn>(B[(uint64_t)k * g.ldb + n]) : 0.f;
+            }
         }
     };
     auto store_tiles = [&](int buf) {
@@ -74,7 +80,8 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g) {
             const int idx = tid + NT * e;
             if (!TR) As[buf][idx / BM][idx % BM] = ra[e];
             else As[buf][idx % BK][idx / BK] = ra[e];
-            Bs[buf][idx % BK][idx / BK] = rb[e];
+            if (!BT) Bs[buf][idx % BK][idx / BK] = rb[e];
+            else Bs[buf][idx / BN][idx % BN] = rb[e];
         }
     };
 
@@ -127,12 +134,12 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(SimtArgs g) {
     }
 }
 
-template <bool TR>
+template <bool TR, bool BT>
 void launch_typed(const GemmProblem &p, const SimtArgs &a, dim3 grid, cudaStream_t st) {
-    if (p.in_dtype == WGB_F32 && p.out_dtype == WGB_F32) gemm_simt_kernel<TR, float, float><<<grid, NT, 0, st>>>(a);
-    else if (p.in_dtype == WGB_F32) gemm_simt_kernel<TR, float, __nv_bfloat16><<<grid, NT, 0, st>>>(a);
-    else if (p.out_dtype == WGB_F32) gemm_simt_kernel<TR, __nv_bfloat16, float><<<grid, NT, 0, st>>>(a);
-    else gemm_simt_kernel<TR, __nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(a);
+    if (p.in_dtype == WGB_F32 && p.out_dtype == WGB_F32) gemm_simt_kernel<TR, BT, float, float><<<grid, NT, 0, st>>>(a);
+    else if (p.in_dtype == WGB_F32) gemm_simt_kernel<TR, BT, float, __nv_bfloat16><<<grid, NT, 0, st>>>(a);
+    else if (p.out_dtype == WGB_F32) gemm_simt_kernel<TR, BT, __nv_bfloat16, float><<<grid, NT, 0, st>>>(a);
+    else gemm_simt_kernel<TR, BT, __nv_bfloat16, __nv_bfloat16><<<grid, NT, 0, st>>>(a);
 }
 
 }  // namespace
@@ -154,8 +161,13 @@ wgb_status launch_gemm_simt(wgb_pass *p, const GemmProblem &g) {
     for (uint32_t z0 = 0; z0 < g.nmats; z0 += 65535) {
         a.z_base = z0;
         dim3 grid(gx, gy, g.nmats - z0 < 65535 ? g.nmats - z0 : 65535);
-        if (g.tr) launch_typed<true>(g, a, grid, p->stream);
-        else launch_typed<false>(g, a, grid, p->stream);
+        if (g.tr) {
+            if (g.b_nmajor) launch_typed<true, true>(g, a, grid, p->stream);
+            else launch_typed<true, false>(g, a, grid, p->stream);
+        } else {
+            if (g.b_nmajor) launch_typed<false, true>(g, a, grid, p->stream);
+            else launch_typed<false, false>(g, a, grid, p->stream);
+        }
         WGB_CUDA(cudaGetLastError());
         count_launch(p->ctx);
     }

@@ -198,12 +198,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
-constexpr uint32_t make_idesc(int kind, bool a_mn_major, int m, int n) {
+constexpr uint32_t make_idesc(int kind, bool a_mn_major, bool b_mn_major, int m, int n) {
     const uint32_t fmt = kind == 0 ? 1u /* BF16 */ : 2u /* TF32 */;
     return (1u << 4)                      // accumulator format F32
            | (fmt << 7) | (fmt << 10)     // A / B element format
            | ((a_mn_major ? 1u : 0u) << 15)  // A major-ness (0 = K-major)
-           | (0u << 16)                   // B is always K-major here
+           | ((b_mn_major ? 1u : 0u) << 16)  // B major-ness (0 = K-major)
            | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
@@ -317,7 +317,8 @@ template <>
 __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
 // KIND: 0 = bf16 (kind::f16), 1 = tf32.  A_MN: operand A is MN-major (the non-transposed product).
-template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
+// B_MN: operand B is MN-major, i.e. N is its contiguous axis (a row-major m2; bf16 only, f32 operands are re-materialised).
+template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -330,7 +331,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int A_ATOMS = A_MN ? (kBlockM * ES) / kRowBytes : 1;   // MN-major: 128-byte atoms along M (2 bf16 / 4 tf32)
     constexpr int A_ATOM_ELEMS = kRowBytes / ES;
     constexpr int A_ATOM_BYTES = BLOCK_K * kRowBytes;     // one atom column: BLOCK_K rows of 128 B
-    constexpr uint32_t IDESC = make_idesc(KIND, A_MN, kBlockM * CG, BN);
+    constexpr uint32_t IDESC = make_idesc(KIND, A_MN, B_MN, kBlockM * CG, BN);
+    static_assert(!B_MN || KIND == 0, "MN-major B is implemented for 16-bit operands only");
     constexpr int STAGES = Cfg::STAGES;
     constexpr bool CHUNKED = PASSES == 3;
 
@@ -421,6 +423,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
                     }
                     if (args.debug_skip & 2u) {
+                    } else if (B_MN) {   // 128-byte atoms along N, each BLOCK_K rows deep
+                        for (uint32_t at = 0; at * A_ATOM_ELEMS < b_rows; ++at) {
+                            if (CG == 2) tma_load_3d_2sm(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
+                            else tma_load_3d(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
+                        }
                     } else if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
                     else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
                 }
@@ -453,17 +460,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int j = 0; j < K_STEPS; ++j) {
                             // K advance inside the swizzled tile: 32 B (K-major) or UMMA_K rows of 128 B (MN-major)
                             const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
-                            const uint32_t b_off = j * 32;
+                            const uint32_t b_off = B_MN ? j * UMMA_K * kRowBytes : j * 32;
+                            const uint32_t b_lbo = B_MN ? A_ATOM_BYTES : 16;
                             const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
                             // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
                             constexpr bool A32 = A_MN && KIND == 1;
                             const uint32_t a_sbo = A32 ? 512 : 1024, a_lt = A32 ? 1 : 2;
                             const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, a_sbo, a_lt);
-                            const uint64_t db_hi = make_smem_desc(sb_hi + b_off, 16, sbo);
+                            const uint64_t db_hi = make_smem_desc(sb_hi + b_off, b_lbo, sbo);
                             const uint32_t first = (kb == chain_begin && j == 0) ? 0u : 1u;
                             if (PASSES == 3) {
                                 const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
-                                const uint64_t db_lo = make_smem_desc(sb_lo + b_off, 16, sbo);
+                                const uint64_t db_lo = make_smem_desc(sb_lo + b_off, b_lbo, sbo);
                                 umma<KIND, CG>(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
                                 umma<KIND, CG>(d_tmem, da_hi, db_lo, idesc, 1u);
                                 umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, 1u);
@@ -782,10 +790,10 @@ struct TcMaps {
     CUtensorMap a, alo, b, blo, bt, blot;   // operands (hi / lo), and B with the narrow box of the tail strips
 };
 
-template <int KIND, bool A_MN, int BN, int PASSES, typename TOut, int CG>
+template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
 wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     using Cfg = TcCfg<BN, PASSES, CG>;
-    auto kern = gemm_tc_kernel<KIND, A_MN, BN, PASSES, TOut, CG>;
+    auto kern = gemm_tc_kernel<KIND, A_MN, B_MN, BN, PASSES, TOut, CG>;
     static bool attr_set[64] = {};   // per instantiation, per device
     const int dev = p->ctx->device & 63;
     if (!attr_set[dev]) {
@@ -816,18 +824,18 @@ wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     return WGB_OK;
 }
 
-template <int KIND, bool A_MN, int PASSES, typename TOut>
+template <int KIND, bool A_MN, bool B_MN, int PASSES, typename TOut>
 wgb_status launch_sel(wgb_pass *p, int bn, int cg, const TcMaps &m, const TcArgs &args) {
     if constexpr (PASSES == 3) {   // 3xTF32: BLOCK_N = 128 only (two accumulator stages + running sum in TMEM)
-        if (cg == 2) return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, m, args);
-        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, m, args);
+        if (cg == 2) return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 2>(p, m, args);
+        return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 1>(p, m, args);
     } else {
         if (cg == 2) {
-            if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 2>(p, m, args);
-            return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 2>(p, m, args);
+            if (bn == 256) return launch_cfg<KIND, A_MN, B_MN, 256, PASSES, TOut, 2>(p, m, args);
+            return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 2>(p, m, args);
         }
-        if (bn == 256) return launch_cfg<KIND, A_MN, 256, PASSES, TOut, 1>(p, m, args);
-        return launch_cfg<KIND, A_MN, 128, PASSES, TOut, 1>(p, m, args);
+        if (bn == 256) return launch_cfg<KIND, A_MN, B_MN, 256, PASSES, TOut, 1>(p, m, args);
+        return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 1>(p, m, args);
     }
 }
 
@@ -864,7 +872,7 @@ static int pick_bn(uint32_t M, uint32_t N, uint32_t nmats, int cg, uint32_t sms)
 // Default: cut each tail tile into 2 or 4 column strips (narrower complete tiles, no fix-up) when that still fits one wave:
 // a 128- / 64-column strip costs ~0.75 / ~0.63 of a 256-column tile (the A tile is loaded either way).
 // WGB_TC_SPLITK=1 selects the K split with a workspace fix-up instead (measured slower, kept for reference).
-static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bool a_mn) {
+static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bool a_mn, bool b_mn) {
     a.full_tiles = a.total_tiles;
     a.split = 1;
     a.kb_per_split = a.num_kb;
@@ -892,7 +900,7 @@ static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bo
     uint32_t nsplit = 1;
     for (uint32_t cand : {4u, 2u}) {
         const uint32_t w = (uint32_t)bn / cand;
-        if ((uint64_t)tail * cand <= clusters && w >= 32 && (w / cg) % 8 == 0) {
+        if ((uint64_t)tail * cand <= clusters && w >= 32 && (w / cg) % (b_mn ? 64 : 8) == 0) {   // MN-major B: whole 128 B atoms
             nsplit = cand;
             break;
         }
@@ -901,7 +909,7 @@ static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bo
     a.full_tiles = a.total_tiles - tail;
     a.nsplit = nsplit;
     a.tail_bn = (uint32_t)bn / nsplit;
-    a.idesc_tail = make_idesc(kind, a_mn, kBlockM * cg, (int)a.tail_bn);
+    a.idesc_tail = make_idesc(kind, a_mn, b_mn, kBlockM * cg, (int)a.tail_bn);
     a.total_units = a.full_tiles + tail * nsplit;
 }
 
@@ -914,13 +922,13 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     // "transpose": the prep kernel writes tr(m1) dense and the K-major kernel variant runs (always valid).
     const bool mn_direct = env_int("WGB_TF32_MN_DIRECT", 1) != 0;   // validated on B200: direct is the default
     const bool transpose_a = f32 && !g.tr && !mn_direct;
-    if (f32 && passes == 1 && !transpose_a &&
-        !(aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4))) {
+    // An N-contiguous (row-major) f32 m2 is always re-materialised K-major by the transposing prep; a bf16 one is read in
+    // place as an MN-major B operand.
+    const bool transpose_b = f32 && g.b_nmajor;
+    const bool prep_a = f32 && (passes == 3 || transpose_a), prep_b = f32 && (passes == 3 || transpose_b);
+    if (f32 && ((!prep_a && !aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4)) ||
+                (!prep_b && !aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)))) {
         *path_out = 1;   // single-pass TF32 reads the caller's views directly: needs TMA alignment
-        return launch_gemm_simt(p, g);
-    }
-    if (f32 && passes == 1 && transpose_a && !aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)) {
-        *path_out = 1;
         return launch_gemm_simt(p, g);
     }
     if (g.nmats > 65535 && f32) {
@@ -938,7 +946,8 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     const char *a_ptr = (const char *)g.a + g.a_off * es, *b_ptr = (const char *)g.b + g.b_off * es;
     const char *alo_ptr = a_ptr, *blo_ptr = b_ptr;
     uint64_t lda = g.lda, ldb = g.ldb, sa = g.sa, sb = g.sb;
-    if (f32 && (passes == 3 || transpose_a)) {
+    const int sgrid = ctx->prop.multiProcessorCount * 8;
+    if (prep_a) {
         // dense re-materialised operands in the context workspace: slot 0 = A (hi, lo), slot 1 = B (hi, lo)
         const uint32_t oa_rows = transpose_a ? g.K : a_rows, oa_cols = transpose_a ? g.M : a_cols;
         const uint64_t lda_d = ((uint64_t)oa_rows + 3) & ~3ull;
@@ -947,7 +956,6 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         void *wa = nullptr;
         WGB_TRY(workspace_reserve(ctx, 0, (passes == 3 ? 2 : 1) * a_bytes, &wa));
         float *ahi = (float *)wa, *alo = passes == 3 ? (float *)((char *)wa + a_bytes) : nullptr;
-        const int sgrid = ctx->prop.multiProcessorCount * 8;
         if (transpose_a) {
             dim3 tg((g.M + 31) / 32, (g.K + 31) / 32, g.nmats);
             if (tg.y > 65535) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: K too large for the transposing prep");
@@ -960,19 +968,27 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         count_launch(ctx);
         a_ptr = (const char *)ahi; alo_ptr = (const char *)alo;
         lda = lda_d; sa = sa_d;
-        if (passes == 3) {
-            const uint64_t ldb_d = ((uint64_t)g.K + 3) & ~3ull, sb_d = ldb_d * g.N;
-            const size_t b_bytes = sb_d * g.nmats * 4;
-            void *wb = nullptr;
-            WGB_TRY(workspace_reserve(ctx, 1, 2 * b_bytes, &wb));
-            float *bhi = (float *)wb, *blo = (float *)((char *)wb + b_bytes);
-            split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)b_ptr, g.K, g.N, g.nmats, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
-            count_launch(ctx);
-            b_ptr = (const char *)bhi; blo_ptr = (const char *)blo;
-            ldb = ldb_d; sb = sb_d;
-        }
         WGB_CUDA(cudaGetLastError());
     }
+    if (prep_b) {
+        const uint64_t ldb_d = ((uint64_t)g.K + 3) & ~3ull, sb_d = ldb_d * g.N;
+        const size_t b_bytes = sb_d * g.nmats * 4;
+        void *wb = nullptr;
+        WGB_TRY(workspace_reserve(ctx, 1, (passes == 3 ? 2 : 1) * b_bytes, &wb));
+        float *bhi = (float *)wb, *blo = passes == 3 ? (float *)((char *)wb + b_bytes) : nullptr;
+        if (transpose_b) {   // memory holds [N x K] with N contiguous: write [K x N] with K contiguous
+            dim3 tg((g.N + 31) / 32, (g.K + 31) / 32, g.nmats);
+            if (tg.y > 65535) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemm: K too large for the transposing prep");
+            split_tf32_transpose_kernel<<<tg, 256, 0, p->stream>>>((const float *)b_ptr, g.N, g.K, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
+        } else {
+            split_tf32_kernel<<<sgrid, 256, 0, p->stream>>>((const float *)b_ptr, g.K, g.N, g.nmats, g.ldb, g.sb, bhi, blo, ldb_d, sb_d);
+        }
+        count_launch(ctx);
+        b_ptr = (const char *)bhi; blo_ptr = (const char *)blo;
+        ldb = ldb_d; sb = sb_d;
+        WGB_CUDA(cudaGetLastError());
+    }
+    const bool b_mn = !f32 && g.b_nmajor;   // bf16: MN-major B read in place
 
     TcMaps maps;
     CUtensorMap &ta = maps.a, &talo = maps.alo, &tb = maps.b, &tblo = maps.blo;
@@ -980,7 +996,8 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     const uint32_t a_box0 = tr ? block_k : (uint32_t)(128 / es);       // K-major: 128 B of K; MN-major: one 128 B atom of M
     const uint32_t a_box1 = tr ? 128u : block_k;
     WGB_TRY(get_tmap(ctx, a_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &ta, atom32));
-    WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tb));
+    if (b_mn) WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.N, g.K, g.nmats, ldb, sb, (uint32_t)(128 / es), block_k, &tb));   // one 128 B atom of N
+    else WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tb));
     if (passes == 3) {
         WGB_TRY(get_tmap(ctx, alo_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &talo, atom32));
         WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tblo));
@@ -1036,10 +1053,10 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     args.ep_ld = g.lde;
     args.ep_sm = g.se;
     args.debug_skip = (uint32_t)env_int("WGB_TC_DEBUG_SKIP", 0) & 3u;   // timing diagnostics only: results are garbage
-    plan_tail(args, sms / cg, bn, cg, f32 ? 1 : 0, !tr);
+    plan_tail(args, sms / cg, bn, cg, f32 ? 1 : 0, !tr, b_mn);
     maps.bt = tb;
     maps.blot = tblo;
-    if (args.nsplit > 1) {
+    if (args.nsplit > 1 && !b_mn) {   // (MN-major B: the box is one atom whatever the strip width)
         WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.bt));
         if (passes == 3) WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.blot));
         else maps.blot = maps.bt;
@@ -1058,17 +1075,21 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
 
     wgb_status st;
     if (!f32) {
-        if (g.out_dtype == WGB_F32)
-            st = tr ? launch_sel<0, false, 1, float>(p, bn, cg, maps, args) : launch_sel<0, true, 1, float>(p, bn, cg, maps, args);
-        else
-            st = tr ? launch_sel<0, false, 1, __nv_bfloat16>(p, bn, cg, maps, args)
-                    : launch_sel<0, true, 1, __nv_bfloat16>(p, bn, cg, maps, args);
+        if (g.out_dtype == WGB_F32) {
+            if (b_mn) st = tr ? launch_sel<0, false, true, 1, float>(p, bn, cg, maps, args) : launch_sel<0, true, true, 1, float>(p, bn, cg, maps, args);
+            else st = tr ? launch_sel<0, false, false, 1, float>(p, bn, cg, maps, args) : launch_sel<0, true, false, 1, float>(p, bn, cg, maps, args);
+        } else {
+            if (b_mn) st = tr ? launch_sel<0, false, true, 1, __nv_bfloat16>(p, bn, cg, maps, args)
+                              : launch_sel<0, true, true, 1, __nv_bfloat16>(p, bn, cg, maps, args);
+            else st = tr ? launch_sel<0, false, false, 1, __nv_bfloat16>(p, bn, cg, maps, args)
+                         : launch_sel<0, true, false, 1, __nv_bfloat16>(p, bn, cg, maps, args);
+        }
         *path_out = 2;
     } else if (passes == 1) {
-        st = tr ? launch_sel<1, false, 1, float>(p, bn, cg, maps, args) : launch_sel<1, true, 1, float>(p, bn, cg, maps, args);
+        st = tr ? launch_sel<1, false, false, 1, float>(p, bn, cg, maps, args) : launch_sel<1, true, false, 1, float>(p, bn, cg, maps, args);
         *path_out = 3;
     } else {
-        st = tr ? launch_sel<1, false, 3, float>(p, bn, cg, maps, args) : launch_sel<1, true, 3, float>(p, bn, cg, maps, args);
+        st = tr ? launch_sel<1, false, false, 3, float>(p, bn, cg, maps, args) : launch_sel<1, true, false, 3, float>(p, bn, cg, maps, args);
         *path_out = 4;
     }
     return st;

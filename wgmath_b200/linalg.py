@@ -52,6 +52,10 @@ class F32Mode(enum.IntEnum):           # wgb_f32_mode
     Simt = 3
 
 
+def _ord(view) -> int:
+    return 1 if view.ordering.is_row_major() else 0   # wgb_ordering
+
+
 class Gemm:
     """gemm.rs:9-127.  The four `ComputePipeline` fields of the reference become kernel-family tags: the CUDA
     kernels are compiled into the library, so `from_device` only checks that the device is usable."""
@@ -77,6 +81,12 @@ class Gemm:
             raise TypeError("Gemm: m1 and m2 must have the same element type")
         so, s1, s2 = (shapes.get(device, v.shape()).to_c() for v in (out, m1, m2))   # gemm.rs:98-100
         mode = self.f32_mode if f32_mode is None else f32_mode
+        if any(v.ordering.is_row_major() for v in (out, m1, m2)):
+            # GpuTensorView<.., RowMajor, ..> operands (tensor.rs:19-39; shape.wgsl:49-57): the ordering travels per operand
+            check(lib().wgb_gemm_ord(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), _ord(out), m1.buffer()._h,
+                                     ctypes.byref(s1), _ord(m1), m2.buffer()._h, ctypes.byref(s2), _ord(m2),
+                                     _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode), -1, None, None))
+            return
         check(lib().wgb_gemm_ex(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m1.buffer()._h, ctypes.byref(s1),
                                 m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode)))
 
@@ -87,6 +97,14 @@ class Gemm:
         out, m1, m2, e = as_view(out, 3), as_view(m1, 3), as_view(m2, 3), as_view(operand, 3)
         so, s1, s2, se = (shapes.get(device, v.shape()).to_c() for v in (out, m1, m2, e))
         mode = self.f32_mode if f32_mode is None else f32_mode
+        if any(v.ordering.is_row_major() for v in (out, m1, m2, e)):
+            if e.ordering is not out.ordering:
+                raise TypeError("Gemm.dispatch_op: operand and out must share one ordering")
+            check(lib().wgb_gemm_ord(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), _ord(out), m1.buffer()._h,
+                                     ctypes.byref(s1), _ord(m1), m2.buffer()._h, ctypes.byref(s2), _ord(m2),
+                                     _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode), int(op), e.buffer()._h,
+                                     ctypes.byref(se)))
+            return
         check(lib().wgb_gemm_op(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m1.buffer()._h, ctypes.byref(s1),
                                 m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode), int(op),
                                 e.buffer()._h, ctypes.byref(se)))
@@ -122,6 +140,10 @@ class Gemv:
     def dispatch_generic(self, device, shapes, pass_, out, m, v, variant: GemvVariant):   # gemv.rs:64-137
         out, m, v = as_view(out, 3), as_view(m, 3), as_view(v, 3)
         so, sm, sv = (shapes.get(device, x.shape()).to_c() for x in (out, m, v))
+        if m.ordering.is_row_major():
+            check(lib().wgb_gemv_ord(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m.buffer()._h, ctypes.byref(sm),
+                                     1, v.buffer()._h, ctypes.byref(sv)))
+            return
         check(lib().wgb_gemv(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m.buffer()._h, ctypes.byref(sm),
                              v.buffer()._h, ctypes.byref(sv)))
 

@@ -107,11 +107,36 @@ class TensorBuilder:
         return GpuTensor(self.shape, Buffer(device, h, arr.nbytes), dtype)
 
 
-class GpuTensorView:
-    """:416-420 — a borrowed (buffer, ViewShape) pair; `dim` is the view's tensor order."""
+class ColumnMajor:
+    """tensor.rs:17-33 — `MatrixOrdering` marker: element (i, j) at offset + i + j * stride (shape.wgsl:59-62)."""
 
-    def __init__(self, view_shape: ViewShape, buffer: Buffer, dtype: str, dim: int):
-        self.view_shape, self._buffer, self.dtype, self.dim = view_shape, buffer, dtype, dim
+    @staticmethod
+    def is_row_major() -> bool:
+        return False
+
+    @staticmethod
+    def is_column_major() -> bool:
+        return True
+
+
+class RowMajor:
+    """tensor.rs:19-39 — element (i, j) at offset + i * stride + j (shape.wgsl:49-53)."""
+
+    @staticmethod
+    def is_row_major() -> bool:
+        return True
+
+    @staticmethod
+    def is_column_major() -> bool:
+        return False
+
+
+class GpuTensorView:
+    """:416-420 — a borrowed (buffer, ViewShape) pair; `dim` is the view's tensor order, `ordering` the reference's
+    `Ordering` type parameter (ColumnMajor unless stated)."""
+
+    def __init__(self, view_shape: ViewShape, buffer: Buffer, dtype: str, dim: int, ordering=ColumnMajor):
+        self.view_shape, self._buffer, self.dtype, self.dim, self.ordering = view_shape, buffer, dtype, dim, ordering
 
     def shape(self) -> ViewShape:                                   # :424-426
         return self.view_shape
@@ -127,18 +152,22 @@ class GpuTensorView:
         return self.view_shape.size[0]
 
     def _with(self, size, stride, stride_mat, offset, dim) -> "GpuTensorView":
-        return GpuTensorView(ViewShape(tuple(size), stride, stride_mat, offset), self._buffer, self.dtype, dim)
+        return GpuTensorView(ViewShape(tuple(size), stride, stride_mat, offset), self._buffer, self.dtype, dim, self.ordering)
 
+    # The reference's sub-view constructors are generic over `Ordering` but use the column-major offset formulas for both
+    # (:484-510); here a row-major view steps by its own addressing (rows are `stride` apart, columns 1 apart).
     def rows(self, first_row: int, nrows: int) -> "GpuTensorView":
         s = self.view_shape
         if self.dim == 1:                                           # :445-462
             assert first_row + nrows <= self.len(), f"Rows slice range out of bounds: {first_row}..{first_row + nrows}"
             return self._with((nrows, 1, 1), s.stride, s.stride_mat, s.offset + first_row, 1)
-        return self._with((nrows, s.size[1], 1), s.stride, s.stride_mat, s.offset + first_row, 2)   # :498-510
+        step = s.stride if self.ordering.is_row_major() else 1
+        return self._with((nrows, s.size[1], 1), s.stride, s.stride_mat, s.offset + step * first_row, 2)   # :498-510
 
     def columns(self, first_col: int, ncols: int) -> "GpuTensorView":   # :484-496
         s = self.view_shape
-        return self._with((s.size[0], ncols, 1), s.stride, s.stride_mat, s.offset + s.stride * first_col, 2)
+        step = 1 if self.ordering.is_row_major() else s.stride
+        return self._with((s.size[0], ncols, 1), s.stride, s.stride_mat, s.offset + step * first_col, 2)
 
     def matrix(self, matrix_id: int) -> "GpuTensorView":            # :466-481 (GpuCubeView::matrix)
         s = self.view_shape
@@ -184,25 +213,29 @@ class GpuTensor:
                                     source.view_shape.offset * es, self.bytes_len()))
 
     # -- views :282-297, :514-541
-    def as_view(self) -> GpuTensorView:
-        return self.as_embedded_view(len(self._shape))
+    def as_view(self, ordering=ColumnMajor) -> GpuTensorView:
+        """`as_view::<Ordering>()`: the same buffer read with the given ordering (a RowMajor view of an r x c tensor
+        expects the r rows stored one after the other)."""
+        return self.as_embedded_view(len(self._shape), ordering)
 
-    def as_embedded_view(self, dim2: int = 3) -> GpuTensorView:
+    def as_embedded_view(self, dim2: int = 3, ordering=ColumnMajor) -> GpuTensorView:
         assert dim2 >= len(self._shape), "Can only embed into a higher-order tensor view."
         embedded = [1] * dim2
         embedded[:len(self._shape)] = self._shape
-        return self.reshape(embedded)
+        return self.reshape(embedded, ordering=ordering)
 
-    def reshape(self, shape: Sequence[int], stride: Optional[int] = None, stride_mat: Optional[int] = None) -> GpuTensorView:
+    def reshape(self, shape: Sequence[int], stride: Optional[int] = None, stride_mat: Optional[int] = None,
+                ordering=ColumnMajor) -> GpuTensorView:
         shape = [int(s) for s in shape]
         assert prod(shape) <= self.len()                            # :520
         size = [1, 1, 1]
         size[:len(shape)] = shape
         s0 = shape[0] if len(shape) > 0 else 1
         s1 = shape[1] if len(shape) > 1 else 1
-        return GpuTensorView(ViewShape(tuple(size), s0 if stride is None else stride,
+        default_stride = s0 if ordering.is_column_major() else s1   # :525-529
+        return GpuTensorView(ViewShape(tuple(size), default_stride if stride is None else stride,
                                        s0 * s1 if stride_mat is None else stride_mat, 0),
-                             self._buffer, self.dtype, len(shape))
+                             self._buffer, self.dtype, len(shape), ordering)
 
     # -- GpuMatrix :561-626
     def column(self, i: int) -> GpuTensorView:                      # :574-585
