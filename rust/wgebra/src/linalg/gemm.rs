@@ -1,7 +1,7 @@
 //! crates/wgebra/src/linalg/gemm.rs:9-127 — same struct, enum and `dispatch*` signatures; one FFI call underneath.
 use super::{B200Scalar, ComposerError};
 use wgcore::shapes::ViewShapeBuffers;
-use wgcore::tensor::GpuCubeView;
+use wgcore::tensor::{GpuCubeView, MatrixOrdering};
 use wgpu::{sys, ComputePass, ComputePipeline, Device};
 
 /// Shader for computing the product of two matrices.
@@ -38,5 +38,18 @@ impl Gemm {
         let (so, s1, s2) = (shapes.get(device, out.shape()), shapes.get(device, m1.shape()), shapes.get(device, m2.shape()));
         sys::check(unsafe { sys::wgb_gemm_ex(pass.raw(), variant as i32, out.buffer().raw(), &so, m1.buffer().raw(), &s1,
                                              m2.buffer().raw(), &s2, T::DTYPE, T::DTYPE, /* WGB_F32_AUTO: parity-gated 3xTF32 */ 0) });
+    }
+
+    /// Extension: the same product on views of any `MatrixOrdering` (tensor.rs:17-39; addressing of shape.wgsl:49-57).  The
+    /// reference's `dispatch*` only accept `ColumnMajor` views (gemm.rs:65-74) and no shader is built with
+    /// `row_major_shader_defs()`; the library computes every ordering combination in place (`wgb_gemm_ord`).
+    pub fn dispatch_ordered<'a, 'b, T: B200Scalar, O: MatrixOrdering + 'b, A: MatrixOrdering + 'b, B: MatrixOrdering + 'b>(
+        &'a self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass, out: impl Into<GpuCubeView<'b, T, O>>,
+        m1: impl Into<GpuCubeView<'b, T, A>>, m2: impl Into<GpuCubeView<'b, T, B>>, variant: GemmVariant) {
+        let (out, m1, m2) = (out.into(), m1.into(), m2.into());
+        let (so, s1, s2) = (shapes.get(device, out.shape()), shapes.get(device, m1.shape()), shapes.get(device, m2.shape()));
+        sys::check(unsafe { sys::wgb_gemm_ord(pass.raw(), variant as i32, out.buffer().raw(), &so, O::is_row_major() as i32,
+                                              m1.buffer().raw(), &s1, A::is_row_major() as i32, m2.buffer().raw(), &s2,
+                                              B::is_row_major() as i32, T::DTYPE, T::DTYPE, 0, -1, std::ptr::null(), std::ptr::null()) });
     }
 }

@@ -41,6 +41,14 @@ pub mod sys {
         pub fn wgb_gemv(pass: *mut wgb_pass, variant: c_int, out: *mut wgb_buffer, out_shape: *const wgb_view_shape,
                         m: *const wgb_buffer, m_shape: *const wgb_view_shape, v: *const wgb_buffer,
                         v_shape: *const wgb_view_shape) -> c_int;
+        /// orderings: 0 = ColumnMajor, 1 = RowMajor (wgb_ordering); op < 0: no fused element-wise step
+        pub fn wgb_gemm_ord(pass: *mut wgb_pass, variant: c_int, out: *mut wgb_buffer, out_shape: *const wgb_view_shape, out_ord: c_int,
+                            m1: *const wgb_buffer, m1_shape: *const wgb_view_shape, m1_ord: c_int, m2: *const wgb_buffer,
+                            m2_shape: *const wgb_view_shape, m2_ord: c_int, in_dtype: c_int, out_dtype: c_int, f32_mode: c_int,
+                            op: c_int, operand: *const wgb_buffer, operand_shape: *const wgb_view_shape) -> c_int;
+        pub fn wgb_gemv_ord(pass: *mut wgb_pass, variant: c_int, out: *mut wgb_buffer, out_shape: *const wgb_view_shape,
+                            m: *const wgb_buffer, m_shape: *const wgb_view_shape, m_ord: c_int, v: *const wgb_buffer,
+                            v_shape: *const wgb_view_shape) -> c_int;
         pub fn wgb_op_assign(pass: *mut wgb_pass, op: c_int, a: *mut wgb_buffer, a_shape: *const wgb_view_shape,
                              b: *const wgb_buffer, b_shape: *const wgb_view_shape) -> c_int;
         pub fn wgb_reduce(pass: *mut wgb_pass, op: c_int, value: *const wgb_buffer, value_shape: *const wgb_view_shape,

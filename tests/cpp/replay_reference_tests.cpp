@@ -15,6 +15,8 @@ int orc_gemm(int variant, float *out, const orc_shape *so, const float *m1, cons
 int orc_gemv(int variant, float *out, const orc_shape *so, const float *m, const orc_shape *sm, const float *v, const orc_shape *sv, int *ran);
 int orc_op_assign(int op, float *a, const orc_shape *sa, const float *b, const orc_shape *sb);
 int orc_reduce(int op, const float *x, const orc_shape *s, float *result);
+int orc_gemm_ord(int variant, float *out, const orc_shape *so, int out_rm, const float *m1, const orc_shape *s1, int m1_rm, const float *m2,
+                 const orc_shape *s2, int m2_rm);
 }
 
 static uint64_t splitmix64(uint64_t z) {
@@ -164,6 +166,28 @@ int main() {
             orc_op_assign(0, ref.data(), &sv, e.data(), &sv);
             const double err = rel_err(got, ref);
             std::printf("fused gemm+add via graph replay: rel err %.3e\n", err);
+            failures += !(err < 1e-5);
+        }
+        {   // RowMajor views (tensor.rs:19-39, shape.wgsl:49-57): row-major out and m2, column-major m1, 3xTF32 path
+            const uint32_t M = 192, N = 320, K = 256;
+            auto a = uniform(SEED + 1, M, K), b = uniform(SEED + 2, N, K);   // b holds the K x N matrix row by row (N contiguous)
+            auto gemm = Gemm::from_device(gpu.device());
+            auto ta = Tensors::matrix(M, K, usage).build_init<float>(gpu.device(), a);
+            auto tb = Tensors::matrix(K, N, usage).build_init<float>(gpu.device(), b);
+            auto to = Tensors::matrix(M, N, usage).build_init<float>(gpu.device(), std::vector<float>((size_t)M * N, -1.f));
+            auto enc = gpu.device().create_command_encoder();
+            {
+                auto pass = enc.compute_pass("row-major");
+                gemm.dispatch<float>(gpu.device(), shapes, pass, to.as_embedded_view<3, RowMajor>(), ta.as_embedded_view<3>(),
+                                     tb.as_embedded_view<3, RowMajor>());
+            }
+            gpu.queue().submit(enc.finish());
+            auto got = to.read(gpu.device());
+            std::vector<float> ref((size_t)M * N, -1.f);
+            orc_shape so{M, N, 1, N, M * N, 0}, s1{M, K, 1, M, M * K, 0}, s2{K, N, 1, N, K * N, 0};
+            orc_gemm_ord(0, ref.data(), &so, 1, a.data(), &s1, 0, b.data(), &s2, 1);
+            const double err = rel_err(got, ref);
+            std::printf("row-major out / m2 gemm: rel err %.3e\n", err);
             failures += !(err < 1e-5);
         }
         {   // the reference's panic on mismatched dimensions (gemm.rs:91)

@@ -156,10 +156,16 @@ struct Buffer {  // wgpu::Buffer
     size_t size() const { return bytes; }
 };
 
+// tensor.rs:17-39 — MatrixOrdering markers.  The reference carries the ordering as a type parameter of the view; here it is
+// a field of the view (set through as_view<RowMajor>() / reshape<D2, RowMajor>()), so the dispatch signatures stay as they are.
+struct ColumnMajor { static constexpr wgb_ordering value = WGB_COLUMN_MAJOR; static constexpr bool is_row_major() { return false; } };
+struct RowMajor { static constexpr wgb_ordering value = WGB_ROW_MAJOR; static constexpr bool is_row_major() { return true; } };
+
 template <typename T, int DIM> class GpuTensorView {  // tensor.rs:416-511
   public:
-    GpuTensorView(ViewShape s, const Buffer *b) : view_shape_(s), buffer_(b) {}
+    GpuTensorView(ViewShape s, const Buffer *b, wgb_ordering o = WGB_COLUMN_MAJOR) : view_shape_(s), buffer_(b), ordering_(o) {}
     ViewShape shape() const { return view_shape_; }
+    wgb_ordering ordering() const { return ordering_; }
     const Buffer *buffer() const { return buffer_; }
     uint32_t len() const { return view_shape_.size[0]; }
     // GpuVectorView::rows (:445-462) / GpuMatrixView::rows (:498-510)
@@ -168,14 +174,14 @@ template <typename T, int DIM> class GpuTensorView {  // tensor.rs:416-511
         if (DIM == 1 && first_row + nrows > len()) throw std::out_of_range("Rows slice range out of bounds");
         s.size[0] = nrows;
         if (DIM == 1) { s.size[1] = 1; s.size[2] = 1; } else { s.size[2] = 1; }
-        s.offset += first_row;
-        return GpuTensorView(s, buffer_);
+        s.offset += (ordering_ == WGB_ROW_MAJOR && DIM > 1 ? s.stride : 1u) * first_row;   // shape.wgsl:49-53 for row-major views
+        return GpuTensorView(s, buffer_, ordering_);
     }
     GpuTensorView columns(uint32_t first_col, uint32_t ncols) const {   // :484-496
         ViewShape s = view_shape_;
         s.size[1] = ncols; s.size[2] = 1;
-        s.offset += s.stride * first_col;
-        return GpuTensorView(s, buffer_);
+        s.offset += (ordering_ == WGB_ROW_MAJOR ? 1u : s.stride) * first_col;
+        return GpuTensorView(s, buffer_, ordering_);
     }
     GpuTensorView<T, 2> matrix(uint32_t matrix_id) const {            // :466-481
         if (matrix_id >= view_shape_.size[2]) throw std::out_of_range("matrix id out of range");
@@ -183,12 +189,13 @@ template <typename T, int DIM> class GpuTensorView {  // tensor.rs:416-511
         s.size[2] = 1;
         s.offset += s.stride_mat * matrix_id;
         s.stride_mat = 1;
-        return GpuTensorView<T, 2>(s, buffer_);
+        return GpuTensorView<T, 2>(s, buffer_, ordering_);
     }
-    template <int D2> operator GpuTensorView<T, D2>() const { return GpuTensorView<T, D2>(view_shape_, buffer_); }
+    template <int D2> operator GpuTensorView<T, D2>() const { return GpuTensorView<T, D2>(view_shape_, buffer_, ordering_); }
   private:
     ViewShape view_shape_;
     const Buffer *buffer_;
+    wgb_ordering ordering_;
 };
 
 template <typename T, int DIM> class GpuTensor {  // tensor.rs:192-399
@@ -200,22 +207,22 @@ template <typename T, int DIM> class GpuTensor {  // tensor.rs:192-399
     const Buffer &buffer() const { return *buffer_; }
 
     // reshape (:514-541) with default strides, offset 0
-    template <int D2> GpuTensorView<T, D2> reshape(std::array<uint32_t, D2> shape) const {
+    template <int D2, typename Ordering = ColumnMajor> GpuTensorView<T, D2> reshape(std::array<uint32_t, D2> shape) const {
         ViewShape s{{1, 1, 1}, 0, 0, 0};
         for (int i = 0; i < D2 && i < 3; ++i) s.size[i] = shape[i];
         const uint32_t s0 = D2 > 0 ? shape[0] : 1, s1 = D2 > 1 ? shape[1] : 1;
-        s.stride = s0;
+        s.stride = Ordering::is_row_major() ? s1 : s0;   // :525-529
         s.stride_mat = s0 * s1;
-        return GpuTensorView<T, D2>(s, buffer_.get());
+        return GpuTensorView<T, D2>(s, buffer_.get(), Ordering::value);
     }
-    template <int D2 = 3> GpuTensorView<T, D2> as_embedded_view() const {   // :287-297
+    template <int D2 = 3, typename Ordering = ColumnMajor> GpuTensorView<T, D2> as_embedded_view() const {   // :287-297
         static_assert(D2 >= DIM, "Can only embed into a higher-order tensor view.");
         std::array<uint32_t, D2> e;
         e.fill(1);
         for (int i = 0; i < DIM; ++i) e[i] = shape_[i];
-        return reshape<D2>(e);
+        return reshape<D2, Ordering>(e);
     }
-    GpuTensorView<T, DIM> as_view() const { return as_embedded_view<DIM>(); }
+    template <typename Ordering = ColumnMajor> GpuTensorView<T, DIM> as_view() const { return as_embedded_view<DIM, Ordering>(); }   // :282-284
     template <int D2> operator GpuTensorView<T, D2>() const { return as_embedded_view<(D2 > DIM ? D2 : DIM)>(); }   // :403-409
 
     GpuTensorView<T, 1> column(uint32_t i) const {                       // GpuMatrix::column :574-585
@@ -294,6 +301,11 @@ class Gemm {  // gemm.rs:9-127
     template <typename T> void dispatch_generic(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m1,
                                                 GpuCubeView<T> m2, GemmVariant variant) const {
         const ViewShape so = shapes.get(d, out.shape()), s1 = shapes.get(d, m1.shape()), s2 = shapes.get(d, m2.shape());   // gemm.rs:98-100
+        if (out.ordering() != WGB_COLUMN_MAJOR || m1.ordering() != WGB_COLUMN_MAJOR || m2.ordering() != WGB_COLUMN_MAJOR) {
+            check(wgb_gemm_ord(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, out.ordering(), m1.buffer()->raw, &s1, m1.ordering(),
+                               m2.buffer()->raw, &s2, m2.ordering(), DType<T>::value, DType<T>::value, f32_mode, -1, nullptr, nullptr));
+            return;
+        }
         check(wgb_gemm_ex(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, m1.buffer()->raw, &s1, m2.buffer()->raw, &s2,
                           DType<T>::value, DType<T>::value, f32_mode));
     }
@@ -334,7 +346,7 @@ class Gemv {  // gemv.rs:9-137
     template <typename T> void dispatch_generic(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m,
                                                 GpuCubeView<T> v, GemvVariant variant) const {
         const ViewShape so = shapes.get(d, out.shape()), sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape());
-        check(wgb_gemv(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, v.buffer()->raw, &sv));
+        check(wgb_gemv_ord(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, m.ordering(), v.buffer()->raw, &sv));
     }
 };
 
