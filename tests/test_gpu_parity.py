@@ -189,6 +189,25 @@ def test_gemm_simt_any_shape(gpu, shapes, M, N, K, tr):
     assert gemm_case(gpu, shapes, M, N, K, tr=tr, mode=w.F32Mode.Simt) == 1
 
 
+@pytest.mark.parametrize("tile", ["32", "64", "128"])
+@pytest.mark.parametrize("tr", [False, True])
+def test_gemm_simt_every_tile_size(gpu, shapes, tile, tr, monkeypatch):
+    """The FFMA family has three tile sizes (128 / 64 / 32) picked by a cost model; force each one over ragged, batched, padded
+    views, f32 and bf16."""
+    monkeypatch.setenv("WGB_SIMT_TILE", tile)
+    for (M, N, K, T) in [(1, 1, 1, 1), (33, 31, 9, 5), (70, 130, 65, 2), (16, 16, 16, 64)]:
+        assert gemm_case(gpu, shapes, M, N, K, T=T, tr=tr, pad=(3, 5, 1), off=(7, 9, 3), mode=w.F32Mode.Simt) == 1
+    assert gemm_case(gpu, shapes, 45, 52, 24, T=3, tr=tr, pad=(1, 3, 5), off=(1, 1, 1), dtype="bf16", out_dtype="bf16", tol=BF16_TOL) == 1
+
+
+def test_gemm_batched_small_matrices(gpu, shapes):
+    # many small matrices: the cost model must not pad them into 128 x 128 tiles; bf16 batches of <= 128 rows run one CTA per tile
+    assert gemm_case(gpu, shapes, 16, 16, 16, T=512) == 1
+    assert gemm_case(gpu, shapes, 64, 64, 64, T=96) == 1
+    assert gemm_case(gpu, shapes, 128, 128, 64, T=40, dtype="bf16", tol=1e-4) == 2
+    assert gemm_case(gpu, shapes, 128, 96, 128, T=7, mode=w.F32Mode.X3Tf32) == 4
+
+
 @pytest.mark.parametrize("tr", [False, True])
 def test_gemm_views_offsets_batches_unaligned(gpu, shapes, tr):
     # odd leading dimensions and offsets: not TMA-eligible -> must still be correct (FFMA path)

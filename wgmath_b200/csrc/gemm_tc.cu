@@ -936,7 +936,8 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         return launch_gemm_simt(p, g);
     }
     const size_t es = f32 ? 4 : 2;
-    const int cg = env_int("WGB_TC_CG", 2) == 1 ? 1 : 2;
+    // CTA pairs own 256 output rows; matrices of at most 128 rows (batches of small matrices) run one CTA per tile instead
+    const int cg = env_int("WGB_TC_CG", g.M <= 128 ? 1 : 2) == 1 ? 1 : 2;
     const uint32_t sms_total = (uint32_t)ctx->prop.multiProcessorCount;
     const int bn = passes == 3 ? 128 : pick_bn(g.M, g.N, g.nmats, cg, sms_total);
     const uint32_t block_k = 128 / (uint32_t)es;
