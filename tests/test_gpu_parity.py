@@ -206,6 +206,8 @@ def test_gemm_batched_small_matrices(gpu, shapes):
     assert gemm_case(gpu, shapes, 64, 64, 64, T=96) == 1
     assert gemm_case(gpu, shapes, 128, 128, 64, T=40, dtype="bf16", tol=1e-4) == 2
     assert gemm_case(gpu, shapes, 128, 96, 128, T=7, mode=w.F32Mode.X3Tf32) == 4
+    assert gemm_case(gpu, shapes, 128, 96, 128, T=7) == 1          # default f32 mode: small matrices stay on the FFMA tiles
+    assert gemm_case(gpu, shapes, 256, 96, 128, T=3) == 4
 
 
 @pytest.mark.parametrize("tr", [False, True])

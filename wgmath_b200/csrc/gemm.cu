@@ -16,7 +16,10 @@ wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode) {
     // Below ~64^3 per matrix a tensor-core launch (tensor-map encode + 2 helper kernels for 3xTF32) costs more
     // than the FFMA kernel's whole run time.
     const bool tiny = work < (uint64_t)96 * 96 * 96 || g.K == 0;
-    const bool want_tc = !tiny && mode != WGB_F32_SIMT && gemm_tc_eligible(g);
+    // f32 matrices of at most 128 x 128 (batches of small matrices): one 3xTF32 tile per matrix plus the two split kernels
+    // measured slower than the FFMA tiles (128 x 128 x 128 x 1024: 215 vs 165 us; profiles/r1_batched_probe.txt)
+    const bool small_f32 = g.in_dtype == WGB_F32 && mode == WGB_F32_AUTO && g.M <= 128 && g.N <= 128 && g.K <= 1024 && !g.fused;
+    const bool want_tc = !tiny && !small_f32 && mode != WGB_F32_SIMT && gemm_tc_eligible(g);
     if (want_tc) {
         int path = 0;
         wgb_status s = launch_gemm_tc(p, g, mode, &path);

@@ -259,7 +259,7 @@ int pick_simt_tile(const GemmProblem &g, int sms) {
     int best = 128;
     double best_cost = 0;
     for (int T : {128, 64, 32}) {
-        const double eff = T == 128 ? 1.0 : T == 64 ? 0.7 : 0.4;
+        const double eff = T == 128 ? 1.0 : T == 64 ? 0.95 : 0.75;   // 28 / 27 / 22 TFLOP/s on full tiles (profiles/r1_batched_probe.txt)
         const uint64_t ctas = (uint64_t)((g.M + T - 1) / T) * ((g.N + T - 1) / T) * g.nmats;
         const uint64_t per_sm = (ctas + sms - 1) / sms;
         const double warps = (double)(per_sm > 16 ? 16 : per_sm) * (T == 32 ? 2 : 8);
