@@ -259,6 +259,15 @@ wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uin
                          const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
                          wgb_f32_mode f32_mode, int n_panels);
 
+/* Diagnostics (no reference counterpart): per-cluster timeline of the most recent tcgen05 GEMM launch on this context.
+ * enable != 0 switches tracing on for later launches (a few global stores per CTA); out, if non-null, receives up to
+ * max_records records of 8 x u64 (one per CTA cluster, in cluster order) after synchronising the queue:
+ *   [0] globaltimer ns at kernel entry      [1] ns after the programmatic-dependent-launch wait
+ *   [2] ns when the first operand stage landed (first MMA issued)      [3] ns when the last MMA was issued
+ *   [4] SM clock cycles between [2] and [3]  [5] k-blocks issued by this cluster  [6] ns when the leader CTA's epilogue finished
+ *   [7] work units processed.  enable == 0 frees the trace buffer. */
+wgb_status wgb_debug_tc_trace(wgb_ctx *ctx, int enable, unsigned long long *out, size_t max_records, size_t *n_records);
+
 /* Which kernel family the last wgb_gemm* call on this pass dispatched to:
  * 0 none, 1 SIMT FFMA, 2 tcgen05 bf16, 3 tcgen05 tf32, 4 tcgen05 3xtf32. */
 wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);

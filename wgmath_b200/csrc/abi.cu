@@ -135,6 +135,7 @@ wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
     cudaStreamSynchronize(ctx->comm_stream);
     comm_destroy(ctx);
     tmap_cache_destroy(ctx);
+    if (ctx->tc_trace) cudaFree(ctx->tc_trace);
     if (ctx->scratch.partials) cudaFree(ctx->scratch.partials);
     if (ctx->scratch.counters) cudaFree(ctx->scratch.counters);
     for (auto &w : ctx->ws)
@@ -142,6 +143,30 @@ wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->comm_stream);
     delete ctx;
+    return WGB_OK;
+}
+
+wgb_status wgb_debug_tc_trace(wgb_ctx *ctx, int enable, unsigned long long *out, size_t max_records, size_t *n_records) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "wgb_debug_tc_trace: null context");
+    DeviceGuard g(ctx->device);
+    constexpr size_t kClusters = 256, kWords = 8;
+    if (enable && !ctx->tc_trace) {
+        WGB_CUDA(cudaMalloc(&ctx->tc_trace, kClusters * kWords * sizeof(unsigned long long)));
+        WGB_CUDA(cudaMemset(ctx->tc_trace, 0, kClusters * kWords * sizeof(unsigned long long)));
+    }
+    if (out && ctx->tc_trace) {
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        const size_t n = max_records < kClusters ? max_records : kClusters;
+        WGB_CUDA(cudaMemcpy(out, ctx->tc_trace, n * kWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (n_records) *n_records = n;
+    } else if (n_records) {
+        *n_records = 0;
+    }
+    if (!enable && ctx->tc_trace) {
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        WGB_CUDA(cudaFree(ctx->tc_trace));
+        ctx->tc_trace = nullptr;
+    }
     return WGB_OK;
 }
 

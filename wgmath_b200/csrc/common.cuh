@@ -76,6 +76,7 @@ struct wgb_ctx {
     wgb::CommState *comm = nullptr;
     std::mutex mu;
     void *tmap_cache = nullptr;  // gemm_tc.cu
+    unsigned long long *tc_trace = nullptr;  // diagnostics: per-cluster timeline of the last tcgen05 GEMM (wgb_debug_tc_trace)
 };
 
 struct wgb_pass {

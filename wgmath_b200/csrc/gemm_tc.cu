@@ -198,6 +198,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     return d;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
 constexpr uint32_t make_idesc(int kind, bool a_mn_major, bool b_mn_major, int m, int n) {
     const uint32_t fmt = kind == 0 ? 1u /* BF16 */ : 2u /* TF32 */;
     return (1u << 4)                      // accumulator format F32
@@ -222,6 +228,7 @@ struct TcArgs {
     const void *ep;          // operand view base (element 0 of the view), element type = TOut
     uint64_t ep_ld, ep_sm;
     uint32_t debug_skip;     // diagnostics only (WGB_TC_DEBUG_SKIP): bit 0 = do not load A tiles, bit 1 = do not load B tiles
+    unsigned long long *trace;   // diagnostics (wgb_debug_tc_trace): 8 words per cluster, null = off
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
@@ -348,6 +355,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     volatile uint32_t *split_flag = tmem_ptr_smem + 1;   // epilogue-warps-only broadcast slot
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned long long tr_entry = 0;
+    if (args.trace) tr_entry = globaltimer_ns();
     const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0u;
     const bool leader = cta_rank == 0;
     const uint32_t cluster_id = blockIdx.x / CG, num_clusters = gridDim.x / CG;
@@ -438,6 +447,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1 && lane == 0) {
         // ===================================== MMA issuer (leader CTA only) =====================
         if (leader) {
+            unsigned long long tr_wait = 0, tr_first = 0, tr_c0 = 0, tr_kb = 0, tr_units = 0;
+            if (args.trace) tr_wait = globaltimer_ns();
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
                 const WorkUnit wu = decode_unit(u, args, BN);
@@ -453,6 +464,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (; kb < chain_end; ++kb) {
                         mbar_wait(smem_u32(full_bar + stage), phase);
                         tc_fence_after();
+                        if (args.trace && tr_first == 0) {
+                            tr_first = globaltimer_ns();
+                            tr_c0 = clock64();
+                        }
                         const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
                         const uint32_t sa_hi = sbase, sa_lo = sbase + kATileBytes;
                         const uint32_t sb_hi = sbase + Cfg::SETS * kATileBytes, sb_lo = sb_hi + Cfg::B_TILE_BYTES;
@@ -486,6 +501,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     acc ^= 1;
                     if (acc == 0) acc_phase ^= 1;
                 }
+                tr_kb += wu.kb1 - wu.kb0;
+                ++tr_units;
+            }
+            if (args.trace && cluster_id < 256) {
+                unsigned long long *t = args.trace + (size_t)cluster_id * 8;
+                t[0] = tr_entry; t[1] = tr_wait; t[2] = tr_first; t[3] = globaltimer_ns();
+                t[4] = (unsigned long long)clock64() - tr_c0; t[5] = tr_kb; t[7] = tr_units;
             }
         }
     } else if (warp >= 4) {
@@ -622,6 +644,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        if (args.trace && leader && threadIdx.x == 128 && cluster_id < 256) args.trace[(size_t)cluster_id * 8 + 6] = globaltimer_ns();
         if (args.handshake) {
             // all of this CTA's peer stores are out: make them visible system-wide, count the CTA, and let the last CTA of
             // the grid publish "rank my_rank's panel is complete" to every peer
@@ -1053,6 +1076,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     args.ep = g.e ? (const char *)g.e + g.e_off * dtype_size(g.out_dtype) : nullptr;
     args.ep_ld = g.lde;
     args.ep_sm = g.se;
+    args.trace = ctx->tc_trace;
     args.debug_skip = (uint32_t)env_int("WGB_TC_DEBUG_SKIP", 0) & 3u;   // timing diagnostics only: results are garbage
     plan_tail(args, sms / cg, bn, cg, f32 ? 1 : 0, !tr, b_mn);
     maps.bt = tb;
