@@ -69,20 +69,37 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank)
         : "memory");
 }
 // Bounded wait: a broken pipeline traps (sticky CUDA error reported to the caller) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
+// The first probe carries no clock read: in steady state the barrier has usually completed already, and the waits sit in the
+// single-warp TMA / MMA issue loops whose instruction count per k-block bounds the tensor-pipe rate.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) break;
+    while (!mbar_try_wait(bar, parity))
         if (clock64() - t0 > 8000000000ll) __trap();
-    }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+}
+// One lane of a converged warp (elect.sync): the form the compiler turns into a single predicated UTCHMMA / UTMALDG instead of
+// the vote-and-retry loop it wraps around uniform-datapath instructions in code it must assume divergent.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred)::"memory");
+    return pred != 0;
 }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2) {
@@ -195,6 +212,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;    // stride-dimension byte offset
     d |= (uint64_t)1 << 46;                              // descriptor version 1 (sm_100)
     d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+// The same descriptor as two 32-bit halves: only the start-address field of the low word changes inside the main loop, so the
+// issue loop adds a 16-byte-unit offset to a precomputed low word instead of rebuilding 64-bit fields per MMA.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ constexpr uint32_t smem_desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t pack_desc(uint32_t lo, uint32_t hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
     return d;
 }
 
@@ -396,9 +427,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
-    if (warp == 0 && lane == 0) {
+    if (warp == 0) {
         // ===================================== TMA producer =====================================
+        // The whole warp runs the loop converged (barrier waits by all lanes); one elected lane issues the copies.
         uint32_t stage = 0, phase = 0;
+        const uint32_t skip = args.debug_skip;
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
             const WorkUnit wu = decode_unit(u, args, BN);
             uint32_t bt, mt, nt;
@@ -406,96 +439,106 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
             const uint32_t b_rows = wu.bn / CG;      // rows of the B tile this CTA loads
             const int n0 = (int)(nt * BN + wu.n_off + cta_rank * b_rows);
-            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (((args.debug_skip & 1u) ? 0u : (uint32_t)kATileBytes) +
-                                                             ((args.debug_skip & 2u) ? 0u : b_rows * kRowBytes)) * CG;
-            for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb) {
+            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (((skip & 1u) ? 0u : (uint32_t)kATileBytes) +
+                                                             ((skip & 2u) ? 0u : b_rows * kRowBytes)) * CG;
+            const CUtensorMap *tb_hi = wu.narrow ? &tmBt : &tmB, *tb_lo = wu.narrow ? &tmBlot : &tmBlo;
+            int k0 = (int)(wu.kb0 * BLOCK_K);
+            for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb, k0 += BLOCK_K) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
-                const uint32_t fb = smem_u32(full_bar + stage);
-                if (leader) mbar_arrive_expect_tx(fb, stage_tx);
-                uint8_t *sbase = smem + stage * Cfg::STAGE_BYTES;
-                const int k0 = (int)(kb * BLOCK_K);
+                if (elect_one()) {
+                    const uint32_t fb = smem_u32(full_bar + stage);
+                    if (leader) mbar_arrive_expect_tx(fb, stage_tx);
+                    const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
 #pragma unroll
-                for (int set = 0; set < Cfg::SETS; ++set) {
-                    const CUtensorMap *ta = set == 0 ? &tmA : &tmAlo;
-                    const CUtensorMap *tb = wu.narrow ? (set == 0 ? &tmBt : &tmBlot) : (set == 0 ? &tmB : &tmBlo);
-                    const uint32_t sa = smem_u32(sbase + set * kATileBytes);
-                    const uint32_t sb = smem_u32(sbase + Cfg::SETS * kATileBytes + set * Cfg::B_TILE_BYTES);
-                    if (args.debug_skip & 1u) {
-                    } else if (A_MN) {
+                    for (int set = 0; set < Cfg::SETS; ++set) {
+                        const CUtensorMap *ta = set == 0 ? &tmA : &tmAlo;
+                        const CUtensorMap *tb = set == 0 ? tb_hi : tb_lo;
+                        const uint32_t sa = sbase + set * kATileBytes;
+                        const uint32_t sb = sbase + Cfg::SETS * kATileBytes + set * Cfg::B_TILE_BYTES;
+                        if (skip & 1u) {
+                        } else if (A_MN) {
 #pragma unroll
-                        for (int at = 0; at < A_ATOMS; ++at) {
-                            if (CG == 2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
-                            else tma_load_3d(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                            for (int at = 0; at < A_ATOMS; ++at) {
+                                if (CG == 2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                                else tma_load_3d(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                            }
+                        } else {
+                            if (CG == 2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
+                            else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
                         }
-                    } else {
-                        if (CG == 2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
-                        else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
+                        if (skip & 2u) {
+                        } else if (B_MN) {   // 128-byte atoms along N, each BLOCK_K rows deep
+                            for (uint32_t at = 0; at * A_ATOM_ELEMS < b_rows; ++at) {
+                                if (CG == 2) tma_load_3d_2sm(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
+                                else tma_load_3d(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
+                            }
+                        } else if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
+                        else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
                     }
-                    if (args.debug_skip & 2u) {
-                    } else if (B_MN) {   // 128-byte atoms along N, each BLOCK_K rows deep
-                        for (uint32_t at = 0; at * A_ATOM_ELEMS < b_rows; ++at) {
-                            if (CG == 2) tma_load_3d_2sm(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
-                            else tma_load_3d(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
-                        }
-                    } else if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
-                    else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
                 }
-                if (args.debug_skip == 3u && leader) {}   // (both skipped: expect_tx(0) completes on the arrive alone)
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
         // ===================================== MMA issuer (leader CTA only) =====================
+        // Converged warp, one elected lane issues.  The loop body is kept to a few instructions per MMA (descriptor low words
+        // advance by constants, high words are compile-time): measured on B200, the previous single-lane form (vote-and-retry
+        // loop around every UTCHMMA, 64-bit descriptor rebuilds, a clock read per wait) spent 666 SM cycles per k-block of four
+        // 256x256x16 MMAs whose tensor-pipe floor is 512 — the issue loop, not the pipe or the operand traffic, set the pace.
         if (leader) {
             unsigned long long tr_wait = 0, tr_first = 0, tr_c0 = 0, tr_kb = 0, tr_units = 0;
-            if (args.trace) tr_wait = globaltimer_ns();
+            bool tr_pending = args.trace != nullptr;
+            if (tr_pending) tr_wait = globaltimer_ns();
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
+            constexpr bool A32 = A_MN && KIND == 1;
+            constexpr uint32_t A_HI = smem_desc_hi(A32 ? 512 : 1024, A32 ? 1 : 2), B_HI = smem_desc_hi(1024, 2);
+            constexpr uint32_t A_STEP = (A_MN ? UMMA_K * kRowBytes : 32) >> 4;   // K advance per MMA, 16-byte units
+            constexpr uint32_t B_STEP = (B_MN ? UMMA_K * kRowBytes : 32) >> 4;
+            const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), A_MN ? A_ATOM_BYTES : 16);
+            const uint32_t b_lo0 = smem_desc_lo(smem_u32(smem) + Cfg::SETS * kATileBytes, B_MN ? A_ATOM_BYTES : 16);
             for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
                 const WorkUnit wu = decode_unit(u, args, BN);
                 const uint32_t idesc = wu.narrow ? args.idesc_tail : IDESC;
                 uint32_t kb = wu.kb0;
                 while (kb < wu.kb1) {
                     // one TMEM accumulation chain: the whole K range, or kChunkKb k-blocks for 3xTF32
-                    const uint32_t chain_begin = kb;
                     const uint32_t chain_end = CHUNKED ? min(wu.kb1, kb + (uint32_t)kChunkKb) : wu.kb1;
                     mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
+                    uint32_t accum = 0;   // the first MMA of a chain overwrites the accumulator
                     for (; kb < chain_end; ++kb) {
                         mbar_wait(smem_u32(full_bar + stage), phase);
                         tc_fence_after();
-                        if (args.trace && tr_first == 0) {
+                        if (tr_pending) {
+                            tr_pending = false;
                             tr_first = globaltimer_ns();
                             tr_c0 = clock64();
                         }
-                        const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                        const uint32_t sa_hi = sbase, sa_lo = sbase + kATileBytes;
-                        const uint32_t sb_hi = sbase + Cfg::SETS * kATileBytes, sb_lo = sb_hi + Cfg::B_TILE_BYTES;
+                        if (elect_one()) {
+                            const uint32_t a_lo = a_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
+                            const uint32_t b_lo = b_lo0 + stage * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-                        for (int j = 0; j < K_STEPS; ++j) {
-                            // K advance inside the swizzled tile: 32 B (K-major) or UMMA_K rows of 128 B (MN-major)
-                            const uint32_t a_off = A_MN ? j * UMMA_K * kRowBytes : j * 32;
-                            const uint32_t b_off = B_MN ? j * UMMA_K * kRowBytes : j * 32;
-                            const uint32_t b_lbo = B_MN ? A_ATOM_BYTES : 16;
-                            const uint32_t a_lbo = A_MN ? A_ATOM_BYTES : 16, sbo = 1024;
-                            // MN-major 32-bit operands use 32-byte swizzle atoms: 4 K-rows (512 B) per atom
-                            constexpr bool A32 = A_MN && KIND == 1;
-                            const uint32_t a_sbo = A32 ? 512 : 1024, a_lt = A32 ? 1 : 2;
-                            const uint64_t da_hi = make_smem_desc(sa_hi + a_off, a_lbo, a_sbo, a_lt);
-                            const uint64_t db_hi = make_smem_desc(sb_hi + b_off, b_lbo, sbo);
-                            const uint32_t first = (kb == chain_begin && j == 0) ? 0u : 1u;
-                            if (PASSES == 3) {
-                                const uint64_t da_lo = make_smem_desc(sa_lo + a_off, a_lbo, a_sbo, a_lt);
-                                const uint64_t db_lo = make_smem_desc(sb_lo + b_off, b_lbo, sbo);
-                                umma<KIND, CG>(d_tmem, da_lo, db_hi, idesc, first);   // small terms first
-                                umma<KIND, CG>(d_tmem, da_hi, db_lo, idesc, 1u);
-                                umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, 1u);
-                            } else {
-                                umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, first);
+                            for (int j = 0; j < K_STEPS; ++j) {
+                                const uint64_t da_hi = pack_desc(a_lo + j * A_STEP, A_HI);
+                                const uint64_t db_hi = pack_desc(b_lo + j * B_STEP, B_HI);
+                                if (PASSES == 3) {
+                                    const uint64_t da_lo = pack_desc(a_lo + (kATileBytes >> 4) + j * A_STEP, A_HI);
+                                    const uint64_t db_lo = pack_desc(b_lo + (Cfg::B_TILE_BYTES >> 4) + j * B_STEP, B_HI);
+                                    umma<KIND, CG>(d_tmem, da_lo, db_hi, idesc, j == 0 ? accum : 1u);   // small terms first
+                                    umma<KIND, CG>(d_tmem, da_hi, db_lo, idesc, 1u);
+                                    umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, 1u);
+                                } else {
+                                    umma<KIND, CG>(d_tmem, da_hi, db_hi, idesc, j == 0 ? accum : 1u);
+                                }
                             }
+                            umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
+                            if (kb + 1 == chain_end) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
                         }
-                        umma_commit<CG>(smem_u32(empty_bar + stage));            // smem slot free once these MMAs retire
-                        if (kb + 1 == chain_end) umma_commit<CG>(smem_u32(tmem_full_bar + acc));   // accumulator ready
+                        __syncwarp();
+                        accum = 1u;
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                     acc ^= 1;
@@ -504,7 +547,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tr_kb += wu.kb1 - wu.kb0;
                 ++tr_units;
             }
-            if (args.trace && cluster_id < 256) {
+            if (args.trace && cluster_id < 256 && lane == 0) {
                 unsigned long long *t = args.trace + (size_t)cluster_id * 8;
                 t[0] = tr_entry; t[1] = tr_wait; t[2] = tr_first; t[3] = globaltimer_ns();
                 t[4] = (unsigned long long)clock64() - tr_c0; t[5] = tr_kb; t[7] = tr_units;
