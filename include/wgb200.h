@@ -259,6 +259,16 @@ wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uin
                          const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
                          wgb_f32_mode f32_mode, int n_panels);
 
+/* The same product, enqueued: returns once the copies and kernels are queued (the wgpu model: queue.submit now, map_async /
+ * poll later — tensor.rs:300-384).  out_host is complete after wgb_ctx_sync(), or — for work recorded later on the queue,
+ * e.g. a timestamp — after wgb_gemm_host_flush(), which makes the queue wait (on the device, without blocking the host) for
+ * every enqueued product's download.  Two device operand slots alternate, so the download of product i overlaps the upload of
+ * product i+1; the host buffers of a product must stay untouched until it has completed. */
+wgb_status wgb_gemm_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                                 const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                                 wgb_f32_mode f32_mode, int n_panels);
+wgb_status wgb_gemm_host_flush(wgb_ctx *ctx);
+
 /* Diagnostics (no reference counterpart): per-cluster timeline of the most recent tcgen05 GEMM launch on this context.
  * enable != 0 switches tracing on for later launches (a few global stores per CTA); out, if non-null, receives up to
  * max_records records of 8 x u64 (one per CTA cluster, in cluster order) after synchronising the queue:

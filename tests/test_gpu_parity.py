@@ -531,6 +531,29 @@ def test_gemm_host_buffers_pipelined(gpu, shapes, tr, dtype):
     assert rel_err(cm(out, M, N), ref) < (1e-4 if dtype == "bf16" else F32_TOL)
 
 
+def test_gemm_host_enqueue_keeps_products_apart(gpu, shapes):
+    """wgb_gemm_host_enqueue: five products in flight over two device slots, each with its own inputs and output; every
+    output must be its own product (no slot is reused before its download has left)."""
+    M, N, K = 256, 520, 264
+    dev = gpu.device()
+    gemm = w.Gemm.from_device(dev)
+    ins, outs = [], []
+    for i in range(5):
+        A, B = O.uniform(SEED_A + 16 * i, M, K), O.uniform(SEED_B + 16 * i, K, N)
+        out = np.full(M * N, -1.0, np.float32)
+        ins.append((A, B))
+        outs.append(out)
+        gemm.enqueue_host(dev, M, N, K, out, A, B, n_panels=2 + i % 2)
+    dev.poll_wait()
+    for (A, B), out in zip(ins, outs):
+        ref = cm(A, M, K).astype(np.float64) @ cm(B, K, N).astype(np.float64)
+        assert rel_err(cm(out, M, N), ref) < F32_TOL
+    # and the blocking form still works after enqueued ones
+    out = np.full(M * N, -1.0, np.float32)
+    gemm.dispatch_host(dev, M, N, K, out, ins[0][0], ins[0][1])
+    assert rel_err(cm(out, M, N), cm(ins[0][0], M, K).astype(np.float64) @ cm(ins[0][1], K, N).astype(np.float64)) < F32_TOL
+
+
 @pytest.mark.parametrize("op", [w.OpAssignVariant.Add, w.OpAssignVariant.Sub, w.OpAssignVariant.Mul, w.OpAssignVariant.Div])
 @pytest.mark.parametrize("M,N,K,mode", [(256, 384, 192, None), (100, 60, 52, w.F32Mode.Simt), (512, 512, 1024, w.F32Mode.Tf32)])
 def test_gemm_fused_op_assign_equals_the_two_dispatch_chain(gpu, shapes, op, M, N, K, mode):

@@ -89,14 +89,16 @@ for npan in (1, 2, 4, 8, 16):
         gemm.dispatch_host(dev, n, n, n, hc, ha, hbb, in_dtype="bf16", out_dtype="bf16", n_panels=npan)
     t = wall(f, 8)
     print(f"HOSTGEMM bf16 4096^3 n_panels={npan:2d}: {t:.3f} ms  {2.0 * n ** 3 / t / 1e9:.1f} TFLOP/s")
-for mode in (1, 2, 3):
-    if not hasattr(L, "wgb_gemm_host_set_mode"):
-        break
-    L.wgb_gemm_host_set_mode(mode)
+hc2 = ctypes.c_void_p()
+check(L.wgb_host_alloc(hb, ctypes.byref(hc2)))
+for npan in (1, 2, 4, 8, 16):
+    steps = 12
     def f():
-        gemm.dispatch_host(dev, n, n, n, hc, ha, hbb, in_dtype="bf16", out_dtype="bf16", n_panels=0)
-    t = wall(f, 8)
-    print(f"HOSTGEMM mode {mode}: {t:.3f} ms  {2.0 * n ** 3 / t / 1e9:.1f} TFLOP/s")
+        for i in range(steps):
+            gemm.enqueue_host(dev, n, n, n, hc if i % 2 == 0 else hc2, ha, hbb, in_dtype="bf16", out_dtype="bf16", n_panels=npan)
+        dev.poll_wait()
+    t = wall(f, 4) / steps
+    print(f"HOSTGEMM enqueue x{steps} n_panels={npan:2d}: {t:.3f} ms/product  {2.0 * n ** 3 / t / 1e9:.1f} TFLOP/s")
 
 # library GEMM (cuBLAS through torch.matmul), operands rotated through 4 sets like bench.py
 sets = [(torch.rand(n, n, device="cuda").bfloat16(), torch.rand(n, n, device="cuda").bfloat16(),

@@ -80,6 +80,8 @@ def lib() -> ctypes.CDLL:
         "wgb_gemv_ord": ([vp, ci, vp, sp, vp, sp, ci, vp, sp], ci),
         "wgb_debug_tc_trace": ([vp, ci, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)], ci),
         "wgb_gemm_host": ([vp, ci, u32, u32, u32, vp, vp, vp, ci, ci, ci, ci], ci),
+        "wgb_gemm_host_enqueue": ([vp, ci, u32, u32, u32, vp, vp, vp, ci, ci, ci, ci], ci),
+        "wgb_gemm_host_flush": ([vp], ci),
         "wgb_gemv": ([vp, ci, vp, sp, vp, sp, vp, sp], ci),
         "wgb_op_assign": ([vp, ci, vp, sp, vp, sp], ci),
         "wgb_reduce": ([vp, ci, vp, sp, vp], ci),
@@ -116,7 +118,7 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_submit", "wgb_pass_last_gemm_path", "wgb_graph_capture_begin", "wgb_graph_capture_end", "wgb_graph_launch",
             "wgb_graph_destroy", "wgb_buffer_create", "wgb_buffer_create_init", "wgb_buffer_wrap",
             "wgb_buffer_destroy", "wgb_buffer_size", "wgb_buffer_device_ptr", "wgb_buffer_write", "wgb_buffer_copy",
-            "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_op", "wgb_gemm_ord", "wgb_gemm_host", "wgb_gemv",
+            "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_op", "wgb_gemm_ord", "wgb_gemm_host", "wgb_gemm_host_enqueue", "wgb_gemm_host_flush", "wgb_gemv",
             "wgb_gemv_ord", "wgb_debug_tc_trace",
             "wgb_op_assign", "wgb_reduce", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",

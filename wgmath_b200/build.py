@@ -18,6 +18,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwgebra_b200.so")
 SOURCES = ["abi.cu", "level1.cu", "gemv.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "comm.cu"]
+# the tcgen05 kernel variants, one operand family per translation unit so they compile in parallel (gemm_tc_kernel.cuh)
+SOURCES += sorted(f for f in os.listdir(CSRC) if f.startswith("gemm_tc_inst_") and f.endswith(".cu"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # /usr/bin/g++ explicitly: this image exports CXX=/opt/gcc/bin/g++ (an incomplete toolchain).
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

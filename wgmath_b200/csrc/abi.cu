@@ -142,6 +142,13 @@ wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
         if (w.ptr) cudaFree(w.ptr);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->comm_stream);
+    if (ctx->h2d_stream) {
+        cudaStreamSynchronize(ctx->h2d_stream);
+        cudaStreamDestroy(ctx->h2d_stream);
+    }
+    for (auto e : ctx->host_gemm.done)
+        if (e) cudaEventDestroy(e);
+    for (auto e : ctx->host_gemm.evs) cudaEventDestroy(e);
     delete ctx;
     return WGB_OK;
 }
@@ -175,6 +182,8 @@ wgb_status wgb_ctx_sync(wgb_ctx *ctx) {
     DeviceGuard g(ctx->device);
     WGB_CUDA(cudaStreamSynchronize(ctx->stream));
     WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+    if (ctx->h2d_stream) WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+    ctx->host_gemm.pending[0] = ctx->host_gemm.pending[1] = false;
     return WGB_OK;
 }
 
@@ -711,9 +720,16 @@ wgb_status wgb_gemm_ord(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *ou
                        out_ord, m1_ord, m2_ord);
 }
 
-wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
-                         const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
-                         int n_panels) {
+// Host-buffer GEMM.  Three in-order streams: uploads (A, then the B panels back to back, so the host->device link never
+// waits for a kernel), the queue (panel GEMMs, each gated on its B panel), downloads (panel j of C leaves while panel j+1 of B
+// arrives).  Two device operand slots alternate between calls, so with the enqueue form the download of product i runs under
+// the upload of product i+1: the link is busy in both directions and the steady-state cost of a product is its link time.
+// Measured on B200 (PCIe gen5 x16, bf16 4096^3: 64 MiB up at 54.6 GB/s = 1.23 ms, 32 MiB down = 0.60 ms): a download that runs
+// under an upload gets about half the link rate, so one blocking call cannot hide C under B (1.58 ms whatever the panel count);
+// back-to-back enqueued products are bounded by the 1.28 ms both directions need together.
+static wgb_status gemm_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                                    const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                                    wgb_f32_mode mode, int n_panels, uint32_t default_panels) {
     if (!ctx || !out_host || !m1_host || !m2_host) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_host: null argument");
     if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_host: unknown variant");
     if (M == 0 || N == 0) return WGB_OK;
@@ -723,30 +739,48 @@ wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uin
     if ((uint64_t)M * K > 0xFFFFFFFFull || (uint64_t)K * N > 0xFFFFFFFFull || (uint64_t)M * N > 0xFFFFFFFFull)
         WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_host: operands exceed u32 element indexing");
     DeviceGuard dg(ctx->device);
+    HostGemmState &hs = ctx->host_gemm;
+    if (!ctx->h2d_stream) WGB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    for (auto &e : hs.done)
+        if (!e) WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const size_t b_off = (a_bytes + 255) & ~(size_t)255, c_off = (b_off + b_bytes + 255) & ~(size_t)255;
+    const size_t slot_bytes = (c_off + c_bytes + 255) & ~(size_t)255;
+    if (ctx->ws[3].bytes < 2 * slot_bytes) {   // growing frees the slots: drain everything that may still use them
+        WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        hs.pending[0] = hs.pending[1] = false;
+    }
     void *w = nullptr;
-    const size_t a_off = 0, b_off = (a_bytes + 255) & ~(size_t)255, c_off = (b_off + b_bytes + 255) & ~(size_t)255;
-    WGB_TRY(workspace_reserve(ctx, 3, c_off + c_bytes, &w));
-    char *dA = (char *)w + a_off, *dB = (char *)w + b_off, *dC = (char *)w + c_off;
+    WGB_TRY(workspace_reserve(ctx, 3, 2 * slot_bytes, &w));
+    const int slot = (int)(hs.calls++ & 1u);
+    // the product that used this slot two calls ago must have left it (its download is the last user)
+    if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));
+    char *dA = (char *)w + (size_t)slot * slot_bytes, *dB = dA + b_off, *dC = dA + c_off;
     // column panels: whole 256-column tiles
-    uint32_t np = n_panels > 0 ? (uint32_t)n_panels : 8u;
+    // every extra copy costs ~10-20 us of link time (measured: enqueued products 1.35 / 1.41 / 1.52 / 1.66 ms at 2 / 4 / 8 / 16
+    // panels, blocking calls 1.65 / 1.58 / 1.61 / 1.66 ms): few panels when products overlap each other, more when one call
+    // has to overlap with itself
+    uint32_t np = n_panels > 0 ? (uint32_t)n_panels : default_panels;
     uint32_t width = (N + np - 1) / np;
     width = (width + 255u) & ~255u;
     np = (N + width - 1) / width;
-    static thread_local std::vector<cudaEvent_t> evs;
-    while (evs.size() < np + 1) {
+    while (hs.evs.size() < 2 * (size_t)np) {
         cudaEvent_t e;
         WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        evs.push_back(e);
+        hs.evs.push_back(e);
     }
     wgb_pass pass;
     pass.ctx = ctx;
     pass.stream = ctx->stream;
-    if (K > 0) WGB_CUDA(cudaMemcpyAsync(dA, m1_host, a_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (K > 0) WGB_CUDA(cudaMemcpyAsync(dA, m1_host, a_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
     for (uint32_t j = 0; j < np; ++j) {
         const uint32_t n0 = j * width, nc = (N - n0) < width ? (N - n0) : width;
         if (K > 0)
             WGB_CUDA(cudaMemcpyAsync(dB + (size_t)n0 * K * es, (const char *)m2_host + (size_t)n0 * K * es, (size_t)nc * K * es,
-                                     cudaMemcpyHostToDevice, ctx->stream));
+                                     cudaMemcpyHostToDevice, ctx->h2d_stream));
+        WGB_CUDA(cudaEventRecord(hs.evs[j], ctx->h2d_stream));
+        WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.evs[j], 0));
         GemmProblem g{};
         g.tr = tr;
         g.M = M; g.N = nc; g.K = K; g.nmats = 1;
@@ -756,13 +790,41 @@ wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uin
         g.sa = (uint64_t)M * K; g.sb = (uint64_t)K * N; g.sc = (uint64_t)M * N;
         g.in_dtype = in_dtype; g.out_dtype = out_dtype;
         WGB_TRY(gemm_dispatch(&pass, g, mode));
-        WGB_CUDA(cudaEventRecord(evs[j], ctx->stream));
-        WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, evs[j], 0));      // download panel j while panel j+1 uploads
+        WGB_CUDA(cudaEventRecord(hs.evs[np + j], ctx->stream));
+        WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, hs.evs[np + j], 0));
         WGB_CUDA(cudaMemcpyAsync((char *)out_host + (size_t)n0 * M * os, dC + (size_t)n0 * M * os, (size_t)nc * M * os,
                                  cudaMemcpyDeviceToHost, ctx->comm_stream));
     }
+    WGB_CUDA(cudaEventRecord(hs.done[slot], ctx->comm_stream));
+    hs.pending[slot] = true;
+    return WGB_OK;
+}
+
+wgb_status wgb_gemm_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                                 const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                                 wgb_f32_mode mode, int n_panels) {
+    return gemm_host_enqueue(ctx, variant, M, N, K, out_host, m1_host, m2_host, in_dtype, out_dtype, mode, n_panels, 2u);
+}
+
+wgb_status wgb_gemm_host_flush(wgb_ctx *ctx) {
+    if (!ctx) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_host_flush: null context");
+    DeviceGuard dg(ctx->device);
+    HostGemmState &hs = ctx->host_gemm;
+    for (int s = 0; s < 2; ++s)
+        if (hs.pending[s]) WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.done[s], 0));
+    return WGB_OK;
+}
+
+wgb_status wgb_gemm_host(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_t M, uint32_t N, uint32_t K, void *out_host,
+                         const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
+                         int n_panels) {
+    WGB_TRY(gemm_host_enqueue(ctx, variant, M, N, K, out_host, m1_host, m2_host, in_dtype, out_dtype, mode, n_panels, 4u));
+    if (M == 0 || N == 0) return WGB_OK;
+    DeviceGuard dg(ctx->device);
     WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
     WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+    WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+    ctx->host_gemm.pending[0] = ctx->host_gemm.pending[1] = false;
     return WGB_OK;
 }
 

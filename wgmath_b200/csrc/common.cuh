@@ -63,17 +63,26 @@ struct Workspace {  // growable device workspace (3xTF32 operand splits, sharded
 
 struct CommState;  // comm.cu
 
+struct HostGemmState {   // wgb_gemm_host / wgb_gemm_host_enqueue: two alternating device operand slots
+    uint64_t calls = 0;
+    bool pending[2] = {false, false};
+    cudaEvent_t done[2] = {nullptr, nullptr};   // recorded on the download stream after a slot's last panel has left
+    std::vector<cudaEvent_t> evs;               // per-panel upload / product events
+};
+
 }  // namespace wgb
 
 struct wgb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;       // the in-order queue
-    cudaStream_t comm_stream = nullptr;  // side stream for the all-gather of C
+    cudaStream_t comm_stream = nullptr;  // side stream for the all-gather of C / the downloads of wgb_gemm_host
+    cudaStream_t h2d_stream = nullptr;   // upload stream of wgb_gemm_host (created on first use)
     cudaDeviceProp prop{};
     std::atomic<uint64_t> launches{0};
     wgb::Scratch scratch;
     wgb::Workspace ws[4];
     wgb::CommState *comm = nullptr;
+    wgb::HostGemmState host_gemm;
     std::mutex mu;
     void *tmap_cache = nullptr;  // gemm_tc.cu
     unsigned long long *tc_trace = nullptr;  // diagnostics: per-cluster timeline of the last tcgen05 GEMM (wgb_debug_tc_trace)

@@ -119,6 +119,22 @@ class Gemm:
         check(lib().wgb_gemm_host(device._h, int(variant), M, N, K, ptr(out_host), ptr(m1_host), ptr(m2_host),
                                   _DTYPE_CODE[in_dtype], _DTYPE_CODE[out_dtype], int(mode), n_panels))
 
+    def enqueue_host(self, device, M: int, N: int, K: int, out_host, m1_host, m2_host, variant=GemmVariant.Gemm,
+                     in_dtype: str = "f32", out_dtype: str = "f32", f32_mode=None, n_panels: int = 0) -> None:
+        """wgb_gemm_host_enqueue: the same product queued without waiting (wgpu's submit-now / map-later model,
+        tensor.rs:300-384).  `out_host` is complete after `device.poll_wait()`; consecutive products overlap on the host
+        link (download of product i under the upload of product i+1)."""
+        def ptr(x):
+            return x if isinstance(x, ctypes.c_void_p) else x.ctypes.data_as(ctypes.c_void_p)
+        mode = self.f32_mode if f32_mode is None else f32_mode
+        check(lib().wgb_gemm_host_enqueue(device._h, int(variant), M, N, K, ptr(out_host), ptr(m1_host), ptr(m2_host),
+                                          _DTYPE_CODE[in_dtype], _DTYPE_CODE[out_dtype], int(mode), n_panels))
+
+    @staticmethod
+    def flush_host(device) -> None:
+        """wgb_gemm_host_flush: later work on the queue (e.g. a timestamp) waits for every enqueued product's download."""
+        check(lib().wgb_gemm_host_flush(device._h))
+
 
 class Gemv:
     """gemv.rs:9-137."""
