@@ -353,8 +353,8 @@ def main_gpu(args):
                 "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
                 "peak_source": f"{peaks['source']} ({'burst' if sec < 1.0 else 'sustained'})",
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full
-                # capture profiles/r1_gemm_tc_bf16_4096_ncu.txt (86.0 MB + 20.6 MB; algorithmic A + B + C = 100.7 MB)
-                "traffic": 106.6e6 if gemm_path == 2 else None, "traffic_unit": "bytes per launch (ncu)",
+                # capture profiles/r1_gemm_tc_bf16_4096_ncu.txt (88.5 MB + 14.3 MB; algorithmic A + B + C = 100.7 MB)
+                "traffic": 102.8e6 if gemm_path == 2 else None, "traffic_unit": "bytes per launch (ncu)",
                 "algorithmic": "2*M*N*K flop per launch"}
         e2e = {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * hbytes, "d2h_bytes_per_step": hbytes,
                "steps": e2e_steps,
