@@ -20,6 +20,9 @@
  *   wgb_op_assign        <-> wgebra/src/linalg/op_assign.rs:71-94 + op_assign.wgsl:14-47
  *   wgb_reduce           <-> wgebra/src/linalg/reduce.rs:100-113  + reduce.wgsl:12-96
  *   wgb_event_*          <-> wgcore/src/timestamps.rs:9-248   GpuTimestamps
+ *   wgb_prefix_sum       <-> wgrapier/src/dynamics/prefix_sum.rs:49-99 WgPrefixSum::dispatch + prefix_sum.wgsl:35-147
+ *   wgb_radix_sort       <-> wgparry/src/utils/radix_sort/mod.rs:111-223 RadixSort::dispatch + sort_*.wgsl
+ *                            (the integer scan / sort primitives next to the linalg path)
  *
  * Extensions that have no reference counterpart (named by BASELINE.json north_star):
  *   wgb_gemm_ex            bf16 operands / bf16 output, f32 compute-mode selection
@@ -268,6 +271,24 @@ wgb_status wgb_gemm_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, uint32_
                                  const void *m1_host, const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
                                  wgb_f32_mode f32_mode, int n_panels);
 wgb_status wgb_gemm_host_flush(wgb_ctx *ctx);
+
+/* WgPrefixSum::dispatch (wgrapier/src/dynamics/prefix_sum.rs:49-99): in-place EXCLUSIVE prefix sum of a u32 vector view,
+ * data[i] <- data[0] + ... + data[i-1] (wrapping u32 adds, data[0] <- 0).  The reference's PrefixSumWorkspace (aux levels,
+ * prefix_sum.rs:119-224) has no counterpart: the look-back descriptors live in the context.  An empty view is a no-op (the
+ * reference's workspace sizing does not terminate for length 0, prefix_sum.rs:188-206). */
+wgb_status wgb_prefix_sum(wgb_pass *pass, wgb_buffer *data, const wgb_view_shape *data_shape);
+
+/* RadixSort::dispatch (wgparry/src/utils/radix_sort/mod.rs:111-223): the first n pairs of (input_keys, input_values), n =
+ * min(*n_sort, length) with n_sort a device-resident u32 (GpuScalar<u32>; element 0 of the buffer), are written to
+ * output_keys / output_values stably ordered by the low 4 * ceil(sorting_bits / 4) bits of the key.  Entries past n and the
+ * inputs are left untouched; sorting_bits == 0 runs no pass (outputs untouched), sorting_bits > 32 is WGB_ERR_INVALID (the
+ * reference's assert).  The key and value views must have equal lengths (its assert_eq!, WGB_ERR_DIM_MISMATCH), the output
+ * views at least that length, and outputs must not overlap inputs.  Ping-pong buffers (RadixSortWorkspace, mod.rs:82-109)
+ * live in the context. */
+wgb_status wgb_radix_sort(wgb_pass *pass, const wgb_buffer *input_keys, const wgb_view_shape *input_keys_shape,
+                          const wgb_buffer *input_values, const wgb_view_shape *input_values_shape, const wgb_buffer *n_sort,
+                          uint32_t sorting_bits, wgb_buffer *output_keys, const wgb_view_shape *output_keys_shape,
+                          wgb_buffer *output_values, const wgb_view_shape *output_values_shape);
 
 /* Diagnostics (no reference counterpart): per-cluster timeline of the most recent tcgen05 GEMM launch on this context.
  * enable != 0 switches tracing on for later launches (a few global stores per CTA); out, if non-null, receives up to

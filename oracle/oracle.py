@@ -42,9 +42,9 @@ def shape(nrows, ncols=1, nmats=1, stride=None, stride_mat=None, offset=0) -> Sh
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "wgsl_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or (
-            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH)):
+    srcs = [os.path.join(_HERE, f) for f in ("wgsl_oracle.c", "scan_sort_oracle.c")]
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
     return _LIB_PATH
 
@@ -68,6 +68,9 @@ def lib():
         L.orc_gemm_f64.restype = None
         L.orc_gemm_ord.argtypes = [ctypes.c_int, fp, sp, ctypes.c_int, fp, sp, ctypes.c_int, fp, sp, ctypes.c_int]
         L.orc_gemv_ord.argtypes = [ctypes.c_int, fp, sp, fp, sp, ctypes.c_int, fp, sp]
+        up = ctypes.POINTER(ctypes.c_uint32)
+        L.orc_prefix_sum.argtypes = [up, ctypes.c_uint32]
+        L.orc_radix_sort.argtypes = [up, up, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, up, up]
         L.orc_num_threads.restype = ctypes.c_int
         L.orc_set_num_threads.argtypes = [ctypes.c_int]
         L.orc_set_num_threads.restype = None
@@ -171,3 +174,20 @@ def bf16_bits(x: np.ndarray) -> np.ndarray:
 
 def bf16_from_bits(h: np.ndarray) -> np.ndarray:
     return (h.astype(np.uint32) << np.uint32(16)).view(np.float32)
+
+
+def _up(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+
+
+def prefix_sum(data: np.ndarray) -> int:
+    """WgPrefixSum::dispatch (wgrapier/src/dynamics/prefix_sum.rs:49-99): in-place exclusive u32 prefix sum."""
+    return lib().orc_prefix_sum(_up(data), data.size)
+
+
+def radix_sort(keys: np.ndarray, values: np.ndarray, n_sort: int, sorting_bits: int, out_keys: np.ndarray,
+               out_values: np.ndarray) -> int:
+    """RadixSort::dispatch (wgparry/src/utils/radix_sort/mod.rs:111-223)."""
+    assert keys.size == values.size and out_keys.size >= keys.size and out_values.size >= keys.size
+    return lib().orc_radix_sort(_up(keys), _up(values), keys.size, n_sort, sorting_bits, _up(out_keys), _up(out_values))

@@ -7,6 +7,7 @@ from ._lib import DimensionMismatch, WgbError, lib  # noqa: F401
 from .gpu import CommandEncoder, ComputePass, Device, GpuInstance, Graph, Queue  # noqa: F401
 from .linalg import (Dot, F32Mode, Gemm, GemmVariant, Gemv, GemvVariant, OpAssign, OpAssignVariant, Reduce,  # noqa: F401
                      ReduceOp, fill_uniform)
+from .primitives import PrefixSumWorkspace, RadixSort, RadixSortWorkspace, WgPrefixSum  # noqa: F401
 from .shapes import ViewShape, ViewShapeBuffers  # noqa: F401
 from .tensor import (BufferUsages, ColumnMajor, RowMajor, GpuCube, GpuCubeView, GpuMatrix, GpuMatrixView, GpuScalar, GpuTensor,  # noqa: F401
                      GpuTensorView, GpuVector, GpuVectorView, TensorBuilder, as_view)

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwgebra_b200.so")
-SOURCES = ["abi.cu", "level1.cu", "gemv.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "comm.cu"]
+SOURCES = ["abi.cu", "level1.cu", "scan_sort.cu", "gemv.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "comm.cu"]
 # the tcgen05 kernel variants, one operand family per translation unit so they compile in parallel (gemm_tc_kernel.cuh)
 SOURCES += sorted(f for f in os.listdir(CSRC) if f.startswith("gemm_tc_inst_") and f.endswith(".cu"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -521,6 +521,42 @@ wgb_status wgb_op_assign(wgb_pass *pass, wgb_op_assign_variant op, wgb_buffer *a
     return launch_op_assign(pass, (int)op, (float *)a->ptr + sa->offset, (const float *)b->ptr + sb->offset, sa->size[0]);
 }
 
+wgb_status wgb_prefix_sum(wgb_pass *pass, wgb_buffer *data, const wgb_view_shape *ds) {
+    if (!pass || !data || !ds) WGB_FAIL(WGB_ERR_INVALID, "wgb_prefix_sum: null argument");
+    if (any_zero_buffer({data}) || ds->size[0] == 0) return WGB_OK;
+    WGB_TRY(check_view(data, *ds, 4, "prefix_sum data", true));
+    DeviceGuard g(pass->ctx->device);
+    return launch_prefix_sum(pass, (uint32_t *)data->ptr + ds->offset, ds->size[0]);
+}
+
+wgb_status wgb_radix_sort(wgb_pass *pass, const wgb_buffer *ik, const wgb_view_shape *iks, const wgb_buffer *iv,
+                          const wgb_view_shape *ivs, const wgb_buffer *n_sort, uint32_t sorting_bits, wgb_buffer *ok,
+                          const wgb_view_shape *oks, wgb_buffer *ov, const wgb_view_shape *ovs) {
+    if (!pass || !ik || !iks || !iv || !ivs || !n_sort || !ok || !oks || !ov || !ovs)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_radix_sort: null argument");
+    if (iks->size[0] != ivs->size[0])   // radix_sort/mod.rs:121-125
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Input keys and values must have the same number of elements (%u vs %u)", iks->size[0],
+                 ivs->size[0]);
+    if (sorting_bits > 32) WGB_FAIL(WGB_ERR_INVALID, "Can only sort up to 32 bits");   // mod.rs:126
+    if (oks->size[0] < iks->size[0] || ovs->size[0] < iks->size[0])
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "radix sort: outputs (%u keys, %u values) shorter than the %u input pairs", oks->size[0],
+                 ovs->size[0], iks->size[0]);
+    if (any_zero_buffer({ik, iv, n_sort, ok, ov}) || iks->size[0] == 0) return WGB_OK;
+    if (n_sort->bytes < 4) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_radix_sort: n_sort buffer smaller than one u32");
+    WGB_TRY(check_view(ik, *iks, 4, "radix_sort input_keys", true));
+    WGB_TRY(check_view(iv, *ivs, 4, "radix_sort input_values", true));
+    WGB_TRY(check_view(ok, *oks, 4, "radix_sort output_keys", true));
+    WGB_TRY(check_view(ov, *ovs, 4, "radix_sort output_values", true));
+    const uint32_t *kin = (const uint32_t *)ik->ptr + iks->offset, *vin = (const uint32_t *)iv->ptr + ivs->offset;
+    uint32_t *kout = (uint32_t *)ok->ptr + oks->offset, *vout = (uint32_t *)ov->ptr + ovs->offset;
+    const size_t len = iks->size[0];
+    auto overlap = [len](const uint32_t *a, const uint32_t *b) { return a < b + len && b < a + len; };
+    if (overlap(kin, kout) || overlap(kin, vout) || overlap(vin, kout) || overlap(vin, vout) || overlap(kout, vout))
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_radix_sort: output views overlap the inputs or each other");
+    DeviceGuard g(pass->ctx->device);
+    return launch_radix_sort(pass, kin, vin, iks->size[0], (const uint32_t *)n_sort->ptr, sorting_bits, kout, vout);
+}
+
 wgb_status wgb_reduce(wgb_pass *pass, wgb_reduce_op op, const wgb_buffer *value, const wgb_view_shape *vs,
                       wgb_buffer *result) {
     if (!pass || !value || !vs || !result) WGB_FAIL(WGB_ERR_INVALID, "wgb_reduce: null argument");

@@ -80,7 +80,7 @@ struct wgb_ctx {
     cudaDeviceProp prop{};
     std::atomic<uint64_t> launches{0};
     wgb::Scratch scratch;
-    wgb::Workspace ws[4];
+    wgb::Workspace ws[6];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort
     wgb::CommState *comm = nullptr;
     wgb::HostGemmState host_gemm;
     std::mutex mu;
@@ -150,6 +150,9 @@ wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, ui
 wgb_status launch_reduce_columns(wgb_pass *p, int op, const float *m, const wgb_view_shape &ms, float *out);
 wgb_status launch_fill_uniform(wgb_pass *p, void *base, const wgb_view_shape &s, wgb_dtype dt, uint64_t seed,
                                uint32_t row0, uint32_t col0);
+wgb_status launch_prefix_sum(wgb_pass *p, uint32_t *data, uint64_t n);
+wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_t *vals_in, uint32_t len, const uint32_t *n_dev,
+                             uint32_t sorting_bits, uint32_t *keys_out, uint32_t *vals_out);
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
                        const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv);
 

@@ -2,7 +2,8 @@
 /root/reference/crates/wgcore/src/tensor.rs (line numbers below refer to that file).
 
 Element types: the reference is generic over `T: Pod`; here a tensor carries a dtype tag,
-"f32" (numpy float32) or "bf16" (numpy uint16 bit patterns)."""
+"f32" (numpy float32), "bf16" (numpy uint16 bit patterns) or "u32" (numpy uint32: the GpuVector<u32> / GpuScalar<u32>
+operands of the scan and sort primitives)."""
 from __future__ import annotations
 
 import ctypes
@@ -25,7 +26,7 @@ class BufferUsages:
     STORAGE = 1 << 7
 
 
-_DT = {"f32": (np.float32, 4), "bf16": (np.uint16, 2)}
+_DT = {"f32": (np.float32, 4), "bf16": (np.uint16, 2), "u32": (np.uint32, 4)}
 
 
 class Buffer:
@@ -95,7 +96,7 @@ class TensorBuilder:
     def build_init(self, device, data, dtype: Optional[str] = None) -> "GpuTensor":  # :175-186
         arr = np.asarray(data)
         if dtype is None:
-            dtype = "bf16" if arr.dtype == np.uint16 else "f32"
+            dtype = "bf16" if arr.dtype == np.uint16 else "u32" if arr.dtype == np.uint32 else "f32"
         arr = np.ascontiguousarray(arr.reshape(-1), dtype=_DT[dtype][0])
         n = self.len()
         assert arr.size >= n, (f"Incorrect number of elements provided for initializing Tensor."
