@@ -470,6 +470,31 @@ def run_extras(w, O, gpu, shapes, timed, peaks, timed_graph):
     rec("reduce sum n=2^26", 4 * n, lambda p, i: rsum.dispatch(dev, shapes, p, a, res))
     rec("reduce sqnorm n=2^26", 4 * n, lambda p, i: rsq.dispatch(dev, shapes, p, a, res))
     rec("dot n=2^26", 8 * n, lambda p, i: dot.dispatch(dev, shapes, p, a, b, res))
+    del a, b
+    # ---- integer primitives next to the linalg path: exclusive scan and key/value radix sort, n = 2^26
+    out["scan_sort"] = []
+    rng = np.random.default_rng(O.SEED_BASE)
+    keys_h = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    keys = w.TensorBuilder.vector(n, ST).build_init(dev, keys_h, "u32")
+    vals = w.TensorBuilder.vector(n, ST).build_init(dev, np.arange(n, dtype=np.uint32), "u32")
+    okeys, ovals = w.TensorBuilder.vector(n, ST).build(dev, "u32"), w.TensorBuilder.vector(n, ST).build(dev, "u32")
+    scan_data = w.TensorBuilder.vector(n, ST).build_init(dev, keys_h & np.uint32(0xFF), "u32")
+    del keys_h
+    nsort = w.TensorBuilder.scalar(ST).build_init(dev, np.array([n], np.uint32), "u32")
+    psum, rsort = w.WgPrefixSum.from_device(dev), w.RadixSort.from_device(dev)
+    psw, rsw = w.PrefixSumWorkspace.new(), w.RadixSortWorkspace.new(dev)
+
+    def rec2(name, nbytes, model, fn, steps=10):
+        sec, _ = timed(fn, steps, 3)
+        gbs = nbytes * steps / sec / 1e9
+        out["scan_sort"].append({"op": name, "bytes": nbytes, "traffic_model": model, "ms": sec * 1e3 / steps, "gbs": gbs,
+                                 "frac_of_hbm": gbs / hbm, "gelems_per_s": n * steps / sec / 1e9})
+    rec2("prefix_sum u32 n=2^26 (in place)", 8 * n, "read + write, single pass", lambda p, i: psum.dispatch(dev, p, psw, scan_data))
+    # onesweep traffic: 4 B/pair histogram + per 8-bit digit (8 B read + 8 B written); the reference's 4-bit passes: 20 B x 8
+    rec2("radix_sort (u32 key, u32 value) n=2^26, 32 bits", (4 + 4 * 16) * n, "4 + 4 digits x 16 B per pair",
+         lambda p, i: rsort.dispatch(dev, p, rsw, keys, vals, nsort, 32, okeys, ovals))
+    rec2("radix_sort (u32 key, u32 value) n=2^26, 16 bits", (4 + 2 * 16) * n, "4 + 2 digits x 16 B per pair",
+         lambda p, i: rsort.dispatch(dev, p, rsw, keys, vals, nsort, 16, okeys, ovals))
     return out
 
 

@@ -4,19 +4,24 @@
 //                    prefix_sum.wgsl:35-147): in-place exclusive prefix sum of a u32 vector (wrapping adds).  The reference scans
 //                    256-element blocks with a Blelloch tree, recurses over the block totals (one dispatch per level) and
 //                    adds them back level by level: 3 passes over the data (read+write, read+write of aux, read+write) and
-//                    2 * levels dispatches.  Here: ONE launch, single pass, decoupled look-back across 4096-element tiles —
-//                    8 bytes of HBM traffic per element (read + write), the algorithmic minimum.
+//                    2 * levels dispatches, one 256-thread workgroup per 256 elements with ~18 barriers each.  Here: reduce /
+//                    scan-the-partials / apply with one warp per 1024 elements and no block barriers, the apply step walking
+//                    backwards so its re-read of the tail comes from L2 (12 B per element, less what L2 still holds).
 //   wgb_radix_sort   replaces RadixSort::dispatch (crates/wgparry/src/utils/radix_sort/mod.rs:111-223 + sort_*.wgsl): stable
 //                    LSD sort of (u32 key, u32 value) pairs by the low 4 * ceil(sorting_bits / 4) key bits, pair count read
 //                    from device memory.  The reference runs ceil(bits / 4) passes of 5 dispatches (count, reduce, scan,
-//                    scan_add, scatter), each pass reading the keys twice: 20 B per pair per 4 bits.  Here: one histogram
-//                    launch for all digits, then one "onesweep" launch per 8-bit digit (tile-local ranking with warp
-//                    match, per-digit decoupled look-back for the global offsets, tile sorted in shared memory and written
-//                    out in runs): 16 B per pair per 8 bits + 4 B once.  A stable sort by the same masked key has exactly
-//                    one result, so the output is bit-identical to the reference's.
+//                    scan_add, scatter), each pass reading the keys twice: 20 B per pair per 4 bits.  Here the same
+//                    count / scan / scatter structure with 8-bit digits (half the passes: 20 B per pair per 8 bits), 8192-pair
+//                    tiles ranked with warp match instead of 2-bit split scans, tiles sorted in shared memory and written out
+//                    in runs, and the scatter walking the tiles backwards so part of its key re-read comes from L2.  (A
+//                    single-sweep variant with per-digit decoupled look-back was built first: 23 Gpair/s — the look-back chain
+//                    is the critical path at B200 bandwidth, see profiles/README.md.)  A stable sort by the same masked key
+//                    has exactly one result, so the output is bit-identical to the reference's.
 //
-// Data layout: plain u32 arrays (GpuVector<u32>), element offsets from the view shape.  Look-back descriptors and the
-// ping-pong buffers live in context workspace slots and are cleared with one memset node per call.
+// Data layout: plain u32 arrays (GpuVector<u32>), element offsets from the view shape.  Scan partials, digit counts and the
+// ping-pong buffers live in context workspace slots; nothing needs clearing between calls.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace wgb {
@@ -41,222 +46,253 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive prefix sum, single pass with decoupled look-back
+// exclusive prefix sum: reduce, scan the partials, scan with carry-in
 // ---------------------------------------------------------------------------------------------
-constexpr int kPsThreads = 256;
-constexpr int kPsRounds = 4;                                // 128-bit accesses per thread and tile
-constexpr int kPsTile = kPsThreads * 4 * kPsRounds;         // 4096 elements
-constexpr unsigned long long kPsAggregate = 1ull << 32, kPsPrefix = 2ull << 32;
+// Unit of work = one warp and 1024 consecutive elements ("warp tile": 8 rounds of one 128-bit access per lane, round r /
+// lane l covers elements [128 r + 4 l, +4)); warps never synchronise with each other, so every warp streams like a copy
+// kernel.  Three steps, all in-order launches (no spinning, safe under graph capture and profiler replay):
+//   1. scan_reduce_kernel   partial[w] = sum of warp tile w                       (4 B / element read)
+//   2. the partials are scanned by the same routine, recursively (ceil(n / 1024) values; one CTA when <= 4096)
+//   3. scan_apply_kernel    exclusive scan inside each warp tile + partial[w]     (4 B read + 4 B written)
+// Step 3 walks the tiles in DESCENDING order: the tail of the array, read last by step 1, is still in the 126 MB L2.
+// Why not a single pass: two decoupled look-back variants were built and measured first (profiles/README.md) — at B200
+// bandwidth ~100 tiles start per microsecond while a descriptor round trip through L2 costs most of one, so every tile
+// waits on hundreds of predecessors: 2.4 TB/s (one-warp window), 2.4 TB/s (whole-CTA window), 2.9 TB/s (two-level group
+// descriptors) against 4.4-5.1 TB/s for the same kernels with the look-back switched off.
+constexpr int kScanRounds = 8;                         // 128-bit accesses per lane and warp tile
+constexpr int kScanWarpTile = kScanRounds * 128;       // 1024 elements per warp tile
+constexpr int kScanThreads = 256;
+constexpr int kScanSmall = 4096;          // largest vector one CTA scans directly (1024 threads x 4 elements)
 
-// desc[tile] = (state << 32) | value; state 0 = not yet published, 1 = tile aggregate, 2 = inclusive prefix up to the tile.
-// Tiles are handed out by an atomic ticket, so a tile only ever waits for tiles whose CTAs are already running.
-__global__ void __launch_bounds__(kPsThreads) prefix_sum_kernel(uint32_t *__restrict__ data, uint64_t n,
-                                                                unsigned long long *__restrict__ desc,
-                                                                unsigned int *__restrict__ ticket) {
-    __shared__ uint32_t s_tile, s_excl;
-    __shared__ uint32_t s_wt[kPsRounds * (kPsThreads / 32)];   // warp totals in (round, warp) order = element order
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint64_t base = (uint64_t)tile * kPsTile;
-    const bool full = base + kPsTile <= n && (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
-
-    uint4 v[kPsRounds];
-    uint32_t sum[kPsRounds], incl[kPsRounds];
+__device__ __forceinline__ void scan_load_tile(const uint32_t *__restrict__ p, uint64_t base, uint64_t n, bool vec, int lane,
+                                               uint4 (&v)[kScanRounds], bool keep) {
 #pragma unroll
-    for (int r = 0; r < kPsRounds; ++r) {
-        const uint64_t i = base + (uint64_t)r * (kPsThreads * 4) + (uint64_t)t * 4;
-        if (full) {
-            v[r] = __ldcs(reinterpret_cast<const uint4 *>(data + i));
+    for (int r = 0; r < kScanRounds; ++r) {
+        const uint64_t i = base + (uint64_t)r * 128 + (uint64_t)lane * 4;
+        if (vec && i + 4 <= n) {
+            v[r] = keep ? __ldg(reinterpret_cast<const uint4 *>(p + i)) : __ldcs(reinterpret_cast<const uint4 *>(p + i));
         } else {
-            v[r].x = i + 0 < n ? data[i + 0] : 0u;
-            v[r].y = i + 1 < n ? data[i + 1] : 0u;
-            v[r].z = i + 2 < n ? data[i + 2] : 0u;
-            v[r].w = i + 3 < n ? data[i + 3] : 0u;
-        }
-        sum[r] = v[r].x + v[r].y + v[r].z + v[r].w;
-    }
-#pragma unroll
-    for (int r = 0; r < kPsRounds; ++r) {
-        uint32_t x = sum[r];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        incl[r] = x;
-        if (lane == 31) s_wt[r * (kPsThreads / 32) + warp] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // 32 warp totals -> exclusive offsets; the last lane ends up with the tile aggregate
-        const uint32_t wt = s_wt[lane];
-        uint32_t x = wt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        s_wt[lane] = x - wt;
-        const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, x, 31);
-        uint32_t exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(desc, kPsPrefix | aggregate);
-        } else {
-            if (lane == 0) st_relaxed_u64(desc + tile, kPsAggregate | aggregate);
-            int64_t pred = (int64_t)tile - 1;
-            while (true) {
-                const int64_t idx = pred - lane;
-                unsigned long long d = kPsPrefix;   // before tile 0: prefix 0
-                if (idx >= 0) {
-                    do {
-                        d = ld_relaxed_u64(desc + idx);
-                    } while ((d >> 32) == 0);
-                }
-                const unsigned has_prefix = __ballot_sync(0xFFFFFFFFu, (d >> 32) == 2);
-                const int first = has_prefix ? __ffs(has_prefix) - 1 : 31;   // nearest predecessor holding a full prefix
-                uint32_t x2 = lane <= first ? (uint32_t)d : 0u;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xFFFFFFFFu, x2, o);
-                exclusive += x2;
-                if (has_prefix) break;
-                pred -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(desc + tile, kPsPrefix | (uint32_t)(exclusive + aggregate));
-        }
-        if (lane == 0) s_excl = exclusive;
-    }
-    __syncthreads();
-    const uint32_t tile_excl = s_excl;
-#pragma unroll
-    for (int r = 0; r < kPsRounds; ++r) {
-        const uint64_t i = base + (uint64_t)r * (kPsThreads * 4) + (uint64_t)t * 4;
-        uint4 o;
-        o.x = tile_excl + s_wt[r * (kPsThreads / 32) + warp] + (incl[r] - sum[r]);
-        o.y = o.x + v[r].x;
-        o.z = o.y + v[r].y;
-        o.w = o.z + v[r].z;
-        if (full) {
-            __stcs(reinterpret_cast<uint4 *>(data + i), o);
-        } else {
-            if (i + 0 < n) data[i + 0] = o.x;
-            if (i + 1 < n) data[i + 1] = o.y;
-            if (i + 2 < n) data[i + 2] = o.z;
-            if (i + 3 < n) data[i + 3] = o.w;
+            v[r].x = i + 0 < n ? p[i + 0] : 0u;
+            v[r].y = i + 1 < n ? p[i + 1] : 0u;
+            v[r].z = i + 2 < n ? p[i + 2] : 0u;
+            v[r].w = i + 3 < n ? p[i + 3] : 0u;
         }
     }
 }
 
+__global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(const uint32_t *__restrict__ data, uint64_t n, uint64_t tiles,
+                                                                   uint32_t *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * kScanThreads + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * kScanThreads) >> 5;
+    const bool vec = (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
+    for (uint64_t w = warp; w < tiles; w += nwarps) {
+        uint4 v[kScanRounds];
+        scan_load_tile(data, w * kScanWarpTile, n, vec, lane, v, true);   // default caching: step 3 re-reads the tail from L2
+        uint32_t s = 0;
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) s += v[r].x + v[r].y + v[r].z + v[r].w;
+        s = __reduce_add_sync(0xFFFFFFFFu, s);
+        if (lane == 0) partial[w] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *__restrict__ data, uint64_t n, uint64_t tiles,
+                                                                  const uint32_t *__restrict__ partial) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = ((uint64_t)blockIdx.x * kScanThreads + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * kScanThreads) >> 5;
+    const bool vec = (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
+    for (uint64_t k = warp; k < tiles; k += nwarps) {
+        const uint64_t w = tiles - 1 - k;   // descending: most recently read tiles first
+        const uint64_t base = w * kScanWarpTile;
+        uint4 v[kScanRounds];
+        scan_load_tile(data, base, n, vec, lane, v, false);
+        const uint32_t carry = partial ? __ldg(partial + w) : 0u;
+        uint32_t sum[kScanRounds], run = carry;
+#pragma unroll
+        for (int r = 0; r < kScanRounds; ++r) {
+            sum[r] = v[r].x + v[r].y + v[r].z + v[r].w;
+            uint32_t x = sum[r];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+                if (lane >= o) x += y;
+            }
+            const uint32_t excl = run + x - sum[r];            // everything before this lane's four elements
+            run += __shfl_sync(0xFFFFFFFFu, x, 31);
+            uint4 o4;
+            o4.x = excl;
+            o4.y = o4.x + v[r].x;
+            o4.z = o4.y + v[r].y;
+            o4.w = o4.z + v[r].z;
+            const uint64_t i = base + (uint64_t)r * 128 + (uint64_t)lane * 4;
+            if (vec && i + 4 <= n) {
+                __stcs(reinterpret_cast<uint4 *>(data + i), o4);
+            } else {
+                if (i + 0 < n) data[i + 0] = o4.x;
+                if (i + 1 < n) data[i + 1] = o4.y;
+                if (i + 2 < n) data[i + 2] = o4.z;
+                if (i + 3 < n) data[i + 3] = o4.w;
+            }
+        }
+    }
+}
+
+// One CTA scans up to 4096 elements in place: 1024 threads, four consecutive elements each.
+__global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t *__restrict__ data, uint32_t n) {
+    __shared__ uint32_t s_w[32];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    uint32_t v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (uint32_t)t * 4 + q < n ? data[t * 4 + q] : 0u;
+    const uint32_t s = v[0] + v[1] + v[2] + v[3];
+    uint32_t x = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_w[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t wv = s_w[lane];
+        uint32_t y2 = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, y2, o);
+            if (lane >= o) y2 += y;
+        }
+        s_w[lane] = y2 - wv;
+    }
+    __syncthreads();
+    uint32_t run = s_w[warp] + x - s;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if ((uint32_t)t * 4 + q < n) data[t * 4 + q] = run;
+        run += v[q];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// radix sort: global digit histograms + one onesweep pass per 8-bit digit
+// radix sort: per 8-bit digit  tile histograms -> exclusive scan of the counts -> stable scatter
 // ---------------------------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;   // 4096 pairs per tile
+constexpr int kRsItems = 32;
+constexpr int kRsTile = kRsThreads * kRsItems;   // 8192 pairs per tile
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsBins = 256;
-constexpr int kRsMaxPasses = 4;
-constexpr unsigned int kRsFlagAggregate = 1u << 30, kRsFlagPrefix = 2u << 30, kRsValueMask = (1u << 30) - 1u;
-
-struct RsPasses {
-    uint32_t num, shift[kRsMaxPasses], mask[kRsMaxPasses];
-};
 
 __device__ __forceinline__ uint32_t rs_count(const uint32_t *n_ptr, uint32_t len) {
     const uint32_t n = *n_ptr;
     return n < len ? n : len;
 }
 
-// hist[p][d] += number of keys whose digit p equals d (all passes in one sweep over the keys: 4 B per key)
-__global__ void __launch_bounds__(256) radix_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr,
-                                                         uint32_t len, RsPasses ps, unsigned int *__restrict__ hist) {
-    __shared__ unsigned int sh[kRsMaxPasses * kRsBins];
-    for (int i = threadIdx.x; i < kRsMaxPasses * kRsBins; i += blockDim.x) sh[i] = 0u;
+// counts[d * tiles + tile] = number of keys of the tile whose digit is d (digit-major, like the reference's
+// counts[bin * num_wgs + wg], sort_count.wgsl).  Every tile of the launch writes its 256 counts (zeros past *n_sort), so
+// the array needs no clearing.  4 B per key.
+__global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ n_ptr,
+                                                                 uint32_t len, uint32_t shift, uint32_t mask, uint32_t tiles,
+                                                                 uint32_t *__restrict__ counts) {
+    __shared__ unsigned int s_hist[kRsWarps][kRsBins];   // one private histogram per warp: no cross-warp contention
+    const int t = threadIdx.x, warp = t >> 5;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) s_hist[w][t] = 0u;
     __syncthreads();
+    const uint32_t tile = blockIdx.x;
     const uint32_t n = rs_count(n_ptr, len);
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const bool vec = (reinterpret_cast<uintptr_t>(keys) & 15u) == 0;
-    if (vec) {
-        const uint64_t n4 = n / 4;
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-            const uint4 k = __ldcs(reinterpret_cast<const uint4 *>(keys) + i);
-            for (uint32_t p = 0; p < ps.num; ++p) {
-                atomicAdd(&sh[p * kRsBins + ((k.x >> ps.shift[p]) & ps.mask[p])], 1u);
-                atomicAdd(&sh[p * kRsBins + ((k.y >> ps.shift[p]) & ps.mask[p])], 1u);
-                atomicAdd(&sh[p * kRsBins + ((k.z >> ps.shift[p]) & ps.mask[p])], 1u);
-                atomicAdd(&sh[p * kRsBins + ((k.w >> ps.shift[p]) & ps.mask[p])], 1u);
+    const uint32_t tile_base = tile * (uint32_t)kRsTile;
+    if (tile_base < n) {
+        const uint32_t tile_n = min((uint32_t)kRsTile, n - tile_base);
+        const uint32_t *kp = keys + tile_base;
+        unsigned int *h = s_hist[warp];
+        if (tile_n == (uint32_t)kRsTile && (reinterpret_cast<uintptr_t>(kp) & 15u) == 0) {
+            uint4 k[kRsItems / 4];
+#pragma unroll
+            for (int i = 0; i < kRsItems / 4; ++i) k[i] = __ldg(reinterpret_cast<const uint4 *>(kp) + i * kRsThreads + t);
+#pragma unroll
+            for (int i = 0; i < kRsItems / 4; ++i) {
+                atomicAdd(h + ((k[i].x >> shift) & mask), 1u);
+                atomicAdd(h + ((k[i].y >> shift) & mask), 1u);
+                atomicAdd(h + ((k[i].z >> shift) & mask), 1u);
+                atomicAdd(h + ((k[i].w >> shift) & mask), 1u);
             }
-        }
-        for (uint64_t i = n4 * 4 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            const uint32_t k = keys[i];
-            for (uint32_t p = 0; p < ps.num; ++p) atomicAdd(&sh[p * kRsBins + ((k >> ps.shift[p]) & ps.mask[p])], 1u);
-        }
-    } else {
-        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-            const uint32_t k = keys[i];
-            for (uint32_t p = 0; p < ps.num; ++p) atomicAdd(&sh[p * kRsBins + ((k >> ps.shift[p]) & ps.mask[p])], 1u);
+        } else {
+            for (uint32_t e = t; e < tile_n; e += kRsThreads) atomicAdd(h + ((kp[e] >> shift) & mask), 1u);
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < (int)ps.num * kRsBins; i += blockDim.x)
-        if (sh[i]) atomicAdd(hist + i, sh[i]);
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) c += s_hist[w][t];
+    counts[(size_t)t * tiles + tile] = c;
 }
 
-// One 8-bit (or narrower, last) digit.  Tile = 4096 consecutive pairs; warp w owns the 512 consecutive pairs
-// [w * 512, (w + 1) * 512), item i of lane l is pair w * 512 + i * 32 + l, so (item, lane) order is input order and every
-// global access of a warp is one contiguous 128 bytes.
-//   1. rank inside the warp: lanes holding the same digit find each other with match.any; the warp's private histogram
+// Stable scatter of one tile.  Tile = 8192 consecutive pairs; warp w owns the 1024 consecutive pairs [w * 1024, (w + 1) *
+// 1024), item i of lane l is pair w * 1024 + i * 32 + l, so (item, lane) order is input order and every global access of a
+// warp is one contiguous 128 bytes.
+//   1. rank inside the warp: lanes holding the same digit find each other with one ballot per digit bit; the warp's private histogram
 //      gives the count of earlier equal digits in the warp;
-//   2. thread d turns the 8 warp histograms of digit d into warp offsets and the tile count, publishes the count, and
-//      walks back over the preceding tiles' descriptors until it meets an inclusive prefix (decoupled look-back);
-//   3. an exclusive scan of the tile counts gives each digit's start inside the tile; pairs are placed in shared memory
-//      in tile-sorted order and written out by consecutive threads: equal digits form contiguous global runs.
-__global__ void __launch_bounds__(kRsThreads) radix_onesweep_kernel(const uint32_t *__restrict__ keys_in,
-                                                                    const uint32_t *__restrict__ vals_in,
-                                                                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                                                                    const uint32_t *__restrict__ n_ptr, uint32_t len, uint32_t shift,
-                                                                    uint32_t mask, const unsigned int *__restrict__ hist,
-                                                                    unsigned int *__restrict__ desc, unsigned int *__restrict__ ticket) {
+//   2. thread d turns the 8 warp histograms of digit d into warp offsets and the tile count; an exclusive scan of the tile
+//      counts gives each digit's start inside the tile; offsets[d * tiles + tile] (the scanned counts) is where the tile's
+//      first pair of digit d goes globally;
+//   3. pairs are placed in shared memory in tile-sorted order and written out by consecutive threads: equal digits form
+//      contiguous global runs.
+// Tiles are independent (all offsets are known), so the grid walks them in DESCENDING order: the keys the count kernel
+// read last are still in L2.  16 B per pair.
+__global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
+                                                                      const uint32_t *__restrict__ vals_in,
+                                                                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                                      const uint32_t *__restrict__ n_ptr, uint32_t len, uint32_t shift,
+                                                                      uint32_t mask, uint32_t tiles,
+                                                                      const uint32_t *__restrict__ offsets) {
     __shared__ uint32_t s_warp_hist[kRsWarps][kRsBins];
     __shared__ uint32_t s_sorted[kRsTile];
     __shared__ uint32_t s_tile_start[kRsBins];   // first slot of digit d inside the tile-sorted order
     __shared__ uint32_t s_gbase[kRsBins];        // global position of the tile's first pair of digit d, minus s_tile_start[d]
     __shared__ uint32_t s_scan[kRsWarps];
-    __shared__ uint32_t s_tile;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(ticket, 1u);
+    const uint32_t tile = gridDim.x - 1 - blockIdx.x;
+    const uint32_t n = rs_count(n_ptr, len);
+    const uint32_t tile_base = tile * (uint32_t)kRsTile;
+    if (tile_base >= n) return;
+    const uint32_t goff = __ldg(offsets + (size_t)t * tiles + tile);
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) s_warp_hist[w][t] = 0u;
     __syncthreads();
-    const uint32_t tile = s_tile;
-    const uint32_t n = rs_count(n_ptr, len);
-    const uint32_t num_tiles = (n + kRsTile - 1) / kRsTile;
-    if (tile >= num_tiles) return;
-    const uint32_t tile_base = tile * (uint32_t)kRsTile;
     const uint32_t tile_n = min((uint32_t)kRsTile, n - tile_base);
+    const bool full = tile_n == (uint32_t)kRsTile;
 
     uint32_t key[kRsItems], val[kRsItems];
-    uint16_t slot[kRsItems];
+    uint32_t slot2[kRsItems / 2];   // two 16-bit slots per register
     const uint32_t wbase = (uint32_t)warp * (kRsItems * 32) + lane;
+    if (full) {
 #pragma unroll
-    for (int i = 0; i < kRsItems; ++i) {
-        const uint32_t e = wbase + i * 32;
-        key[i] = e < tile_n ? __ldcs(keys_in + tile_base + e) : 0xFFFFFFFFu;
-    }
+        for (int i = 0; i < kRsItems; ++i) key[i] = __ldcs(keys_in + tile_base + wbase + i * 32);
 #pragma unroll
-    for (int i = 0; i < kRsItems; ++i) {
-        const uint32_t e = wbase + i * 32;
-        val[i] = e < tile_n ? __ldcs(vals_in + tile_base + e) : 0u;
+        for (int i = 0; i < kRsItems; ++i) val[i] = __ldcs(vals_in + tile_base + wbase + i * 32);
+    } else {
+#pragma unroll
+        for (int i = 0; i < kRsItems; ++i) {
+            const uint32_t e = wbase + i * 32;
+            key[i] = e < tile_n ? keys_in[tile_base + e] : 0xFFFFFFFFu;
+            val[i] = e < tile_n ? vals_in[tile_base + e] : 0u;
+        }
     }
     // 1. ranks inside the warp
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *wh = s_warp_hist[warp];
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i) {
-        const bool valid = wbase + i * 32 < tile_n;
+        const bool valid = full || wbase + i * 32 < tile_n;
         const uint32_t d = (key[i] >> shift) & mask;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0x100u);
+        // lanes holding the same digit: eight ballots, one per digit bit (match.any computes the same set but measured
+        // ~25 us per 8192-pair tile on B200: its issue rate, not memory, bounded the whole sort)
+        uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
+        if (!valid) peers = 1u << lane;
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
         if (lane == leader && valid) {
@@ -264,11 +300,13 @@ __global__ void __launch_bounds__(kRsThreads) radix_onesweep_kernel(const uint32
             wh[d] = pre + __popc(peers);
         }
         pre = __shfl_sync(0xFFFFFFFFu, pre, leader);
-        slot[i] = (uint16_t)(pre + __popc(peers & lt_mask));
+        const uint32_t r = pre + __popc(peers & lt_mask);
+        if (i & 1) slot2[i / 2] |= r << 16;
+        else slot2[i / 2] = r;
         __syncwarp();
     }
     __syncthreads();
-    // 2. digit t: warp offsets, tile count, look-back
+    // 2. digit t: warp offsets, tile count, start inside the tile
     uint32_t count = 0;
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w) {
@@ -276,91 +314,97 @@ __global__ void __launch_bounds__(kRsThreads) radix_onesweep_kernel(const uint32
         s_warp_hist[w][t] = count;
         count += c;
     }
-    unsigned int *my_desc = desc + (size_t)tile * kRsBins + t;
-    uint32_t exclusive = 0;
-    if (tile == 0) {
-        st_relaxed_u32(my_desc, kRsFlagPrefix | count);
-    } else {
-        st_relaxed_u32(my_desc, kRsFlagAggregate | count);
-        const unsigned int *pd = my_desc - kRsBins;
-        while (true) {
-            unsigned int dsc;
-            do {
-                dsc = ld_relaxed_u32(pd);
-            } while ((dsc >> 30) == 0);
-            exclusive += dsc & kRsValueMask;
-            if ((dsc >> 30) == 2) break;
-            pd -= kRsBins;
-        }
-        st_relaxed_u32(my_desc, kRsFlagPrefix | (exclusive + count));
-    }
-    // global start of digit t = number of keys with a smaller digit (exclusive scan of the histogram) ...
-    const uint32_t h = hist[t];
-    uint32_t hx = h, cx = count;
+    uint32_t cx = count;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t a = __shfl_up_sync(0xFFFFFFFFu, hx, o), b = __shfl_up_sync(0xFFFFFFFFu, cx, o);
-        if (lane >= o) { hx += a; cx += b; }
+        const uint32_t b = __shfl_up_sync(0xFFFFFFFFu, cx, o);
+        if (lane >= o) cx += b;
     }
-    __shared__ uint32_t s_hscan[kRsWarps];
-    if (lane == 31) { s_hscan[warp] = hx; s_scan[warp] = cx; }
+    if (lane == 31) s_scan[warp] = cx;
     __syncthreads();
-    uint32_t hoff = 0, coff = 0;
+    uint32_t coff = 0;
 #pragma unroll
     for (int w = 0; w < kRsWarps; ++w)
-        if (w < warp) { hoff += s_hscan[w]; coff += s_scan[w]; }
-    const uint32_t digit_start = hoff + hx - h;    // ... over all tiles
-    const uint32_t tile_start = coff + cx - count; // ... and inside this tile
+        if (w < warp) coff += s_scan[w];
+    const uint32_t tile_start = coff + cx - count;
     s_tile_start[t] = tile_start;
-    s_gbase[t] = digit_start + exclusive - tile_start;
+    s_gbase[t] = goff - tile_start;
     __syncthreads();
     // 3. place in tile-sorted order, write out in runs
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i) {
-        if (wbase + i * 32 < tile_n) {
+        if (full || wbase + i * 32 < tile_n) {
             const uint32_t d = (key[i] >> shift) & mask;
-            slot[i] = (uint16_t)(s_tile_start[d] + wh[d] + slot[i]);
-            s_sorted[slot[i]] = key[i];
+            const uint32_t sl = s_tile_start[d] + wh[d] + ((slot2[i / 2] >> ((i & 1) * 16)) & 0xFFFFu);
+            slot2[i / 2] = (i & 1) ? ((slot2[i / 2] & 0xFFFFu) | (sl << 16)) : ((slot2[i / 2] & 0xFFFF0000u) | sl);
+            s_sorted[sl] = key[i];
         }
     }
     __syncthreads();
-    uint32_t gpos[kRsItems];
+    uint32_t dig4[kRsItems / 4];   // digit of the key at sorted position j * 256 + t, four per register
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = (uint32_t)j * kRsThreads + t;
-        if (e < tile_n) {
+        if ((j & 3) == 0) dig4[j / 4] = 0;
+        if (full || e < tile_n) {
             const uint32_t k = s_sorted[e];
-            gpos[j] = s_gbase[(k >> shift) & mask] + e;
-            keys_out[gpos[j]] = k;
+            const uint32_t d = (k >> shift) & mask;
+            dig4[j / 4] |= d << ((j & 3) * 8);
+            keys_out[s_gbase[d] + e] = k;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i)
-        if (wbase + i * 32 < tile_n) s_sorted[slot[i]] = val[i];
+        if (full || wbase + i * 32 < tile_n) s_sorted[(slot2[i / 2] >> ((i & 1) * 16)) & 0xFFFFu] = val[i];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = (uint32_t)j * kRsThreads + t;
-        if (e < tile_n) vals_out[gpos[j]] = s_sorted[e];
+        if (full || e < tile_n) vals_out[s_gbase[(dig4[j / 4] >> ((j & 3) * 8)) & 0xFFu] + e] = s_sorted[e];
     }
 }
 
 }  // namespace
 
-wgb_status launch_prefix_sum(wgb_pass *p, uint32_t *data, uint64_t n) {
+// Exclusive scan of data[0, n) in place; `ws` provides room for the partials of every level (scan_workspace_elems(n)).
+static size_t scan_workspace_elems(uint64_t n) {
+    size_t total = 0;
+    while (n > (uint64_t)kScanSmall) {
+        n = (n + kScanWarpTile - 1) / kScanWarpTile;
+        total += (n + 3) & ~(size_t)3;   // keep every level 16-byte aligned
+    }
+    return total;
+}
+
+static wgb_status scan_in_place(wgb_pass *p, uint32_t *data, uint64_t n, uint32_t *ws) {
     if (n == 0) return WGB_OK;
     wgb_ctx *ctx = p->ctx;
-    const uint64_t tiles = (n + kPsTile - 1) / kPsTile;
-    void *w = nullptr;
-    const size_t bytes = 16 + tiles * sizeof(unsigned long long);
-    WGB_TRY(workspace_reserve(ctx, 4, bytes, &w));
-    WGB_CUDA(cudaMemsetAsync(w, 0, bytes, p->stream));
-    prefix_sum_kernel<<<(unsigned)tiles, kPsThreads, 0, p->stream>>>(data, n, reinterpret_cast<unsigned long long *>((char *)w + 16),
-                                                                     reinterpret_cast<unsigned int *>(w));
+    if (n <= (uint64_t)kScanSmall) {
+        scan_small_kernel<<<1, 1024, 0, p->stream>>>(data, (uint32_t)n);
+        WGB_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        return WGB_OK;
+    }
+    const uint64_t tiles = (n + kScanWarpTile - 1) / kScanWarpTile;
+    const uint64_t ctas_needed = (tiles + kScanThreads / 32 - 1) / (kScanThreads / 32);
+    uint64_t grid = (uint64_t)ctx->prop.multiProcessorCount * 8;   // one resident wave: 8 CTAs of 256 threads per SM
+    if (grid > ctas_needed) grid = ctas_needed;
+    scan_reduce_kernel<<<(unsigned)grid, kScanThreads, 0, p->stream>>>(data, n, tiles, ws);
+    WGB_CUDA(cudaGetLastError());
+    count_launch(ctx);
+    WGB_TRY(scan_in_place(p, ws, tiles, ws + ((tiles + 3) & ~(uint64_t)3)));
+    scan_apply_kernel<<<(unsigned)grid, kScanThreads, 0, p->stream>>>(data, n, tiles, ws);
     WGB_CUDA(cudaGetLastError());
     count_launch(ctx);
     return WGB_OK;
+}
+
+wgb_status launch_prefix_sum(wgb_pass *p, uint32_t *data, uint64_t n) {
+    if (n == 0) return WGB_OK;
+    void *w = nullptr;
+    WGB_TRY(workspace_reserve(p->ctx, 4, scan_workspace_elems(n) * 4 + 16, &w));
+    return scan_in_place(p, data, n, reinterpret_cast<uint32_t *>(w));
 }
 
 wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_t *vals_in, uint32_t len, const uint32_t *n_dev,
@@ -368,43 +412,31 @@ wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_
     if (sorting_bits > 32) WGB_FAIL(WGB_ERR_INVALID, "Can only sort up to 32 bits");   // radix_sort/mod.rs:126
     const uint32_t total_bits = 4 * ((sorting_bits + 3) / 4);   // the reference sorts whole 4-bit digits (mod.rs:156)
     if (total_bits == 0 || len == 0) return WGB_OK;             // zero passes: outputs untouched, like the reference
-    if (len > kRsValueMask) WGB_FAIL(WGB_ERR_UNSUPPORTED, "radix sort: more than 2^30 - 1 pairs");
     wgb_ctx *ctx = p->ctx;
-    RsPasses ps{};
-    ps.num = (total_bits + 7) / 8;
-    for (uint32_t i = 0; i < ps.num; ++i) {
-        ps.shift[i] = 8 * i;
-        const uint32_t nb = total_bits - 8 * i < 8 ? total_bits - 8 * i : 8;
-        ps.mask[i] = (1u << nb) - 1u;
-    }
+    const uint32_t passes = (total_bits + 7) / 8;
     const uint32_t tiles = (len + kRsTile - 1) / kRsTile;
-    // workspace: [hist 4 x 256][tickets 4 (+pad)][descriptors passes x tiles x 256][pong keys][pong values]
-    const size_t hist_bytes = kRsMaxPasses * kRsBins * 4, ticket_bytes = 64;
-    const size_t desc_bytes = (size_t)ps.num * tiles * kRsBins * 4;
-    const size_t clear_bytes = hist_bytes + ticket_bytes + desc_bytes;
-    const size_t pong_off = (clear_bytes + 255) & ~(size_t)255;
-    const size_t pong_bytes = ps.num > 1 ? (((size_t)len * 4 + 255) & ~(size_t)255) : 0;
+    // workspace: [counts 256 x tiles][scan partials][pong keys][pong values]
+    const size_t n_counts = (size_t)kRsBins * tiles;
+    const size_t counts_bytes = (n_counts * 4 + 255) & ~(size_t)255;
+    const size_t scan_bytes = (scan_workspace_elems(n_counts) * 4 + 16 + 255) & ~(size_t)255;
+    const size_t pong_bytes = passes > 1 ? (((size_t)len * 4 + 255) & ~(size_t)255) : 0;
     void *w = nullptr;
-    WGB_TRY(workspace_reserve(ctx, 5, pong_off + 2 * pong_bytes, &w));
-    unsigned int *hist = reinterpret_cast<unsigned int *>(w);
-    unsigned int *tickets = reinterpret_cast<unsigned int *>((char *)w + hist_bytes);
-    unsigned int *desc = reinterpret_cast<unsigned int *>((char *)w + hist_bytes + ticket_bytes);
-    uint32_t *pong_k = reinterpret_cast<uint32_t *>((char *)w + pong_off);
-    uint32_t *pong_v = reinterpret_cast<uint32_t *>((char *)w + pong_off + pong_bytes);
-    WGB_CUDA(cudaMemsetAsync(w, 0, clear_bytes, p->stream));
-    int hgrid = ctx->prop.multiProcessorCount * 8;
-    const uint32_t hneed = (len + 1023) / 1024;
-    if ((uint32_t)hgrid > hneed) hgrid = (int)hneed;
-    radix_hist_kernel<<<hgrid, 256, 0, p->stream>>>(keys_in, n_dev, len, ps, hist);
-    WGB_CUDA(cudaGetLastError());
-    count_launch(ctx);
+    WGB_TRY(workspace_reserve(ctx, 5, counts_bytes + scan_bytes + 2 * pong_bytes, &w));
+    uint32_t *counts = reinterpret_cast<uint32_t *>(w);
+    uint32_t *scan_ws = reinterpret_cast<uint32_t *>((char *)w + counts_bytes);
+    uint32_t *pong_k = reinterpret_cast<uint32_t *>((char *)w + counts_bytes + scan_bytes);
+    uint32_t *pong_v = reinterpret_cast<uint32_t *>((char *)w + counts_bytes + scan_bytes + pong_bytes);
     // the last pass lands in the caller's output; passes alternate between it and the workspace pair (mod.rs:163-221)
     const uint32_t *cur_k = keys_in, *cur_v = vals_in;
-    for (uint32_t i = 0; i < ps.num; ++i) {
-        const bool to_out = (ps.num - 1 - i) % 2 == 0;
+    for (uint32_t i = 0; i < passes; ++i) {
+        const uint32_t shift = 8 * i, nb = total_bits - shift < 8 ? total_bits - shift : 8, mask = (1u << nb) - 1u;
+        const bool to_out = (passes - 1 - i) % 2 == 0;
         uint32_t *dk = to_out ? keys_out : pong_k, *dv = to_out ? vals_out : pong_v;
-        radix_onesweep_kernel<<<tiles, kRsThreads, 0, p->stream>>>(cur_k, cur_v, dk, dv, n_dev, len, ps.shift[i], ps.mask[i],
-                                                                   hist + i * kRsBins, desc + (size_t)i * tiles * kRsBins, tickets + i);
+        radix_count_kernel<<<tiles, kRsThreads, 0, p->stream>>>(cur_k, n_dev, len, shift, mask, tiles, counts);
+        WGB_CUDA(cudaGetLastError());
+        count_launch(ctx);
+        WGB_TRY(scan_in_place(p, counts, n_counts, scan_ws));
+        radix_scatter_kernel<<<tiles, kRsThreads, 0, p->stream>>>(cur_k, cur_v, dk, dv, n_dev, len, shift, mask, tiles, counts);
         WGB_CUDA(cudaGetLastError());
         count_launch(ctx);
         cur_k = dk;
