@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t *__restrict__
 // radix sort: per 8-bit digit  tile histograms -> exclusive scan of the counts -> stable scatter
 // ---------------------------------------------------------------------------------------------
 constexpr int kRsThreads = 256;
-constexpr int kRsItems = 32;
-constexpr int kRsTile = kRsThreads * kRsItems;   // 8192 pairs per tile
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kRsThreads * kRsItems;   // 4096 pairs per tile
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsBins = 256;
 
@@ -226,11 +226,11 @@ __global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const uint32_t 
     counts[(size_t)t * tiles + tile] = c;
 }
 
-// Stable scatter of one tile.  Tile = 8192 consecutive pairs; warp w owns the 1024 consecutive pairs [w * 1024, (w + 1) *
-// 1024), item i of lane l is pair w * 1024 + i * 32 + l, so (item, lane) order is input order and every global access of a
-// warp is one contiguous 128 bytes.
-//   1. rank inside the warp: lanes holding the same digit find each other with one ballot per digit bit; the warp's private histogram
-//      gives the count of earlier equal digits in the warp;
+// Stable scatter of one tile.  Tile = 4096 consecutive pairs; warp w owns the 512 consecutive pairs [w * 512, (w + 1) * 512),
+// item i of lane l is pair w * 512 + i * 32 + l, so (item, lane) order is input order and every global access of a warp is
+// one contiguous 128 bytes.
+//   1. rank inside the warp: lanes holding the same digit find each other with one ballot per digit bit; the warp's private
+//      histogram gives the count of earlier equal digits in the warp;
 //   2. thread d turns the 8 warp histograms of digit d into warp offsets and the tile count; an exclusive scan of the tile
 //      counts gives each digit's start inside the tile; offsets[d * tiles + tile] (the scanned counts) is where the tile's
 //      first pair of digit d goes globally;
@@ -238,72 +238,65 @@ __global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const uint32_t 
 //      contiguous global runs.
 // Tiles are independent (all offsets are known), so the grid walks them in DESCENDING order: the keys the count kernel
 // read last are still in L2.  16 B per pair.
-__global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
-                                                                      const uint32_t *__restrict__ vals_in,
-                                                                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
-                                                                      const uint32_t *__restrict__ n_ptr, uint32_t len, uint32_t shift,
-                                                                      uint32_t mask, uint32_t tiles,
-                                                                      const uint32_t *__restrict__ offsets) {
-    __shared__ uint32_t s_warp_hist[kRsWarps][kRsBins];
-    __shared__ uint32_t s_sorted[kRsTile];
-    __shared__ uint32_t s_tile_start[kRsBins];   // first slot of digit d inside the tile-sorted order
-    __shared__ uint32_t s_gbase[kRsBins];        // global position of the tile's first pair of digit d, minus s_tile_start[d]
-    __shared__ uint32_t s_scan[kRsWarps];
+// The kernel is instruction-bound, not memory-bound (ncu, profiles/README.md: ~140 warp instructions per pair at 50 % issue
+// utilisation in the first version), hence: full tiles take a predicate-free instantiation, 16 items per thread keep four
+// CTAs resident per SM, and the digit-bit ballots are batched four items at a time so they overlap.
+template <bool FULL>
+__device__ __forceinline__ void radix_scatter_tile(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                                                   uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t tile_base,
+                                                   uint32_t tile_n, uint32_t shift, uint32_t mask, uint32_t goff,
+                                                   uint32_t (&s_warp_hist)[kRsWarps][kRsBins], uint32_t (&s_sorted)[kRsTile],
+                                                   uint32_t (&s_tile_start)[kRsBins], uint32_t (&s_gbase)[kRsBins],
+                                                   uint32_t (&s_scan)[kRsWarps]) {
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t tile = gridDim.x - 1 - blockIdx.x;
-    const uint32_t n = rs_count(n_ptr, len);
-    const uint32_t tile_base = tile * (uint32_t)kRsTile;
-    if (tile_base >= n) return;
-    const uint32_t goff = __ldg(offsets + (size_t)t * tiles + tile);
-#pragma unroll
-    for (int w = 0; w < kRsWarps; ++w) s_warp_hist[w][t] = 0u;
-    __syncthreads();
-    const uint32_t tile_n = min((uint32_t)kRsTile, n - tile_base);
-    const bool full = tile_n == (uint32_t)kRsTile;
-
-    uint32_t key[kRsItems], val[kRsItems];
-    uint32_t slot2[kRsItems / 2];   // two 16-bit slots per register
+    uint32_t key[kRsItems], val[kRsItems], slot[kRsItems];
     const uint32_t wbase = (uint32_t)warp * (kRsItems * 32) + lane;
-    if (full) {
 #pragma unroll
-        for (int i = 0; i < kRsItems; ++i) key[i] = __ldcs(keys_in + tile_base + wbase + i * 32);
+    for (int i = 0; i < kRsItems; ++i) {
+        const uint32_t e = wbase + i * 32;
+        key[i] = (FULL || e < tile_n) ? __ldcs(keys_in + tile_base + e) : 0xFFFFFFFFu;
+    }
 #pragma unroll
-        for (int i = 0; i < kRsItems; ++i) val[i] = __ldcs(vals_in + tile_base + wbase + i * 32);
-    } else {
-#pragma unroll
-        for (int i = 0; i < kRsItems; ++i) {
-            const uint32_t e = wbase + i * 32;
-            key[i] = e < tile_n ? keys_in[tile_base + e] : 0xFFFFFFFFu;
-            val[i] = e < tile_n ? vals_in[tile_base + e] : 0u;
-        }
+    for (int i = 0; i < kRsItems; ++i) {
+        const uint32_t e = wbase + i * 32;
+        val[i] = (FULL || e < tile_n) ? __ldcs(vals_in + tile_base + e) : 0u;
     }
     // 1. ranks inside the warp
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t *wh = s_warp_hist[warp];
 #pragma unroll
-    for (int i = 0; i < kRsItems; ++i) {
-        const bool valid = full || wbase + i * 32 < tile_n;
-        const uint32_t d = (key[i] >> shift) & mask;
-        // lanes holding the same digit: eight ballots, one per digit bit (match.any computes the same set but measured
-        // ~25 us per 8192-pair tile on B200: its issue rate, not memory, bounded the whole sort)
-        uint32_t peers = __ballot_sync(0xFFFFFFFFu, valid);
+    for (int i0 = 0; i0 < kRsItems; i0 += 4) {
+        uint32_t peers[4];
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t d = (key[i0 + q] >> shift) & mask;
+            uint32_t pm = 0xFFFFFFFFu;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+                pm &= bit ? bal : ~bal;
+            }
+            if (!FULL) {
+                const bool valid = wbase + (i0 + q) * 32 < tile_n;
+                pm &= __ballot_sync(0xFFFFFFFFu, valid);
+                if (!valid) pm = 0u;
+            }
+            peers[q] = pm;
         }
-        if (!valid) peers = 1u << lane;
-        const int leader = __ffs(peers) - 1;
-        uint32_t pre = 0;
-        if (lane == leader && valid) {
-            pre = wh[d];
-            wh[d] = pre + __popc(peers);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t d = (key[i0 + q] >> shift) & mask;
+            const uint32_t pm = peers[q];
+            uint32_t pre = 0;
+            if (pm != 0u && (pm & lt_mask) == 0u) {   // lowest lane of the group
+                pre = wh[d];
+                wh[d] = pre + __popc(pm);
+            }
+            __syncwarp();
+            pre = __shfl_sync(0xFFFFFFFFu, pre, pm ? __ffs(pm) - 1 : lane);
+            slot[i0 + q] = pre + __popc(pm & lt_mask);
         }
-        pre = __shfl_sync(0xFFFFFFFFu, pre, leader);
-        const uint32_t r = pre + __popc(peers & lt_mask);
-        if (i & 1) slot2[i / 2] |= r << 16;
-        else slot2[i / 2] = r;
-        __syncwarp();
     }
     __syncthreads();
     // 2. digit t: warp offsets, tile count, start inside the tile
@@ -333,11 +326,10 @@ __global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(const uint
     // 3. place in tile-sorted order, write out in runs
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i) {
-        if (full || wbase + i * 32 < tile_n) {
+        if (FULL || wbase + i * 32 < tile_n) {
             const uint32_t d = (key[i] >> shift) & mask;
-            const uint32_t sl = s_tile_start[d] + wh[d] + ((slot2[i / 2] >> ((i & 1) * 16)) & 0xFFFFu);
-            slot2[i / 2] = (i & 1) ? ((slot2[i / 2] & 0xFFFFu) | (sl << 16)) : ((slot2[i / 2] & 0xFFFF0000u) | sl);
-            s_sorted[sl] = key[i];
+            slot[i] += s_tile_start[d] + wh[d];
+            s_sorted[slot[i]] = key[i];
         }
     }
     __syncthreads();
@@ -346,7 +338,7 @@ __global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(const uint
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = (uint32_t)j * kRsThreads + t;
         if ((j & 3) == 0) dig4[j / 4] = 0;
-        if (full || e < tile_n) {
+        if (FULL || e < tile_n) {
             const uint32_t k = s_sorted[e];
             const uint32_t d = (k >> shift) & mask;
             dig4[j / 4] |= d << ((j & 3) * 8);
@@ -356,13 +348,42 @@ __global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(const uint
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < kRsItems; ++i)
-        if (full || wbase + i * 32 < tile_n) s_sorted[(slot2[i / 2] >> ((i & 1) * 16)) & 0xFFFFu] = val[i];
+        if (FULL || wbase + i * 32 < tile_n) s_sorted[slot[i]] = val[i];
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kRsItems; ++j) {
         const uint32_t e = (uint32_t)j * kRsThreads + t;
-        if (full || e < tile_n) vals_out[s_gbase[(dig4[j / 4] >> ((j & 3) * 8)) & 0xFFu] + e] = s_sorted[e];
+        if (FULL || e < tile_n) vals_out[s_gbase[(dig4[j / 4] >> ((j & 3) * 8)) & 0xFFu] + e] = s_sorted[e];
     }
+}
+
+__global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
+                                                                      const uint32_t *__restrict__ vals_in,
+                                                                      uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                                      const uint32_t *__restrict__ n_ptr, uint32_t len, uint32_t shift,
+                                                                      uint32_t mask, uint32_t tiles,
+                                                                      const uint32_t *__restrict__ offsets) {
+    __shared__ uint32_t s_warp_hist[kRsWarps][kRsBins];
+    __shared__ uint32_t s_sorted[kRsTile];
+    __shared__ uint32_t s_tile_start[kRsBins];   // first slot of digit d inside the tile-sorted order
+    __shared__ uint32_t s_gbase[kRsBins];        // global position of the tile's first pair of digit d, minus s_tile_start[d]
+    __shared__ uint32_t s_scan[kRsWarps];
+    const int t = threadIdx.x;
+    const uint32_t tile = gridDim.x - 1 - blockIdx.x;
+    const uint32_t n = rs_count(n_ptr, len);
+    const uint32_t tile_base = tile * (uint32_t)kRsTile;
+    if (tile_base >= n) return;
+    const uint32_t goff = __ldg(offsets + (size_t)t * tiles + tile);
+#pragma unroll
+    for (int w = 0; w < kRsWarps; ++w) s_warp_hist[w][t] = 0u;
+    __syncthreads();
+    const uint32_t tile_n = min((uint32_t)kRsTile, n - tile_base);
+    if (tile_n == (uint32_t)kRsTile)
+        radix_scatter_tile<true>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
+                                 s_tile_start, s_gbase, s_scan);
+    else
+        radix_scatter_tile<false>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
+                                  s_tile_start, s_gbase, s_scan);
 }
 
 }  // namespace
