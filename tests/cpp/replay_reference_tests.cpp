@@ -15,6 +15,9 @@ int orc_gemm(int variant, float *out, const orc_shape *so, const float *m1, cons
 int orc_gemv(int variant, float *out, const orc_shape *so, const float *m, const orc_shape *sm, const float *v, const orc_shape *sv, int *ran);
 int orc_op_assign(int op, float *a, const orc_shape *sa, const float *b, const orc_shape *sb);
 int orc_reduce(int op, const float *x, const orc_shape *s, float *result);
+int orc_prefix_sum(uint32_t *data, uint32_t n);
+int orc_radix_sort(const uint32_t *input_keys, const uint32_t *input_values, uint32_t len, uint32_t n_sort, uint32_t sorting_bits,
+                   uint32_t *output_keys, uint32_t *output_values);
 int orc_gemm_ord(int variant, float *out, const orc_shape *so, int out_rm, const float *m1, const orc_shape *s1, int m1_rm, const float *m2,
                  const orc_shape *s2, int m2_rm);
 }
@@ -139,6 +142,61 @@ int main() {
                 std::printf("gpu_reduce op %d: got %.8g ref %.8g rel %.3e\n", op, got, ref, e);
                 failures += !(e < 1e-5);
             }
+        }
+        {   // gpu_prefix_sum (wgrapier prefix_sum.rs:243-288): LEN = 15071, ones / iota / pseudo-random % 10000, exact
+            const uint32_t n = 15071;
+            auto ps = WgPrefixSum::from_device(gpu.device());
+            for (int which = 0; which < 3; ++which) {
+                std::vector<uint32_t> v(n);
+                uint32_t lcg = 12345u;
+                for (uint32_t i = 0; i < n; ++i) {
+                    lcg = lcg * 1664525u + 1013904223u;
+                    v[i] = which == 0 ? 1u : which == 1 ? i : (lcg >> 8) % 10000u;
+                }
+                auto t = Tensors::vector(n, usage).build_init<uint32_t>(gpu.device(), v);
+                auto ws = PrefixSumWorkspace::with_capacity(gpu.device(), n);
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    ps.dispatch(gpu.device(), pass, ws, t);
+                }
+                gpu.queue().submit(enc.finish());
+                auto got = t.read(gpu.device());
+                std::vector<uint32_t> ref = v, cpu = v;
+                orc_prefix_sum(ref.data(), n);
+                WgPrefixSum::eval_cpu(cpu);
+                const bool same = got == ref && got == cpu;
+                std::printf("gpu_prefix_sum input %d: %s\n", which, same ? "exact" : "MISMATCH");
+                failures += !same;
+            }
+        }
+        {   // test_sorting (wgparry radix_sort/mod.rs:238-330): 15 keys, values = 2 * key + 5, 32 bits
+            auto sort = RadixSort::from_device(gpu.device());
+            auto ws = RadixSortWorkspace::make(gpu.device());
+            int bad = 0;
+            for (uint32_t i = 0; i < 128; i += 5) {
+                std::vector<uint32_t> keys = {5 + i * 4, i, 6, 123, 74657, 123, 999, (1u << 24) + 123, 6, 7, 8, 0, i * 2, 16 + i, 128 * i};
+                std::vector<uint32_t> vals(keys.size());
+                for (size_t k = 0; k < keys.size(); ++k) vals[k] = keys[k] * 2 + 5;
+                const uint32_t n = (uint32_t)keys.size();
+                auto tk = Tensors::vector(n, usage).build_init<uint32_t>(gpu.device(), keys);
+                auto tv = Tensors::vector(n, usage).build_init<uint32_t>(gpu.device(), vals);
+                auto ok = Tensors::vector(n, usage).build_init<uint32_t>(gpu.device(), keys);
+                auto ov = Tensors::vector(n, usage).build_init<uint32_t>(gpu.device(), vals);
+                auto ns = Tensors::scalar(usage).build_init<uint32_t>(gpu.device(), std::vector<uint32_t>{n});
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    sort.dispatch(gpu.device(), pass, ws, tk, tv, ns, 32, ok, ov);
+                }
+                gpu.queue().submit(enc.finish());
+                auto gk = ok.read(gpu.device()), gv = ov.read(gpu.device());
+                std::vector<uint32_t> rk = keys, rv = vals;
+                orc_radix_sort(keys.data(), vals.data(), n, n, 32, rk.data(), rv.data());
+                bad += !(gk == rk && gv == rv);
+            }
+            std::printf("gpu_radix_sort: %s\n", bad == 0 ? "exact" : "MISMATCH");
+            failures += bad;
         }
         {   // extensions through the C++ mirror: fused Gemm + OpAssign(Add) epilogue, recorded into a graph and replayed
             const uint32_t n = 256;

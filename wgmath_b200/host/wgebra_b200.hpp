@@ -50,6 +50,7 @@ template <typename T> struct DType;
 template <> struct DType<float> { static constexpr wgb_dtype value = WGB_F32; };
 struct bf16 { uint16_t bits; };
 template <> struct DType<bf16> { static constexpr wgb_dtype value = WGB_BF16; };
+template <> struct DType<uint32_t> { static constexpr wgb_dtype value = WGB_F32; };   // 4-byte elements (GpuVector<u32> of the scan / sort primitives)
 
 using ViewShape = wgb_view_shape;  // shapes.rs:9-21
 
@@ -367,6 +368,56 @@ class Reduce {  // reduce.rs:62-124
     template <typename T> void dispatch(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuVectorView<T> value, const GpuScalar<T> &result) const {
         const ViewShape sv = shapes.get(d, value.shape());
         check(wgb_reduce(pass.raw(), (wgb_reduce_op)op, value.buffer()->raw, &sv, result.buffer().raw));
+    }
+};
+
+// wgrapier/src/dynamics/prefix_sum.rs:119-224 — auxiliary levels in the reference; only its bookkeeping here.
+struct PrefixSumWorkspace {
+    std::vector<uint32_t> stages;
+    static PrefixSumWorkspace make() { return {}; }
+    static PrefixSumWorkspace with_capacity(const Device &d, uint32_t buffer_len) { PrefixSumWorkspace w; w.reserve(d, buffer_len); return w; }
+    void reserve(const Device &, uint32_t buffer_len) {   // :185-224 (the reference never terminates for 0)
+        stages.clear();
+        uint32_t stage_len = (buffer_len + 255) / 256;
+        while (stage_len > 1) { stages.push_back(stage_len); stage_len = (stage_len + 255) / 256; }
+        stages.push_back(1);
+    }
+};
+
+class WgPrefixSum {  // prefix_sum.rs:22-117: in-place exclusive prefix sum of a GpuVector<u32>
+  public:
+    static WgPrefixSum from_device(const Device &) { return WgPrefixSum(); }
+    void dispatch(const Device &d, ComputePass &pass, PrefixSumWorkspace &workspace, const GpuVector<uint32_t> &data) const {
+        dispatch(d, pass, workspace, data.as_view());
+    }
+    void dispatch(const Device &d, ComputePass &pass, PrefixSumWorkspace &workspace, GpuVectorView<uint32_t> data) const {
+        workspace.reserve(d, data.len());
+        const ViewShape s = data.shape();
+        check(wgb_prefix_sum(pass.raw(), data.buffer()->raw, &s));
+    }
+    static void eval_cpu(std::vector<uint32_t> &v) {   // :101-117
+        uint32_t run = 0;
+        for (auto &x : v) { const uint32_t t = x; x = run; run += t; }
+    }
+};
+
+struct RadixSortWorkspace {  // wgparry/src/utils/radix_sort/mod.rs:82-109 (buffers live in the context here)
+    static RadixSortWorkspace make(const Device &) { return {}; }
+};
+
+class RadixSort {  // radix_sort/mod.rs:67-223
+  public:
+    static RadixSort from_device(const Device &) { return RadixSort(); }
+    void dispatch(const Device &, ComputePass &pass, RadixSortWorkspace &, const GpuVector<uint32_t> &input_keys,
+                  const GpuVector<uint32_t> &input_values, const GpuScalar<uint32_t> &n_sort, uint32_t sorting_bits,
+                  const GpuVector<uint32_t> &output_keys, const GpuVector<uint32_t> &output_values) const {
+        if (input_keys.len() != input_values.len())     // assert_eq! :121-125
+            throw DimensionMismatch(WGB_ERR_DIM_MISMATCH, "Input keys and values must have the same number of elements");
+        if (sorting_bits > 32) throw Error(WGB_ERR_INVALID, "Can only sort up to 32 bits");   // assert! :126
+        const ViewShape sk = input_keys.as_view().shape(), sv = input_values.as_view().shape(), so = output_keys.as_view().shape(),
+                        sw = output_values.as_view().shape();
+        check(wgb_radix_sort(pass.raw(), input_keys.buffer().raw, &sk, input_values.buffer().raw, &sv, n_sort.buffer().raw, sorting_bits,
+                             output_keys.buffer().raw, &so, output_values.buffer().raw, &sw));
     }
 };
 
