@@ -495,6 +495,39 @@ def run_extras(w, O, gpu, shapes, timed, peaks, timed_graph):
          lambda p, i: rsort.dispatch(dev, p, rsw, keys, vals, nsort, 32, okeys, ovals))
     rec2("radix_sort (u32 key, u32 value) n=2^26, 16 bits", (4 + 2 * 16) * n, "4 + 2 digits x 16 B per pair",
          lambda p, i: rsort.dispatch(dev, p, rsw, keys, vals, nsort, 16, okeys, ovals))
+    del keys, vals, okeys, ovals, scan_data
+    # ---- batched small-matrix factorizations: out[i] = f(in[i]) over 2^22 (2x2: 2^24) matrices, one per thread.
+    # algorithmic bytes = (input matrix + output struct) per element; the iterative ones (eig3/4, svd3) are FP32-pipe bound
+    from wgmath_b200 import geometry as G
+    out["geometry"] = []
+    for dim in (2, 3, 4):
+        ng, lg = (1 << 24, 24) if dim == 2 else (1 << 22, 22)   # >= 192 MB of input either way (> the 126 MB L2)
+        # inputs generated on the device: U[0,1) words, then A^T A + I written over them would need another kernel, so the
+        # symmetric ops are timed on s = (a + a^T) / 2 + dim * I built once on the host for 2^16 matrices and tiled
+        base = np.random.default_rng(O.SEED_BASE + dim).random((1 << 16, dim, dim)).astype(np.float32)
+        sym = ((base + np.transpose(base, (0, 2, 1))) * 0.5 + dim * np.eye(dim, dtype=np.float32)).astype(np.float32)
+        gen_in = w.TensorBuilder.vector(ng, ST).build_init(dev, np.tile(G.pack(base), ng >> 16), f"mat{dim}")
+        sym_in = w.TensorBuilder.vector(ng, ST).build_init(dev, np.tile(G.pack(sym), ng >> 16), f"mat{dim}")
+        ops = [("cholesky", getattr(w, f"WgCholesky{dim}"), sym_in, f"mat{dim}"), ("lu", getattr(w, f"WgLU{dim}"), gen_in, f"lu{dim}"),
+               ("qr", getattr(w, f"WgQR{dim}"), gen_in, f"qr{dim}"), ("symmetric_eigen", getattr(w, f"WgSymmetricEigen{dim}"), sym_in, f"eig{dim}")]
+        if dim < 4:
+            ops.append(("svd", getattr(w, f"WgSvd{dim}"), gen_in, f"svd{dim}"))
+        for name, cls, src, odt in ops:
+            dst = w.TensorBuilder.vector(ng, ST).build(dev, odt)
+            sh = cls.from_device(dev)
+            nbytes = ng * (G.Matrix[dim].itemsize + cls.OUT_TYPE.itemsize)
+            sec, _ = timed(lambda p, i: sh.dispatch(dev, p, src, dst), 10, 3)
+            gbs = nbytes * 10 / sec / 1e9
+            out["geometry"].append({"op": f"{name}{dim} n=2^{lg}", "bytes": nbytes, "ms": sec * 1e2, "gbs": gbs, "frac_of_hbm": gbs / hbm,
+                                    "gmat_per_s": ng * 10 / sec / 1e9})
+            del dst
+        inv_dst = w.TensorBuilder.vector(ng, ST).build(dev, f"mat{dim}")
+        winv = w.WgInv.from_device(dev)
+        nbytes = ng * 2 * G.Matrix[dim].itemsize
+        sec, _ = timed(lambda p, i: winv.dispatch(dev, p, dim, sym_in, inv_dst), 10, 3)
+        out["geometry"].append({"op": f"inv{dim} n=2^{lg}", "bytes": nbytes, "ms": sec * 1e2, "gbs": nbytes * 10 / sec / 1e9,
+                                "frac_of_hbm": nbytes * 10 / sec / 1e9 / hbm, "gmat_per_s": ng * 10 / sec / 1e9})
+        del gen_in, sym_in, inv_dst
     return out
 
 

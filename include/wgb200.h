@@ -23,6 +23,9 @@
  *   wgb_prefix_sum       <-> wgrapier/src/dynamics/prefix_sum.rs:49-99 WgPrefixSum::dispatch + prefix_sum.wgsl:35-147
  *   wgb_radix_sort       <-> wgparry/src/utils/radix_sort/mod.rs:111-223 RadixSort::dispatch + sort_*.wgsl
  *                            (the integer scan / sort primitives next to the linalg path)
+ *   wgb_geometry_batch   <-> wgebra/src/geometry/{cholesky,lu,qr2,qr3,qr4,eig2,eig3,eig4,svd2,svd3,inv}.wgsl applied as
+ *                            `out[i] = f(in[i])`, the kernel every test of that module builds (cholesky.rs:53-63,
+ *                            lu.rs:101-111, qr2.rs:36-46, eig3.rs:36-46, svd3.rs:34-44) — SURVEY.md §8(f) 4, first half
  *
  * Extensions that have no reference counterpart (named by BASELINE.json north_star):
  *   wgb_gemm_ex            bf16 operands / bf16 output, f32 compute-mode selection
@@ -127,6 +130,17 @@ typedef enum wgb_reduce_op {
     WGB_RED_PROD = 3,
     WGB_RED_SQNORM = 4
 } wgb_reduce_op;
+
+/* wgebra/src/geometry/mod.rs:3-17: the factorization libraries (WgCholesky2..4, WgLU2..4, WgQR2..4, WgSymmetricEigen2..4,
+ * WgSvd2 / WgSvd3, WgInv) */
+typedef enum wgb_geom_op {
+    WGB_GEOM_CHOLESKY = 0,
+    WGB_GEOM_LU = 1,
+    WGB_GEOM_QR = 2,
+    WGB_GEOM_SYMMETRIC_EIGEN = 3,
+    WGB_GEOM_SVD = 4, /* 2x2 and 3x3 only, like the reference */
+    WGB_GEOM_INV = 5
+} wgb_geom_op;
 
 /* How an f32 x f32 GEMM is computed on the tensor cores. */
 typedef enum wgb_f32_mode {
@@ -289,6 +303,25 @@ wgb_status wgb_radix_sort(wgb_pass *pass, const wgb_buffer *input_keys, const wg
                           const wgb_buffer *input_values, const wgb_view_shape *input_values_shape, const wgb_buffer *n_sort,
                           uint32_t sorting_bits, wgb_buffer *output_keys, const wgb_view_shape *output_keys_shape,
                           wgb_buffer *output_values, const wgb_view_shape *output_values_shape);
+
+/* Batched small-matrix factorizations: out[i] = f(in[i]) for i < n, one dim x dim f32 matrix per element (dim = 2, 3, 4).
+ * In the reference these are WGSL function libraries other shaders import (geometry/mod.rs:3-17); the batched form is the
+ * kernel each of its tests builds around them.  Elements use WGSL's storage layout, which is what the reference's Rust side
+ * uploads and reads back (Matrix2 / Matrix4x3 / Matrix4, GpuLU*, GpuQR*, GpuSymmetricEigen*, GpuSvd2, GpuSvd3):
+ *   matrix  = dim columns of CS floats, CS = 2 (dim 2) or 4 (dim 3 and 4; the 4th float of a vec3 column is padding)
+ *   CHOLESKY, INV      -> matrix                                   16 / 48 / 64 bytes   (cholesky.wgsl:16-35, inv.wgsl:8-88)
+ *   LU                 -> {lu: matrix, ia: uvecN, ib: uvecN, len}   40 / 80 / 112 bytes  (lu.wgsl:12-81; lu.rs:25-56)
+ *   QR                 -> {q: matrix, r: matrix}                    32 / 96 / 128 bytes  (qr2.wgsl:7-107; qr3.rs:15-20)
+ *   SYMMETRIC_EIGEN    -> {eigenvectors: matrix, eigenvalues: vecN} 24 / 64 / 80 bytes   (eig2.wgsl:7-40, eig3.wgsl:13-160)
+ *   SVD (dim 2, 3)     -> {U: matrix, S: vecN, Vt: matrix}          40 / 112 bytes       (svd2.wgsl:5-39, svd3.wgsl:12-305)
+ * Padding words are written as zero.  in_first / out_first are element indices into the buffers (a GpuVector view's offset).
+ * In place (same buffer, same first element) is allowed for CHOLESKY and INV; any other overlap is WGB_ERR_INVALID.
+ * n == 0 or a zero-sized buffer enqueues nothing (kernel.rs:111-113,144).  The QR sweeps of eig3 / eig4 are unbounded in the
+ * reference (eig3.wgsl:77); here they stop after 256 sweeps. */
+uint32_t wgb_geometry_in_bytes(int dim);
+uint32_t wgb_geometry_out_bytes(wgb_geom_op op, int dim);
+wgb_status wgb_geometry_batch(wgb_pass *pass, wgb_geom_op op, int dim, const wgb_buffer *in, uint64_t in_first, wgb_buffer *out,
+                              uint64_t out_first, uint64_t n);
 
 /* Diagnostics (no reference counterpart): per-cluster timeline of the most recent tcgen05 GEMM launch on this context.
  * enable != 0 switches tracing on for later launches (a few global stores per CTA); out, if non-null, receives up to

@@ -42,7 +42,7 @@ def shape(nrows, ncols=1, nmats=1, stride=None, stride_mat=None, offset=0) -> Sh
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("wgsl_oracle.c", "scan_sort_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("wgsl_oracle.c", "scan_sort_oracle.c", "geometry_oracle.c")]
     if force or not os.path.exists(_LIB_PATH) or any(
             os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(_LIB_PATH) for src in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s", "clean", "all"])
@@ -71,6 +71,11 @@ def lib():
         up = ctypes.POINTER(ctypes.c_uint32)
         L.orc_prefix_sum.argtypes = [up, ctypes.c_uint32]
         L.orc_radix_sort.argtypes = [up, up, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, up, up]
+        L.orc_geom_batch.argtypes = [ctypes.c_int, ctypes.c_int, fp, ctypes.c_void_p, ctypes.c_uint64]
+        L.orc_geom_out_words.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.orc_geom_out_words.restype = ctypes.c_uint32
+        L.orc_geom_in_words.argtypes = [ctypes.c_int]
+        L.orc_geom_in_words.restype = ctypes.c_uint32
         L.orc_num_threads.restype = ctypes.c_int
         L.orc_set_num_threads.argtypes = [ctypes.c_int]
         L.orc_set_num_threads.restype = None
@@ -191,3 +196,42 @@ def radix_sort(keys: np.ndarray, values: np.ndarray, n_sort: int, sorting_bits: 
     """RadixSort::dispatch (wgparry/src/utils/radix_sort/mod.rs:111-223)."""
     assert keys.size == values.size and out_keys.size >= keys.size and out_values.size >= keys.size
     return lib().orc_radix_sort(_up(keys), _up(values), keys.size, n_sort, sorting_bits, _up(out_keys), _up(out_values))
+
+
+# wgebra::geometry batched factorizations (geometry_oracle.c)
+GEOM_CHOLESKY, GEOM_LU, GEOM_QR, GEOM_EIG, GEOM_SVD, GEOM_INV = range(6)
+
+
+def geom_in_words(dim: int) -> int:
+    return lib().orc_geom_in_words(dim)
+
+
+def geom_out_words(op: int, dim: int) -> int:
+    return lib().orc_geom_out_words(op, dim)
+
+
+def geom_batch(op: int, dim: int, mats: np.ndarray) -> np.ndarray:
+    """out[i] = f(in[i]) in WGSL storage layout (the test kernels of wgebra/src/geometry/*.rs).  `mats` is a float32 array
+    [n, geom_in_words(dim)]; returns float32 [n, geom_out_words(op, dim)] (view as uint32 for the LU permutation words)."""
+    iw, ow = geom_in_words(dim), geom_out_words(op, dim)
+    assert ow, f"unsupported geometry op {op} for dim {dim}"
+    mats = np.ascontiguousarray(mats, np.float32).reshape(-1, iw)
+    out = np.zeros((mats.shape[0], ow), np.float32)
+    rc = lib().orc_geom_batch(op, dim, _fp(mats), out.ctypes.data_as(ctypes.c_void_p), mats.shape[0])
+    assert rc == 0
+    return out
+
+
+def geom_pack(mats: np.ndarray) -> np.ndarray:
+    """[n, dim, dim] matrices (mats[i][r][c]) -> WGSL storage layout [n, dim * col_stride] (column-major, vec3 columns padded)."""
+    n, dim, _ = mats.shape
+    cs = 2 if dim == 2 else 4
+    out = np.zeros((n, dim, cs), np.float32)
+    out[:, :, :dim] = np.transpose(mats, (0, 2, 1))
+    return out.reshape(n, dim * cs)
+
+
+def geom_unpack(words: np.ndarray, dim: int) -> np.ndarray:
+    """Inverse of geom_pack for one matrix field: [n, dim * col_stride] -> [n, dim, dim] (row, column)."""
+    cs = 2 if dim == 2 else 4
+    return np.transpose(words.reshape(-1, dim, cs)[:, :, :dim], (0, 2, 1))

@@ -32,6 +32,25 @@ def main():
     np.savez(os.path.join(HERE, "level12.npz"), m=m, v=v, x128=x128, x345=x345,
              gemv=mm @ v.astype(np.float64), gemv_tr=mm.T @ x128.astype(np.float64),
              min=x.min(), max=x.max(), sum=x.sum(), prod=x.prod(), sqnorm=(x * x).sum())
+    geometry()
+
+
+def geometry():
+    """wgebra::geometry fixtures: seeded U[0,1) matrices a (general) and s = a^T a + 0.05 I (SDP), with float64 factorizations
+    from numpy / scipy (nalgebra's conventions: lower Cholesky factor, QR with a non-negative diagonal of r)."""
+    out = {}
+    for dim in (2, 3, 4):
+        a = O.uniform(O.SEED_BASE + 10 + dim, 64 * dim * dim).reshape(64, dim, dim)
+        a64 = a.astype(np.float64)
+        s = (np.einsum("nki,nkj->nij", a64, a64) + 0.05 * np.eye(dim)).astype(np.float32)
+        s64 = s.astype(np.float64)
+        q, r = np.linalg.qr(a64)
+        sg = np.sign(np.diagonal(r, axis1=1, axis2=2))
+        sg[sg == 0] = 1.0
+        out.update({f"a{dim}": a, f"s{dim}": s, f"chol{dim}": np.linalg.cholesky(s64), f"q{dim}": q * sg[:, None, :],
+                    f"r{dim}": r * sg[:, :, None], f"eigvals{dim}": np.linalg.eigvalsh(s64), f"inv{dim}": np.linalg.inv(s64),
+                    f"det{dim}": np.linalg.det(a64), f"sv{dim}": np.linalg.svd(a64, compute_uv=False)})
+    np.savez(os.path.join(HERE, "geometry.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,260 @@
+"""CPU tests (no GPU) for oracle/geometry_oracle.c — the restatement of wgebra::geometry's factorization libraries.
+
+The reference's own tests (cholesky.rs:86-149, lu.rs:129-181, qr2.rs:70-121 (= qr3 / qr4), eig2.rs:69-114, eig3.rs:71-131,
+eig4.rs:72-131, svd2.rs:68-107, svd3.rs:70-111) are replayed at their sizes (LEN = 345 random matrices, seeded here), their
+tolerances (1e-3 / 1e-4) and their pass criteria (reconstruction, or factor-by-factor against nalgebra with 1-2 % allowed
+failures) with numpy float64 standing in for nalgebra; tighter float32-level bounds are asserted next to them.  Also: the
+committed fixture tests/golden/geometry.npz (float64 factorizations of seeded inputs), storage layout, and the host mirror's
+struct dtypes against the C ABI's sizes (symbol lookups only — no GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+import wgmath_b200 as w
+from oracle import oracle as O
+from wgmath_b200 import geometry as G
+
+LEN = 345
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "geometry.npz")
+OPS = {"cholesky": O.GEOM_CHOLESKY, "lu": O.GEOM_LU, "qr": O.GEOM_QR, "eig": O.GEOM_EIG, "svd": O.GEOM_SVD, "inv": O.GEOM_INV}
+
+
+def cs(dim):
+    return 2 if dim == 2 else 4
+
+
+def random_mats(dim, seed, n=LEN):
+    """DVector::<MatrixN<f32>>::new_random(LEN): entries U[0, 1)."""
+    return np.random.default_rng(seed).random((n, dim, dim)).astype(np.float32)
+
+
+def sdp(a):
+    """m.transpose() * m (cholesky.rs:98-102, eig3.rs:80-82), rounded to f32 like the reference's f32 product."""
+    return np.einsum("nki,nkj->nij", a, a).astype(np.float32)
+
+
+def relative_eq(a, b, eps):
+    """approx::relative_eq!(a, b, epsilon = eps) with the default max_relative = f32::EPSILON, element-wise."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    d = np.abs(a - b)
+    ok = (d <= eps) | (d <= np.maximum(np.abs(a), np.abs(b)) * np.finfo(np.float32).eps)
+    return ok.reshape(ok.shape[0], -1).all(axis=1)
+
+
+def lu_fields(words, dim):
+    mw = dim * cs(dim)
+    lu = O.geom_unpack(words[:, :mw], dim)
+    p = np.ascontiguousarray(words[:, mw:]).view(np.uint32)
+    return lu, p[:, :dim], p[:, cs(dim):cs(dim) + dim], p[:, 7 if dim == 3 else 2 * cs(dim)]
+
+
+def lu_reconstruct_error(a, lu, ia, ib, ln):
+    dim = a.shape[1]
+    err = 0.0
+    for i in range(a.shape[0]):
+        L = np.tril(lu[i].astype(np.float64), -1) + np.eye(dim)
+        U = np.triu(lu[i].astype(np.float64))
+        pa = a[i].astype(np.float64).copy()
+        for k in range(ln[i]):
+            pa[[ia[i, k], ib[i, k]]] = pa[[ib[i, k], ia[i, k]]]
+        err = max(err, np.abs(L @ U - pa).max() / max(1.0, np.abs(pa).max()))
+    return err
+
+
+def split(words, dim, op):
+    """Output words -> dict of unpacked fields."""
+    mw, c = dim * cs(dim), cs(dim)
+    if op in ("cholesky", "inv"):
+        return {"m": O.geom_unpack(words, dim)}
+    if op == "qr":
+        return {"q": O.geom_unpack(words[:, :mw], dim), "r": O.geom_unpack(words[:, mw:], dim)}
+    if op == "eig":
+        return {"vectors": O.geom_unpack(words[:, :mw], dim), "values": words[:, mw:mw + dim], "pad": words[:, mw + dim:]}
+    if op == "svd":
+        return {"u": O.geom_unpack(words[:, :mw], dim), "s": words[:, mw:mw + dim], "vt": O.geom_unpack(words[:, mw + c:], dim)}
+    raise KeyError(op)
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_reference_cholesky_replay(dim):
+    """cholesky.rs:86-149: SDP inputs, lower triangle vs nalgebra's cholesky at 1e-3, up to 1 % failures allowed."""
+    m = sdp(random_mats(dim, 100 + dim))
+    got = split(O.geom_batch(O.GEOM_CHOLESKY, dim, O.geom_pack(m)), dim, "cholesky")["m"]
+    fails = checked = 0
+    for i in range(LEN):
+        try:
+            ref = np.linalg.cholesky(m[i].astype(np.float64))
+        except np.linalg.LinAlgError:
+            continue                                      # `if let Some(chol_cpu)`
+        checked += 1
+        # unpack_dirty(): only the lower triangle is meaningful; the oracle passes the upper triangle of the input through
+        fails += not relative_eq(np.tril(got[i])[None], ref[None], 1e-3)[0]
+        assert np.array_equal(np.triu(got[i], 1), np.triu(m[i], 1))
+    assert checked > LEN // 2 and fails <= LEN // 100
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_reference_lu_replay(dim):
+    """lu.rs:129-181 compares lu_internal() with nalgebra at 1e-3.  Partial pivoting picks the same pivots unless two
+    candidates tie to within rounding, so besides the factor comparison P*A = L*U is checked (which the reference leaves as
+    a TODO: 'check the permutation vectors')."""
+    m = sdp(random_mats(dim, 200 + dim))
+    lu, ia, ib, ln = lu_fields(O.geom_batch(O.GEOM_LU, dim, O.geom_pack(m)), dim)
+    assert lu_reconstruct_error(m, lu, ia, ib, ln) < 1e-5
+    assert (ln <= dim).all() and (ia[np.arange(dim)[None] < ln[:, None]] <= ib[np.arange(dim)[None] < ln[:, None]]).all()
+    import scipy.linalg
+    agree = 0
+    for i in range(LEN):
+        p, l, u = scipy.linalg.lu(m[i].astype(np.float64))
+        agree += bool(relative_eq((np.tril(l, -1) + u)[None], lu[i][None], 1e-3)[0])
+    assert agree >= LEN - LEN // 50
+    # a general (non-symmetric) batch and an exactly singular column: `continue` without a permutation (lu.wgsl:55-58)
+    g = random_mats(dim, 210 + dim) - 0.5
+    g[0, :, 0] = 0.0
+    lu, ia, ib, ln = lu_fields(O.geom_batch(O.GEOM_LU, dim, O.geom_pack(g)), dim)
+    assert lu_reconstruct_error(g, lu, ia, ib, ln) < 1e-5
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_reference_qr_replay(dim):
+    """qr2.rs:70-121: q and r vs nalgebra at 1e-4, 2 % failures allowed.  nalgebra's convention (r has a non-negative
+    diagonal, qr2.wgsl:99-104) makes the factorization unique, so numpy's QR with the signs fixed is the comparison."""
+    m = random_mats(dim, 300 + dim)
+    f = split(O.geom_batch(O.GEOM_QR, dim, O.geom_pack(m)), dim, "qr")
+    fails = 0
+    for i in range(LEN):
+        q, r = np.linalg.qr(m[i].astype(np.float64))
+        s = np.sign(np.diag(r))
+        s[s == 0] = 1.0
+        q, r = q * s[None, :], r * s[:, None]
+        fails += not (relative_eq(q[None], f["q"][i][None], 1e-4)[0] and relative_eq(r[None], f["r"][i][None], 1e-4)[0])
+    assert fails <= LEN * 2 // 100
+    q64, r64 = f["q"].astype(np.float64), f["r"].astype(np.float64)
+    assert np.abs(q64 @ r64 - m).max() < 2e-5
+    assert np.abs(q64 @ np.transpose(q64, (0, 2, 1)) - np.eye(dim)).max() < 2e-5
+    assert (np.tril(f["r"], -1) == 0).all() and (np.diagonal(f["r"], axis1=1, axis2=2) >= 0).all()
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_reference_symmetric_eigen_replay(dim):
+    """eig2.rs:69-114 (every matrix), eig3.rs:71-131 / eig4.rs:72-131 (2 % failures allowed): V diag(w) V^T == m at 1e-4."""
+    m = sdp(random_mats(dim, 400 + dim))
+    f = split(O.geom_batch(O.GEOM_EIG, dim, O.geom_pack(m)), dim, "eig")
+    v, wv = f["vectors"].astype(np.float64), f["values"].astype(np.float64)
+    rec = np.einsum("nij,nj,nkj->nik", v, wv, v)
+    fails = int((~relative_eq(m, rec, 1e-4)).sum())
+    assert fails <= (0 if dim == 2 else LEN * 2 // 100)
+    assert (f["pad"] == 0).all()
+    # the eigenvalue set is right for every matrix (the rare failures are a value / vector pairing quirk of the 2x2 deflation
+    # step when the rotation is skipped, eig3.wgsl:139-146 — inherited from the algorithm, see test below)
+    ref = np.linalg.eigvalsh(m.astype(np.float64))
+    assert np.abs(np.sort(wv, axis=1) - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_eig4_deflation_pairing_quirk_is_reproduced():
+    """A matrix from the replay batch where the final 2x2 block is already diagonal to within EPS: eigenvalues() orders the
+    pair (larger first) but the rotation that would swap the vectors is skipped (basis_len <= EPS, eig3.wgsl:143), so values
+    1 and 2 come out swapped relative to their vectors.  The oracle must reproduce this — it is the reference's behaviour and
+    the reason its own test tolerates failures."""
+    s = np.array([[0.37746996, 0.8060205, 0.6533892, 0.8363194], [0.8060205, 2.350354, 1.8683364, 2.3084645],
+                  [0.6533892, 1.8683364, 1.5784148, 1.8615451], [0.8363194, 2.3084645, 1.8615451, 2.2928061]], np.float32)
+    f = split(O.geom_batch(O.GEOM_EIG, 4, O.geom_pack(s[None])), 4, "eig")
+    v, wv = f["vectors"][0].astype(np.float64), f["values"][0].astype(np.float64)
+    assert np.abs(v @ v.T - np.eye(4)).max() < 1e-6                      # still orthonormal
+    assert np.abs(np.sort(wv) - np.linalg.eigvalsh(s.astype(np.float64))).max() < 1e-5
+    rayleigh = np.einsum("ij,ik,kj->j", v, s.astype(np.float64), v)      # the value each vector really belongs to
+    assert np.abs(rayleigh[[0, 2, 1, 3]] - wv).max() < 1e-5 and abs(rayleigh[1] - wv[1]) > 0.05
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_reference_svd_replay(dim):
+    """svd2.rs:68-107, svd3.rs:70-111: U diag(S) Vt == m at 1e-4 for every matrix."""
+    m = random_mats(dim, 500 + dim)
+    f = split(O.geom_batch(O.GEOM_SVD, dim, O.geom_pack(m)), dim, "svd")
+    u, s, vt = f["u"].astype(np.float64), f["s"].astype(np.float64), f["vt"].astype(np.float64)
+    rec = np.einsum("nij,nj,njk->nik", u, s, vt)
+    assert relative_eq(m, rec, 1e-4).all()
+    ref = np.linalg.svd(m.astype(np.float64), compute_uv=False)
+    assert np.abs(np.abs(s) - ref).max() < 3e-5 * max(1.0, ref.max())    # sorted descending (svd2.wgsl:21-27, svd3.wgsl:183-212)
+    assert np.abs(u @ np.transpose(u, (0, 2, 1)) - np.eye(dim)).max() < 5e-5   # svd3 builds U / V from approximate rsqrt steps
+    assert np.abs(vt @ np.transpose(vt, (0, 2, 1)) - np.eye(dim)).max() < 5e-5
+
+
+def test_svd2_identity_edge_case():
+    """trig.wgsl:21-41: stable_atan2 exists so that svd(identity) is well defined."""
+    f = split(O.geom_batch(O.GEOM_SVD, 2, O.geom_pack(np.eye(2, dtype=np.float32)[None])), 2, "svd")
+    assert np.array_equal(f["s"][0], [1.0, 1.0])
+    assert np.allclose(f["u"][0] @ np.diag(f["s"][0]) @ f["vt"][0], np.eye(2), atol=1e-7)
+
+
+@pytest.mark.parametrize("dim", [2, 3, 4])
+def test_inverse(dim):
+    """inv.wgsl:8-88 (no test in the reference): A^-1 A = I on well-conditioned inputs."""
+    m = random_mats(dim, 600 + dim) + 2.0 * np.eye(dim, dtype=np.float32)
+    inv = split(O.geom_batch(O.GEOM_INV, dim, O.geom_pack(m)), dim, "inv")["m"].astype(np.float64)
+    assert np.abs(inv @ m - np.eye(dim)).max() < 1e-5
+    assert np.abs(inv - np.linalg.inv(m.astype(np.float64))).max() < 1e-5
+
+
+def test_golden_fixture():
+    """tests/golden/geometry.npz (make_golden.py): seeded inputs and their float64 factorizations."""
+    g = np.load(GOLDEN)
+    for dim in (2, 3, 4):
+        a, s = g[f"a{dim}"], g[f"s{dim}"]
+        chol = split(O.geom_batch(O.GEOM_CHOLESKY, dim, O.geom_pack(s)), dim, "cholesky")["m"]
+        assert np.abs(np.tril(chol) - g[f"chol{dim}"]).max() < 1e-4
+        f = split(O.geom_batch(O.GEOM_QR, dim, O.geom_pack(a)), dim, "qr")
+        assert np.abs(f["q"] - g[f"q{dim}"]).max() < 1e-4 and np.abs(f["r"] - g[f"r{dim}"]).max() < 1e-4
+        e = split(O.geom_batch(O.GEOM_EIG, dim, O.geom_pack(s)), dim, "eig")
+        assert np.abs(np.sort(e["values"], axis=1) - g[f"eigvals{dim}"]).max() < 1e-4
+        inv = split(O.geom_batch(O.GEOM_INV, dim, O.geom_pack(s)), dim, "inv")["m"]
+        assert np.abs(inv - g[f"inv{dim}"]).max() < 1e-3 * np.abs(g[f"inv{dim}"]).max()
+        lu, ia, ib, ln = lu_fields(O.geom_batch(O.GEOM_LU, dim, O.geom_pack(a)), dim)
+        assert np.abs(np.abs(np.prod(np.diagonal(lu, axis1=1, axis2=2), axis=1)) - np.abs(g[f"det{dim}"])).max() < 1e-5
+        if dim < 4:
+            sv = split(O.geom_batch(O.GEOM_SVD, dim, O.geom_pack(a)), dim, "svd")
+            assert np.abs(np.abs(sv["s"]) - g[f"sv{dim}"]).max() < 1e-4
+
+
+def test_storage_layout_and_padding():
+    """vec3 columns are padded to 16 bytes (Matrix4x3 in the reference's tests); padding words come back as zero."""
+    assert [O.geom_in_words(d) for d in (2, 3, 4)] == [4, 12, 16]
+    expect = {"cholesky": [4, 12, 16], "inv": [4, 12, 16], "lu": [10, 20, 28], "qr": [8, 24, 32], "eig": [6, 16, 20], "svd": [10, 28, 0]}
+    for name, words in expect.items():
+        assert [O.geom_out_words(OPS[name], d) for d in (2, 3, 4)] == words
+    m = random_mats(3, 7, 5)
+    packed = O.geom_pack(m)
+    packed.reshape(5, 3, 4)[:, :, 3] = 123.0                                 # garbage in the input padding must not leak
+    for name in ("cholesky", "qr", "eig", "svd", "inv"):
+        out = O.geom_batch(OPS[name], 3, packed).reshape(5, -1, 4)
+        assert (out[:, :, 3] == 0).all(), name
+
+
+def test_host_mirror_struct_sizes_match_the_abi():
+    """The numpy struct dtypes of wgmath_b200.geometry against wgb_geometry_{in,out}_bytes (no GPU: size queries only)."""
+    L = w.lib()
+    for d in (2, 3, 4):
+        assert L.wgb_geometry_in_bytes(d) == G.Matrix[d].itemsize == 4 * O.geom_in_words(d)
+        for op, t in ((G.GEOM_CHOLESKY, G.Matrix), (G.GEOM_LU, G.GpuLU), (G.GEOM_QR, G.GpuQR), (G.GEOM_SYMMETRIC_EIGEN, G.GpuSymmetricEigen),
+                      (G.GEOM_INV, G.Matrix)):
+            assert L.wgb_geometry_out_bytes(op, d) == t[d].itemsize == 4 * O.geom_out_words(op, d)
+    assert [L.wgb_geometry_out_bytes(G.GEOM_SVD, d) for d in (2, 3, 4)] == [40, 112, 0]
+    assert G.GpuSvd[2].itemsize == 40 and G.GpuSvd[3].itemsize == 112
+    assert L.wgb_geometry_in_bytes(5) == 0 and L.wgb_geometry_in_bytes(1) == 0
+    lu3 = np.zeros(1, G.GpuLU[3])
+    assert lu3.dtype.fields["ib"][1] == 64 and lu3.dtype.fields["len"][1] == 76   # len packs behind the 12-byte vec3<u32>
+    p = G.pack(random_mats(3, 1, 4))
+    assert np.array_equal(G.unpack(p["m"]), random_mats(3, 1, 4))
+
+
+def test_geometry_without_gpu_fails_loudly():
+    """No CPU fallback: without a device the context cannot be created, so nothing can be dispatched."""
+    import ctypes
+    h = ctypes.c_void_p()
+    rc = w.lib().wgb_ctx_create(0, ctypes.byref(h))
+    if rc == 0:
+        w.lib().wgb_ctx_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc != 0
+    assert w.lib().wgb_geometry_batch(None, 0, 2, None, 0, None, 0, 1) != 0     # null pass: WGB_ERR_INVALID, never computes

@@ -87,6 +87,9 @@ def lib() -> ctypes.CDLL:
         "wgb_reduce": ([vp, ci, vp, sp, vp], ci),
         "wgb_prefix_sum": ([vp, vp, sp], ci),
         "wgb_radix_sort": ([vp, vp, sp, vp, sp, vp, u32, vp, sp, vp, sp], ci),
+        "wgb_geometry_in_bytes": ([ci], u32),
+        "wgb_geometry_out_bytes": ([ci, ci], u32),
+        "wgb_geometry_batch": ([vp, ci, ci, vp, u64, vp, u64, u64], ci),
         "wgb_dot": ([vp, vp, sp, vp, sp, vp], ci),
         "wgb_reduce_columns": ([vp, ci, vp, sp, vp, sp], ci),
         "wgb_fill_uniform": ([vp, vp, sp, ci, u64, u32, u32], ci),
@@ -122,7 +125,7 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_buffer_destroy", "wgb_buffer_size", "wgb_buffer_device_ptr", "wgb_buffer_write", "wgb_buffer_copy",
             "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_op", "wgb_gemm_ord", "wgb_gemm_host", "wgb_gemm_host_enqueue", "wgb_gemm_host_flush", "wgb_gemv",
             "wgb_gemv_ord", "wgb_debug_tc_trace",
-            "wgb_op_assign", "wgb_reduce", "wgb_prefix_sum", "wgb_radix_sort", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",
+            "wgb_op_assign", "wgb_reduce", "wgb_prefix_sum", "wgb_radix_sort", "wgb_geometry_in_bytes", "wgb_geometry_out_bytes", "wgb_geometry_batch", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",
             "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded", "wgb_peer_gather_create",
             "wgb_peer_gather_export", "wgb_peer_gather_connect", "wgb_peer_gather_buffer", "wgb_peer_gather_destroy",

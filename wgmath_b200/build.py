@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libwgebra_b200.so")
-SOURCES = ["abi.cu", "level1.cu", "scan_sort.cu", "gemv.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "comm.cu"]
+SOURCES = ["abi.cu", "level1.cu", "scan_sort.cu", "geometry.cu", "gemv.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm.cu", "comm.cu"]
 # the tcgen05 kernel variants, one operand family per translation unit so they compile in parallel (gemm_tc_kernel.cuh)
 SOURCES += sorted(f for f in os.listdir(CSRC) if f.startswith("gemm_tc_inst_") and f.endswith(".cu"))
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -25,6 +25,11 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 HOST_CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX,
                      "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+
+
+# per-file flags.  geometry.cu: no FMA contraction, so the factorizations evaluate exactly the operation sequence of the WGSL
+# (and of oracle/geometry_oracle.c, built with -ffp-contract=off); the only fused operations are the WGSL's own fma() calls.
+EXTRA_FLAGS = {"geometry.cu": ["-fmad=false"]}
 
 
 def nvcc() -> str:
@@ -51,7 +56,7 @@ def _stale(target: str, deps) -> bool:
 
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-    cmd = [nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [nvcc()] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

@@ -2,8 +2,9 @@
 /root/reference/crates/wgcore/src/tensor.rs (line numbers below refer to that file).
 
 Element types: the reference is generic over `T: Pod`; here a tensor carries a dtype tag,
-"f32" (numpy float32), "bf16" (numpy uint16 bit patterns) or "u32" (numpy uint32: the GpuVector<u32> / GpuScalar<u32>
-operands of the scan and sort primitives)."""
+"f32" (numpy float32), "bf16" (numpy uint16 bit patterns), "u32" (numpy uint32: the GpuVector<u32> / GpuScalar<u32>
+operands of the scan and sort primitives) or a registered struct type (register_dtype: the small-matrix element types of
+wgebra::geometry)."""
 from __future__ import annotations
 
 import ctypes
@@ -27,6 +28,14 @@ class BufferUsages:
 
 
 _DT = {"f32": (np.float32, 4), "bf16": (np.uint16, 2), "u32": (np.uint32, 4)}
+
+
+def register_dtype(name: str, dtype: np.dtype) -> str:
+    """A `T: Pod` / `T: ShaderType` element type beyond the scalar ones: a numpy structured dtype laid out like the WGSL
+    storage struct (geometry.py registers Matrix2 / Matrix4x3 / Matrix4 and the GpuLU* / GpuQR* / ... structs)."""
+    dtype = np.dtype(dtype)
+    _DT[name] = (dtype, dtype.itemsize)
+    return name
 
 
 class Buffer:
