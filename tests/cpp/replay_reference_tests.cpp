@@ -18,6 +18,7 @@ int orc_reduce(int op, const float *x, const orc_shape *s, float *result);
 int orc_prefix_sum(uint32_t *data, uint32_t n);
 int orc_radix_sort(const uint32_t *input_keys, const uint32_t *input_values, uint32_t len, uint32_t n_sort, uint32_t sorting_bits,
                    uint32_t *output_keys, uint32_t *output_values);
+int orc_geom_batch(int op, int dim, const float *in, void *out, uint64_t n);
 int orc_gemm_ord(int variant, float *out, const orc_shape *so, int out_rm, const float *m1, const orc_shape *s1, int m1_rm, const float *m2,
                  const orc_shape *s2, int m2_rm);
 }
@@ -197,6 +198,64 @@ int main() {
             }
             std::printf("gpu_radix_sort: %s\n", bad == 0 ? "exact" : "MISMATCH");
             failures += bad;
+        }
+        {   // wgebra::geometry test kernels (cholesky.rs:86-149, lu.rs:129-181, qr3.rs, eig4.rs:72-131, svd3.rs:70-111): LEN = 345
+            // random matrices, out[i] = f(in[i]); every output word equal to the oracle's (both evaluate the WGSL's sequence
+            // without contraction); NaNs (non-SDP Cholesky inputs) only need to be NaN on both sides
+            const uint32_t n = 345;
+            auto check_op = [&](auto shader, auto mat_tag, auto out_tag, int op, bool symmetric, const char *name) {
+                using Mat = decltype(mat_tag);
+                using Out = decltype(out_tag);
+                constexpr int dim = sizeof(Mat) == 16 ? 2 : sizeof(Mat) == 48 ? 3 : 4;
+                auto a = uniform(SEED + 20 + dim, n * dim * dim);
+                std::vector<Mat> in(n);
+                for (uint32_t i = 0; i < n; ++i) {
+                    std::memset(&in[i], 0, sizeof(Mat));
+                    for (int c = 0; c < dim; ++c)
+                        for (int r = 0; r < dim; ++r) {
+                            const float *m = &a[(size_t)i * dim * dim];
+                            if (!symmetric) { in[i].m[c][r] = m[c * dim + r]; continue; }
+                            float acc = 0.0f;                         // m^T m (cholesky.rs:98-102)
+                            for (int k = 0; k < dim; ++k) acc += m[r * dim + k] * m[c * dim + k];
+                            in[i].m[c][r] = acc;
+                        }
+                }
+                auto tin = Tensors::vector(n, usage).build_init<Mat>(gpu.device(), in);
+                auto tout = Tensors::vector(n, usage).build<Out>(gpu.device());
+                auto enc = gpu.device().create_command_encoder();
+                {
+                    auto pass = enc.compute_pass("test");
+                    shader.dispatch(gpu.device(), pass, tin, tout);
+                }
+                gpu.queue().submit(enc.finish());
+                auto got = tout.read(gpu.device());
+                std::vector<Out> ref(n);
+                orc_geom_batch(op, dim, reinterpret_cast<const float *>(in.data()), ref.data(), n);
+                const uint32_t *g = reinterpret_cast<const uint32_t *>(got.data()), *r = reinterpret_cast<const uint32_t *>(ref.data());
+                size_t bad = 0;
+                for (size_t k = 0; k < n * sizeof(Out) / 4; ++k) {
+                    float fg, fr;
+                    std::memcpy(&fg, &g[k], 4);
+                    std::memcpy(&fr, &r[k], 4);
+                    bad += !(g[k] == r[k] || (fg != fg && fr != fr));
+                }
+                std::printf("gpu_%s%d: %s\n", name, dim, bad == 0 ? "exact" : "MISMATCH");
+                failures += bad != 0;
+            };
+            check_op(WgCholesky<2>::from_device(gpu.device()), GpuMat<2>{}, GpuMat<2>{}, 0, true, "cholesky");
+            check_op(WgCholesky<3>::from_device(gpu.device()), GpuMat<3>{}, GpuMat<3>{}, 0, true, "cholesky");
+            check_op(WgCholesky<4>::from_device(gpu.device()), GpuMat<4>{}, GpuMat<4>{}, 0, true, "cholesky");
+            check_op(WgLU<2>::from_device(gpu.device()), GpuMat<2>{}, GpuLU<2>{}, 1, true, "lu");
+            check_op(WgLU<3>::from_device(gpu.device()), GpuMat<3>{}, GpuLU<3>{}, 1, true, "lu");
+            check_op(WgLU<4>::from_device(gpu.device()), GpuMat<4>{}, GpuLU<4>{}, 1, true, "lu");
+            check_op(WgQR<2>::from_device(gpu.device()), GpuMat<2>{}, GpuQR<2>{}, 2, false, "qr");
+            check_op(WgQR<3>::from_device(gpu.device()), GpuMat<3>{}, GpuQR<3>{}, 2, false, "qr");
+            check_op(WgQR<4>::from_device(gpu.device()), GpuMat<4>{}, GpuQR<4>{}, 2, false, "qr");
+            check_op(WgSymmetricEigen<2>::from_device(gpu.device()), GpuMat<2>{}, GpuSymmetricEigen<2>{}, 3, true, "eig");
+            check_op(WgSymmetricEigen<3>::from_device(gpu.device()), GpuMat<3>{}, GpuSymmetricEigen<3>{}, 3, true, "eig");
+            check_op(WgSymmetricEigen<4>::from_device(gpu.device()), GpuMat<4>{}, GpuSymmetricEigen<4>{}, 3, true, "eig");
+            check_op(WgSvd<3>::from_device(gpu.device()), GpuMat<3>{}, GpuSvd<3>{}, 4, false, "svd");
+            check_op(WgInv<4>::from_device(gpu.device()), GpuMat<4>{}, GpuMat<4>{}, 5, false, "inv");
         }
         {   // extensions through the C++ mirror: fused Gemm + OpAssign(Add) epilogue, recorded into a graph and replayed
             const uint32_t n = 256;

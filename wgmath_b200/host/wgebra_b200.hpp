@@ -421,4 +421,43 @@ class RadixSort {  // radix_sort/mod.rs:67-223
     }
 };
 
+// ---- wgebra::geometry (factorization libraries) -----------------------------
+// Element types in WGSL storage layout: what the reference's tests upload / read back (Matrix2 / Matrix4x3 / Matrix4,
+// cholesky.rs:151-153; GpuLU* lu.rs:25-56; GpuQR* qr3.rs:15-20; GpuSymmetricEigen* eig3.rs:16-21; GpuSvd2 svd2.rs:12-19;
+// GpuSvd3 svd3.rs:15-22).  m[c][r] = column c, row r; 3x3 matrices have 4-float columns.
+template <int D> struct GpuMat { float m[D][D == 2 ? 2 : 4]; };
+template <int D> struct GpuLU;
+template <> struct GpuLU<2> { GpuMat<2> lu; uint32_t ia[2], ib[2], len, _pad; };
+template <> struct GpuLU<3> { GpuMat<3> lu; uint32_t ia[4], ib[3], len; };
+template <> struct GpuLU<4> { GpuMat<4> lu; uint32_t ia[4], ib[4], len, _pad[3]; };
+template <int D> struct GpuQR { GpuMat<D> q, r; };
+template <int D> struct GpuSymmetricEigen { GpuMat<D> eigenvectors; float eigenvalues[D == 2 ? 2 : 4]; };
+template <int D> struct GpuSvd { GpuMat<D> u; float s[D == 2 ? 2 : 4]; GpuMat<D> vt; };
+static_assert(sizeof(GpuMat<2>) == 16 && sizeof(GpuMat<3>) == 48 && sizeof(GpuMat<4>) == 64, "WGSL matrix layout");
+static_assert(sizeof(GpuLU<2>) == 40 && sizeof(GpuLU<3>) == 80 && sizeof(GpuLU<4>) == 112, "lu.wgsl:12-34 layout");
+static_assert(sizeof(GpuQR<2>) == 32 && sizeof(GpuQR<3>) == 96 && sizeof(GpuQR<4>) == 128, "qr2.wgsl:7-12 layout");
+static_assert(sizeof(GpuSymmetricEigen<2>) == 24 && sizeof(GpuSymmetricEigen<3>) == 64 && sizeof(GpuSymmetricEigen<4>) == 80, "eig2.wgsl:7-12");
+static_assert(sizeof(GpuSvd<2>) == 40 && sizeof(GpuSvd<3>) == 112, "svd2.wgsl:5-9 / svd3.wgsl:12-16 layout");
+
+// One class per reference `Shader` struct.  The reference builds exactly one kind of kernel from each — out[i] = f(in[i])
+// (cholesky.rs:53-63 ...) — and that is `dispatch`: KernelDispatch::new(device, &mut pass, &pipeline).bind0([in, out]).dispatch(len).
+template <wgb_geom_op OP, int D, typename Out> class GeometryShader {
+  public:
+    static GeometryShader from_device(const Device &) { return GeometryShader(); }
+    void dispatch(const Device &, ComputePass &pass, const GpuVector<GpuMat<D>> &inputs, const GpuVector<Out> &outputs) const {
+        dispatch(pass, inputs.as_view(), outputs.as_view());
+    }
+    void dispatch(ComputePass &pass, GpuVectorView<GpuMat<D>> inputs, GpuVectorView<Out> outputs) const {
+        static_assert(OP != WGB_GEOM_SVD || D < 4, "the reference has no 4x4 SVD");
+        check(wgb_geometry_batch(pass.raw(), OP, D, inputs.buffer()->raw, inputs.shape().offset, outputs.buffer()->raw,
+                                 outputs.shape().offset, inputs.len()));
+    }
+};
+template <int D> using WgCholesky = GeometryShader<WGB_GEOM_CHOLESKY, D, GpuMat<D>>;        // cholesky.rs:21-38 WgCholesky2/3/4
+template <int D> using WgLU = GeometryShader<WGB_GEOM_LU, D, GpuLU<D>>;                     // lu.rs:65-79
+template <int D> using WgQR = GeometryShader<WGB_GEOM_QR, D, GpuQR<D>>;                     // qr2.rs:22-27 ...
+template <int D> using WgSymmetricEigen = GeometryShader<WGB_GEOM_SYMMETRIC_EIGEN, D, GpuSymmetricEigen<D>>;   // eig2.rs:23-27 ...
+template <int D> using WgSvd = GeometryShader<WGB_GEOM_SVD, D, GpuSvd<D>>;                  // svd2.rs:21-23, svd3.rs:24-28
+template <int D> using WgInv = GeometryShader<WGB_GEOM_INV, D, GpuMat<D>>;                  // inv.rs:3-8 (inv2 / inv3 / inv4)
+
 }  // namespace wgb
