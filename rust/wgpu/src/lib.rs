@@ -53,6 +53,10 @@ pub mod sys {
                              b: *const wgb_buffer, b_shape: *const wgb_view_shape) -> c_int;
         pub fn wgb_reduce(pass: *mut wgb_pass, op: c_int, value: *const wgb_buffer, value_shape: *const wgb_view_shape,
                           result: *mut wgb_buffer) -> c_int;
+        pub fn wgb_geometry_in_bytes(dim: c_int) -> u32;
+        pub fn wgb_geometry_out_bytes(op: c_int, dim: c_int) -> u32;
+        pub fn wgb_geometry_batch(pass: *mut wgb_pass, op: c_int, dim: c_int, input: *const wgb_buffer, in_first: u64,
+                                  output: *mut wgb_buffer, out_first: u64, n: u64) -> c_int;
         pub fn wgb_event_create(ctx: *mut wgb_ctx, out: *mut *mut wgb_event) -> c_int;
         pub fn wgb_event_destroy(ev: *mut wgb_event) -> c_int;
         pub fn wgb_event_elapsed_ms(begin: *mut wgb_event, end: *mut wgb_event, ms: *mut f32) -> c_int;
