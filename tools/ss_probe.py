@@ -26,13 +26,18 @@ ns = w.TensorBuilder.scalar(ST).build_init(dev, np.array([n], np.uint32), "u32")
 ps, rs = w.WgPrefixSum.from_device(dev), w.RadixSort.from_device(dev)
 
 
+NCU = os.environ.get("SS_NCU") == "1"   # one dispatch per case, so an ncu capture holds every kernel once
+
+
 def timed(fn, steps=10):
+    if NCU:
+        steps = 1
     e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
     check(L.wgb_event_create(dev._h, ctypes.byref(e0)))
     check(L.wgb_event_create(dev._h, ctypes.byref(e1)))
     enc = dev.create_command_encoder()
     with enc.compute_pass("t", None) as p:
-        for _ in range(3):
+        for _ in range(0 if NCU else 3):
             fn(p)
         check(L.wgb_event_record(e0, p._h))
         for _ in range(steps):
