@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const uint32_t 
 // The kernel is instruction-bound, not memory-bound (ncu, profiles/README.md: ~140 warp instructions per pair at 50 % issue
 // utilisation in the first version), hence: full tiles take a predicate-free instantiation, 16 items per thread keep four
 // CTAs resident per SM, and the digit-bit ballots are batched four items at a time so they overlap.
-template <bool FULL>
+template <bool FULL, bool MATCH>
 __device__ __forceinline__ void radix_scatter_tile(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                                                    uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, uint32_t tile_base,
                                                    uint32_t tile_n, uint32_t shift, uint32_t mask, uint32_t goff,
@@ -271,16 +271,22 @@ __device__ __forceinline__ void radix_scatter_tile(const uint32_t *__restrict__ 
         for (int q = 0; q < 4; ++q) {
             const uint32_t d = (key[i0 + q] >> shift) & mask;
             uint32_t pm = 0xFFFFFFFFu;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const bool bit = (d >> b) & 1u;
-                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
-                pm &= bit ? bal : ~bal;
-            }
-            if (!FULL) {
-                const bool valid = wbase + (i0 + q) * 32 < tile_n;
-                pm &= __ballot_sync(0xFFFFFFFFu, valid);
+            if (MATCH) {   // one match.any instead of eight ballots (WGB_RS_MATCH=1; measured, see profiles/README.md)
+                const bool valid = FULL || wbase + (i0 + q) * 32 < tile_n;
+                pm = __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu);
                 if (!valid) pm = 0u;
+            } else {
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const bool bit = (d >> b) & 1u;
+                    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, bit);
+                    pm &= bit ? bal : ~bal;
+                }
+                if (!FULL) {
+                    const bool valid = wbase + (i0 + q) * 32 < tile_n;
+                    pm &= __ballot_sync(0xFFFFFFFFu, valid);
+                    if (!valid) pm = 0u;
+                }
             }
             peers[q] = pm;
         }
@@ -357,6 +363,7 @@ __device__ __forceinline__ void radix_scatter_tile(const uint32_t *__restrict__ 
     }
 }
 
+template <bool MATCH>
 __global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
                                                                       const uint32_t *__restrict__ vals_in,
                                                                       uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
@@ -379,10 +386,10 @@ __global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const uint
     __syncthreads();
     const uint32_t tile_n = min((uint32_t)kRsTile, n - tile_base);
     if (tile_n == (uint32_t)kRsTile)
-        radix_scatter_tile<true>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
+        radix_scatter_tile<true, MATCH>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
                                  s_tile_start, s_gbase, s_scan);
     else
-        radix_scatter_tile<false>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
+        radix_scatter_tile<false, MATCH>(keys_in, vals_in, keys_out, vals_out, tile_base, tile_n, shift, mask, goff, s_warp_hist, s_sorted,
                                   s_tile_start, s_gbase, s_scan);
 }
 
@@ -457,7 +464,9 @@ wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_
         WGB_CUDA(cudaGetLastError());
         count_launch(ctx);
         WGB_TRY(scan_in_place(p, counts, n_counts, scan_ws));
-        radix_scatter_kernel<<<tiles, kRsThreads, 0, p->stream>>>(cur_k, cur_v, dk, dv, n_dev, len, shift, mask, tiles, counts);
+        static const bool use_match = [] { const char *e = getenv("WGB_RS_MATCH"); return e && atoi(e) != 0; }();
+        if (use_match) radix_scatter_kernel<true><<<tiles, kRsThreads, 0, p->stream>>>(cur_k, cur_v, dk, dv, n_dev, len, shift, mask, tiles, counts);
+        else radix_scatter_kernel<false><<<tiles, kRsThreads, 0, p->stream>>>(cur_k, cur_v, dk, dv, n_dev, len, shift, mask, tiles, counts);
         WGB_CUDA(cudaGetLastError());
         count_launch(ctx);
         cur_k = dk;
