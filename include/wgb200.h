@@ -168,6 +168,9 @@ const char *wgb_last_error_string(void);
 /* ------------------------------------------------------------------ context ---------- */
 /* gpu.rs:15-58 GpuInstance::new: pick the device, create its in-order queue (stream). */
 wgb_status wgb_ctx_create(int device_ordinal, wgb_ctx **out);
+/* Drains the queue and drops the caller's reference.  Like wgpu's handles (every Buffer keeps its Device alive), buffers,
+ * events, passes, graphs and peer groups created from the context each hold a reference: they stay valid, and may be destroyed,
+ * after wgb_ctx_destroy; the context's own resources are released with the last of them. */
 wgb_status wgb_ctx_destroy(wgb_ctx *ctx);
 /* device.poll(PollType::wait()) — tensor.rs:304-312: block until all submitted work is done. */
 wgb_status wgb_ctx_sync(wgb_ctx *ctx);
@@ -346,6 +349,15 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out,
 wgb_status wgb_gemv_ord(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *out_shape,
                         const wgb_buffer *m, const wgb_view_shape *m_shape, wgb_ordering m_ordering, const wgb_buffer *v,
                         const wgb_view_shape *v_shape);
+
+/* GEMV with the caller's next element-wise step fused into the store: out = (m * v) (op) operand, i.e.
+ * Gemv::dispatch followed by OpAssign::dispatch(out, operand) (gemv.rs:64-137, op_assign.rs:71-94) as one launch.  `operand` is
+ * an f32 view with out's rows and at least out's columns / matrices; it may be the output view itself (out = m * v + out, the
+ * residual update), any other overlap is WGB_ERR_INVALID.  op < 0: plain wgb_gemv_ord (operand ignored); WGB_OP_COPY is rejected
+ * (it would discard the product).  A row mismatch is the reference's "Op-assign: dimension mismatch." panic. */
+wgb_status wgb_gemv_op(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *out_shape,
+                       const wgb_buffer *m, const wgb_view_shape *m_shape, wgb_ordering m_ordering, const wgb_buffer *v,
+                       const wgb_view_shape *v_shape, int op, const wgb_buffer *operand, const wgb_view_shape *operand_shape);
 
 /* op_assign.rs:71-94.  a[i] = a[i] (op) b[i]; only size[0] and offset of the shapes are used
  * (shape.wgsl:36-38 iv()). */

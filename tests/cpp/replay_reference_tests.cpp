@@ -285,6 +285,30 @@ int main() {
             std::printf("fused gemm+add via graph replay: rel err %.3e\n", err);
             failures += !(err < 1e-5);
         }
+        {   // fused Gemv + OpAssign(Add) with operand == out: the residual update out = m * v + out
+            const uint32_t n = 1024;
+            auto mc = uniform(SEED + 1, n, n), vc = uniform(SEED + 3, n), oc = uniform(SEED + 4, n);
+            auto gemv = Gemv::from_device(gpu.device());
+            auto tm = Tensors::matrix(n, n, usage).build_init<float>(gpu.device(), mc);
+            auto tv = Tensors::vector(n, usage).build_init<float>(gpu.device(), vc);
+            auto out = Tensors::vector(n, usage).build_init<float>(gpu.device(), oc);
+            auto enc = gpu.device().create_command_encoder();
+            {
+                auto pass = enc.compute_pass("fused gemv");
+                gemv.dispatch_op<float>(gpu.device(), shapes, pass, out.as_embedded_view<3>(), tm.as_embedded_view<3>(), tv.as_embedded_view<3>(),
+                                        OpAssignVariant::Add, out.as_embedded_view<3>());
+            }
+            gpu.queue().submit(enc.finish());
+            auto got = out.read(gpu.device());
+            std::vector<float> ref(n, 0.f);
+            orc_shape sm = oshape(n, n), sv = oshape(n);
+            int ran = 0;
+            orc_gemv(0, ref.data(), &sv, mc.data(), &sm, vc.data(), &sv, &ran);
+            orc_op_assign(0, ref.data(), &sv, oc.data(), &sv);
+            const double err = rel_err(got, ref);
+            std::printf("fused gemv+add (residual update): rel err %.3e\n", err);
+            failures += !(err < 1e-5);
+        }
         {   // RowMajor views (tensor.rs:19-39, shape.wgsl:49-57): row-major out and m2, column-major m1, 3xTF32 path
             const uint32_t M = 192, N = 320, K = 256;
             auto a = uniform(SEED + 1, M, K), b = uniform(SEED + 2, N, K);   // b holds the K x N matrix row by row (N contiguous)

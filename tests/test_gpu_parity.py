@@ -598,6 +598,64 @@ def test_gemm_fused_accumulate_in_place(gpu, shapes):
         run_pass(gpu, lambda p: gemm.dispatch_op(dev, shapes, p, out, ta, tb, w.OpAssignVariant.Copy, out))
 
 
+@pytest.mark.parametrize("op", [w.OpAssignVariant.Add, w.OpAssignVariant.Sub, w.OpAssignVariant.Mul, w.OpAssignVariant.Div])
+@pytest.mark.parametrize("variant,M,K,C", [(w.GemvVariant.Gemv, 1024, 1024, 1), (w.GemvVariant.GemvTr, 1024, 1024, 1),
+                                           (w.GemvVariant.Gemv, 130, 4100, 3), (w.GemvVariant.GemvTr, 77, 9000, 2),
+                                           (w.GemvVariant.Gemv, 40000, 36, 1)])
+def test_gemv_fused_op_assign_equals_the_two_dispatch_chain(gpu, shapes, op, variant, M, K, C):
+    """wgb_gemv_op == Gemv::dispatch then OpAssign::dispatch(out, operand): bit-identical to the unfused GPU chain (every
+    reduction path: single CTA per tile, split reduction with last-CTA fold, ragged scalar tiles, multi-column), and within the
+    f32 tolerance of the oracle's gemv + op_assign."""
+    dev = gpu.device()
+    tr = variant == w.GemvVariant.GemvTr
+    mr, mc = (K, M) if tr else (M, K)                       # m is [M x K], or [K x M] for the transposed product
+    Mm, V = O.uniform(SEED_A, mr, mc), O.uniform(SEED_V, K, C)
+    E = O.uniform(SEED_OUT, M, C) + np.float32(0.5)
+    tm, tv, te = upload(gpu, Mm, (mr, mc)), upload(gpu, V, (K, C)), upload(gpu, E, (M, C))
+    fused = upload(gpu, np.full(M * C, -3.0, np.float32), (M, C))
+    chain = upload(gpu, np.full(M * C, -3.0, np.float32), (M, C))
+    gemv, opk = w.Gemv.from_device(dev), w.OpAssign.new(dev, op)
+
+    def go(p):
+        gemv.dispatch_op(dev, shapes, p, fused, tm, tv, op, te, variant)
+        gemv.dispatch_generic(dev, shapes, p, chain, tm, tv, variant)
+        opk.dispatch(dev, shapes, p, chain.reshape((M * C,)), te.reshape((M * C,)))
+    run_pass(gpu, go)
+    np.testing.assert_array_equal(fused.read(), chain.read())
+    a64 = cm(Mm, mr, mc).astype(np.float64)
+    prod = ((a64.T if tr else a64) @ cm(V, K, C).astype(np.float64)).T.reshape(-1).astype(np.float32)
+    ref = prod.copy()
+    assert O.op_assign(int(op), ref, O.shape(M * C), E, O.shape(M * C)) == O.ORC_OK
+    # (m*v) - e cancels for some elements: compare against the magnitude of the operands, like the reference's abs-eps tests
+    scale = np.maximum(np.abs(ref.astype(np.float64)), np.abs(prod.astype(np.float64)))
+    assert float(np.max(np.abs(fused.read().astype(np.float64) - ref) / scale)) < F32_TOL
+
+
+def test_gemv_fused_residual_update_and_errors(gpu, shapes):
+    """operand == out: out = m * v + out (the residual update), applied twice; Copy, row mismatch and partial overlap are rejected."""
+    dev = gpu.device()
+    M, K = 2048, 512
+    Mm, V = O.uniform(SEED_A, M, K), O.uniform(SEED_V, K)
+    tm, tv = upload(gpu, Mm, (M, K)), upload(gpu, V, (K,))
+    out = upload(gpu, np.ones(M, np.float32), (M,))
+    gemv = w.Gemv.from_device(dev)
+    run_pass(gpu, lambda p: [gemv.dispatch_op(dev, shapes, p, out, tm, tv, w.OpAssignVariant.Add, out) for _ in range(2)])
+    ref = 1.0 + 2.0 * (cm(Mm, M, K).astype(np.float64) @ V.astype(np.float64))
+    assert rel_err(out.read(), ref) < F32_TOL
+    with pytest.raises(w.WgbError):
+        run_pass(gpu, lambda p: gemv.dispatch_op(dev, shapes, p, out, tm, tv, w.OpAssignVariant.Copy, out))
+    big = upload(gpu, np.zeros(M + 64, np.float32), (M + 64,))
+    with pytest.raises(w.WgbError):                                     # overlapping but not the same view
+        run_pass(gpu, lambda p: gemv.dispatch_op(dev, shapes, p, big.rows(0, M), tm, tv, w.OpAssignVariant.Add, big.rows(64, M)))
+    with pytest.raises(w.DimensionMismatch):                            # op_assign.rs:82-86
+        run_pass(gpu, lambda p: gemv.dispatch_op(dev, shapes, p, out, tm, tv, w.OpAssignVariant.Add, big))
+    # K == 0: the product is the zero vector (gemv.wgsl:74,88), so out = 0 + operand
+    e = upload(gpu, O.uniform(SEED_OUT, M), (M,))
+    empty_m, empty_v = upload(gpu, np.zeros(4, np.float32), (4,)).reshape((M, 0)), upload(gpu, np.zeros(4, np.float32), (4,)).reshape((0,))
+    run_pass(gpu, lambda p: gemv.dispatch_op(dev, shapes, p, out, empty_m, empty_v, w.OpAssignVariant.Add, e))
+    np.testing.assert_array_equal(out.read(), e.read())
+
+
 def test_graph_capture_replays_a_dispatch_chain(gpu, shapes):
     """wgb_graph_*: record gemm -> op_assign -> reduce once, replay it, same result as the eager sequence."""
     dev = gpu.device()
@@ -643,3 +701,26 @@ def test_timestamps_and_launch_counter(gpu, shapes):
     ms = ts.wait_for_results_ms(dev, gpu.queue())
     assert len(ms) == 2 and ms[1] > 0.0
     assert dev.launch_count() - n0 == 4
+
+
+def test_context_outlives_its_handle_while_children_exist():
+    """wgpu handles are reference counted (a Buffer keeps its Device alive); so are these: destroying the context first leaves
+    its buffers / events usable and destroyable, and host bindings whose finalisers run in arbitrary order cannot crash."""
+    import subprocess
+    import sys
+    L = w.lib()
+    ctx, buf, ev = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    assert L.wgb_ctx_create(0, ctypes.byref(ctx)) == 0
+    data = np.arange(1024, dtype=np.float32)
+    assert L.wgb_buffer_create_init(ctx, data.ctypes.data_as(ctypes.c_void_p), data.nbytes, STORAGE, ctypes.byref(buf)) == 0
+    assert L.wgb_event_create(ctx, ctypes.byref(ev)) == 0
+    assert L.wgb_ctx_destroy(ctx) == 0                       # the caller's reference only
+    back = np.zeros_like(data)
+    assert L.wgb_buffer_read(ctx, buf, 0, back.ctypes.data_as(ctypes.c_void_p), back.nbytes) == 0
+    np.testing.assert_array_equal(back, data)
+    assert L.wgb_event_destroy(ev) == 0
+    assert L.wgb_buffer_destroy(buf) == 0                    # last child: the context goes with it
+    # interpreter exit with module-level tensors caught in a reference cycle (finalisers in arbitrary order)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "exit_probe.py"), "all"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "done all" in r.stdout, (r.returncode, r.stdout, r.stderr)

@@ -128,8 +128,16 @@ wgb_status wgb_ctx_create(int device_ordinal, wgb_ctx **out) {
     return WGB_OK;
 }
 
-wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
-    if (!ctx) return WGB_OK;
+}  // extern "C"
+
+static void ctx_teardown(wgb_ctx *ctx);
+namespace wgb {
+void ctx_release(wgb_ctx *ctx) {
+    if (ctx->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) ctx_teardown(ctx);
+}
+}  // namespace wgb
+
+static void ctx_teardown(wgb_ctx *ctx) {
     DeviceGuard g(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->comm_stream);
@@ -150,6 +158,18 @@ wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
         if (e) cudaEventDestroy(e);
     for (auto e : ctx->host_gemm.evs) cudaEventDestroy(e);
     delete ctx;
+}
+
+extern "C" {
+
+wgb_status wgb_ctx_destroy(wgb_ctx *ctx) {
+    if (!ctx) return WGB_OK;
+    {   // queued work is drained now; the resources go with the last child object (common.cuh: context lifetime)
+        DeviceGuard g(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->comm_stream);
+    }
+    wgb::ctx_release(ctx);
     return WGB_OK;
 }
 
@@ -221,11 +241,13 @@ wgb_status wgb_pass_begin(wgb_ctx *ctx, const char *label, wgb_event *begin_ts, 
     p->ctx = ctx;
     p->stream = ctx->stream;
     p->end_ts = end_ts;
+    ctx_retain(ctx);
     if (begin_ts) {
         DeviceGuard g(ctx->device);
         cudaError_t e = cudaEventRecord(begin_ts->ev, p->stream);
         if (e != cudaSuccess) {
             delete p;
+            ctx_release(ctx);
             WGB_FAIL(WGB_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
         }
     }
@@ -243,7 +265,9 @@ wgb_status wgb_pass_end(wgb_pass *pass) {
             st = WGB_ERR_CUDA;
         }
     }
+    wgb_ctx *ctx = pass->ctx;
     delete pass;
+    ctx_release(ctx);
     return st;
 }
 
@@ -307,6 +331,7 @@ wgb_status wgb_graph_capture_end(wgb_ctx *ctx, wgb_graph **out) {
         delete gr;
         WGB_FAIL(WGB_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     }
+    ctx_retain(ctx);
     *out = gr;
     return WGB_OK;
 }
@@ -325,7 +350,9 @@ wgb_status wgb_graph_destroy(wgb_graph *graph) {
     cudaStreamSynchronize(graph->ctx->stream);
     if (graph->exec) cudaGraphExecDestroy(graph->exec);
     if (graph->graph) cudaGraphDestroy(graph->graph);
+    wgb_ctx *ctx = graph->ctx;
     delete graph;
+    ctx_release(ctx);
     return WGB_OK;
 }
 
@@ -346,6 +373,7 @@ wgb_status wgb_buffer_create(wgb_ctx *ctx, size_t bytes, uint32_t usage, wgb_buf
             WGB_FAIL(WGB_ERR_OOM, "allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
         }
     }
+    ctx_retain(ctx);
     *out = b;
     return WGB_OK;
 }
@@ -381,6 +409,7 @@ wgb_status wgb_buffer_wrap(wgb_ctx *ctx, void *device_ptr, size_t bytes, wgb_buf
     b->bytes = bytes;
     b->owned = false;
     b->usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    ctx_retain(ctx);
     *out = b;
     return WGB_OK;
 }
@@ -394,7 +423,9 @@ wgb_status wgb_buffer_destroy(wgb_buffer *buf) {
         if (buf->host_pinned) cudaFreeHost(buf->ptr);
         else cudaFree(buf->ptr);
     }
+    wgb_ctx *ctx = buf->ctx;
     delete buf;
+    ctx_release(ctx);
     return WGB_OK;
 }
 
@@ -475,14 +506,20 @@ wgb_status wgb_event_create(wgb_ctx *ctx, wgb_event **out) {
         delete ev;
         WGB_FAIL(WGB_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
     }
+    ctx_retain(ctx);
     *out = ev;
     return WGB_OK;
 }
 
 wgb_status wgb_event_destroy(wgb_event *ev) {
     if (!ev) return WGB_OK;
-    cudaEventDestroy(ev->ev);
+    {
+        DeviceGuard g(ev->ctx->device);
+        cudaEventDestroy(ev->ev);
+    }
+    wgb_ctx *ctx = ev->ctx;
     delete ev;
+    ctx_release(ctx);
     return WGB_OK;
 }
 
@@ -621,9 +658,21 @@ wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, c
 
 wgb_status wgb_gemv_ord(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *so, const wgb_buffer *m,
                         const wgb_view_shape *sm, wgb_ordering m_ord, const wgb_buffer *v, const wgb_view_shape *sv) {
+    return wgb_gemv_op(pass, variant, out, so, m, sm, m_ord, v, sv, -1, nullptr, nullptr);
+}
+
+wgb_status wgb_gemv_op(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out, const wgb_view_shape *so, const wgb_buffer *m,
+                       const wgb_view_shape *sm, wgb_ordering m_ord, const wgb_buffer *v, const wgb_view_shape *sv, int op,
+                       const wgb_buffer *e, const wgb_view_shape *se) {
     if (!pass || !out || !so || !m || !sm || !v || !sv) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: null argument");
     if ((int)variant < 0 || (int)variant > WGB_GEMV_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: unknown variant %d", (int)variant);
     if (bad_ordering(m_ord)) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv: unknown ordering %d", (int)m_ord);
+    if (op >= 0) {
+        if (!e || !se) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_op: null operand");
+        if (op >= WGB_OP_COPY) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_op: op %d (Copy would discard the product)", op);
+        if (se->size[0] != so->size[0] || se->size[1] < so->size[1] || se->size[2] < so->size[2])   // op_assign.rs:82-86
+            WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Op-assign: dimension mismatch. (%u vs %u)", so->size[0], se->size[0]);
+    }
     bool tr = variant == WGB_GEMV_TR || variant == WGB_GEMV_TR_FAST;
     const uint32_t m_rows = tr ? sm->size[1] : sm->size[0];
     const uint32_t m_cols = tr ? sm->size[0] : sm->size[1];
@@ -654,8 +703,24 @@ wgb_status wgb_gemv_ord(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *ou
     WGB_TRY(check_view(out, *so, 4, "gemv out"));
     WGB_TRY(check_view(m, sm_used, 4, "gemv m"));
     WGB_TRY(check_view(v, sv_used, 4, "gemv v"));
+    wgb_view_shape se_used{};
+    if (op >= 0) {
+        if (e->bytes == 0) return WGB_OK;
+        se_used = *se;
+        se_used.size[1] = so->size[1];
+        se_used.size[2] = so->size[2];
+        WGB_TRY(check_view(e, se_used, 4, "gemv operand"));
+        // the operand may BE the output view (out = m*v + out: each element is read, then written, by one thread); any other
+        // overlap would race
+        const char *ob = (const char *)out->ptr + 4ull * so->offset, *eb = (const char *)e->ptr + 4ull * se_used.offset;
+        const bool same = ob == eb && so->stride == se_used.stride && (so->size[2] == 1 || so->stride_mat == se_used.stride_mat);
+        const uint64_t on = 4 * (view_extent(*so) - so->offset), en = 4 * (view_extent(se_used) - se_used.offset);
+        if (!same && ob < eb + en && eb < ob + on)
+            WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_op: the operand overlaps the output without being the same view");
+    }
     DeviceGuard g(pass->ctx->device);
-    return launch_gemv(pass, tr, (float *)out->ptr, *so, (const float *)m->ptr, sm_used, (const float *)v->ptr, sv_used);
+    return launch_gemv(pass, tr, (float *)out->ptr, *so, (const float *)m->ptr, sm_used, (const float *)v->ptr, sv_used, op,
+                       op >= 0 ? (const float *)e->ptr : nullptr, op >= 0 ? &se_used : nullptr);
 }
 
 static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,

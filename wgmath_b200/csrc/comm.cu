@@ -293,6 +293,7 @@ wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gat
     pg->view.bytes = gathered_bytes;
     pg->view.owned = false;
     pg->view.usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    wgb::ctx_retain(ctx);
     *out = pg;
     return WGB_OK;
 }
@@ -335,7 +336,9 @@ wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
     for (int q = 0; q < pg->nranks; ++q)
         if (q != pg->rank && pg->peer[q]) cudaIpcCloseMemHandle(pg->peer[q]);
     if (pg->local) cudaFree(pg->local);
+    wgb_ctx *ctx = pg->ctx;
     delete pg;
+    wgb::ctx_release(ctx);
     return WGB_OK;
 }
 

@@ -79,6 +79,7 @@ struct wgb_ctx {
     cudaStream_t h2d_stream = nullptr;   // upload stream of wgb_gemm_host (created on first use)
     cudaDeviceProp prop{};
     std::atomic<uint64_t> launches{0};
+    std::atomic<int> refs{1};            // the caller's handle + one per live buffer / event / pass / graph / peer group (abi.cu)
     wgb::Scratch scratch;
     wgb::Workspace ws[6];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort
     wgb::CommState *comm = nullptr;
@@ -110,6 +111,13 @@ struct wgb_event {
 };
 
 namespace wgb {
+
+// Context lifetime: wgpu handles are reference counted (Arc<Device> inside every Buffer), so dropping the device before the
+// buffers is legal in the reference.  Same here: wgb_ctx_destroy drops the caller's reference, every child object holds one, and
+// the context is torn down when the last of them goes (host bindings whose finalisers run in arbitrary order — Python's cycle
+// collector at interpreter exit — rely on this).
+inline void ctx_retain(wgb_ctx *ctx) { ctx->refs.fetch_add(1, std::memory_order_relaxed); }
+void ctx_release(wgb_ctx *ctx);
 
 inline void count_launch(wgb_ctx *ctx, uint64_t n = 1) { ctx->launches.fetch_add(n, std::memory_order_relaxed); }
 
@@ -154,7 +162,8 @@ wgb_status launch_prefix_sum(wgb_pass *p, uint32_t *data, uint64_t n);
 wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_t *vals_in, uint32_t len, const uint32_t *n_dev,
                              uint32_t sorting_bits, uint32_t *keys_out, uint32_t *vals_out);
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
-                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv);
+                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv, int op = -1,
+                       const float *operand = nullptr, const wgb_view_shape *operand_shape = nullptr);
 
 // Fused all-gather of the GEMM output over peer (NVLink-mapped) memory: the epilogue stores every output element
 // into the gathered buffer of every rank, then the last CTA publishes a completion flag to each peer.

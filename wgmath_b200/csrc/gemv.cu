@@ -44,7 +44,27 @@ struct GemvArgs {
     uint32_t z_base;
     float *partials;
     unsigned int *counters;
+    int op;             // < 0: out = result (gemv.wgsl:88); else out = result (op) e — the fused OpAssign step (op_assign.wgsl:14-47)
+    const float *e;     // operand of the fused step, indexed like out with its own strides
+    uint64_t lde, se;
 };
+
+// The single store of an output element (t = matrix, c = output column, r = row).  With a fused op this is OpAssign's
+// `a[i] = a[i] op b[i]` (op_assign.wgsl:41-47) applied to a = the GEMV result the unfused chain would have written to `out`
+// first and b = the operand: same operands, same f32 operation, one HBM round trip of `out` less.
+__device__ __forceinline__ void store_out(const GemvArgs &a, uint64_t t, uint64_t c, uint64_t r, float s) {
+    if (a.op >= 0) {
+        const float b = a.e[t * a.se + c * a.lde + r];
+        switch (a.op) {
+        case WGB_OP_ADD: s = s + b; break;
+        case WGB_OP_SUB: s = s - b; break;
+        case WGB_OP_MUL: s = s * b; break;
+        case WGB_OP_DIV: s = s / b; break;
+        default: break;
+        }
+    }
+    a.out[t * a.so + c * a.ldo + r] = s;
+}
 
 __device__ __forceinline__ void fma4(float (&acc)[4], const float4 &x, float s) {
     acc[0] = fmaf(x.x, s, acc[0]);
@@ -132,7 +152,7 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(GemvArgs a) {
 #pragma unroll
         for (int ww = 0; ww < kWarps; ++ww) s += red[ww][c][rl];
         if (!split) {
-            if (row0 + rl < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + row0 + rl] = s;
+            if (row0 + rl < a.M && c < nv) store_out(a, t, c0 + c, row0 + rl, s);
         } else {
             a.partials[((tile_id * a.nsplit + blockIdx.y) * NV + c) * kTileRows + rl] = s;
         }
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(GemvArgs a) {
         const uint32_t c = idx / kTileRows, rl = idx % kTileRows;
         float s = 0.f;
         for (uint32_t y = 0; y < a.nsplit; ++y) s += __ldcg(a.partials + ((tile_id * a.nsplit + y) * NV + c) * kTileRows + rl);
-        if (row0 + rl < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + row0 + rl] = s;
+        if (row0 + rl < a.M && c < nv) store_out(a, t, c0 + c, row0 + rl, s);
     }
     if (threadIdx.x == 0) a.counters[tile_id] = 0u;
 }
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
         if (valid && lane == 0)
 #pragma unroll
             for (int c = 0; c < NV; ++c)
-                if (c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + j] = acc[c];
+                if (c < nv) store_out(a, t, c0 + c, j, acc[c]);
         return;
     }
     const uint64_t tile_id = (uint64_t)z * gridDim.x + blockIdx.x;
@@ -261,7 +281,7 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
         const uint32_t jj = blockIdx.x * kWarps + ww;
         float s = 0.f;
         for (uint32_t y = 0; y < a.nsplit; ++y) s += __ldcg(a.partials + ((tile_id * a.nsplit + y) * kWarps + ww) * NV + c);
-        if (jj < a.M && c < nv) a.out[(uint64_t)t * a.so + (uint64_t)(c0 + c) * a.ldo + jj] = s;
+        if (jj < a.M && c < nv) store_out(a, t, c0 + c, jj, s);
     }
     if (threadIdx.x == 0) a.counters[tile_id] = 0u;
 }
@@ -285,10 +305,25 @@ static void launch_sel(bool vec, int nv, const GemvArgs &a, dim3 grid, cudaStrea
     }
 }
 
+__global__ void gemv_empty_k_kernel(GemvArgs a, uint32_t nmats) {   // K == 0 with a fused op: out = 0 (op) operand
+    const uint64_t total = (uint64_t)a.M * a.C * nmats;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i % a.M, c = (i / a.M) % a.C, t = i / ((uint64_t)a.M * a.C);
+        store_out(a, t, c, r, 0.0f);
+    }
+}
+
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
-                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv) {
+                       const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv, int op, const float *operand,
+                       const wgb_view_shape *se) {
     wgb_ctx *ctx = p->ctx;
     GemvArgs a{};
+    a.op = op;
+    if (op >= 0) {
+        a.e = operand + se->offset;
+        a.lde = se->stride;
+        a.se = se->stride_mat;
+    }
     a.m = m + sm.offset;
     a.v = v + sv.offset;
     a.out = out + so.offset;
@@ -305,6 +340,12 @@ wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &s
 
     if (a.K == 0) {
         // empty reduction: the reference's loops do not execute and it stores zeros (gemv.wgsl:74,88)
+        if (op >= 0) {
+            gemv_empty_k_kernel<<<ctx->prop.multiProcessorCount, 256, 0, p->stream>>>(a, nmats);
+            WGB_CUDA(cudaGetLastError());
+            count_launch(ctx);
+            return WGB_OK;
+        }
         for (uint32_t t = 0; t < nmats; ++t)
             for (uint32_t c = 0; c < a.C; ++c)
                 WGB_CUDA(cudaMemsetAsync(a.out + (uint64_t)t * a.so + (uint64_t)c * a.ldo, 0, (size_t)a.M * 4, p->stream));

@@ -349,6 +349,13 @@ class Gemv {  // gemv.rs:9-137
         const ViewShape so = shapes.get(d, out.shape()), sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape());
         check(wgb_gemv_ord(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, m.ordering(), v.buffer()->raw, &sv));
     }
+    // out = (m * v) (op) operand: Gemv::dispatch + OpAssign::dispatch(out, operand) as one launch (wgb_gemv_op); operand may be out
+    template <typename T> void dispatch_op(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuCubeView<T> out, GpuCubeView<T> m,
+                                           GpuCubeView<T> v, OpAssignVariant op, GpuCubeView<T> operand, GemvVariant variant = GemvVariant::Gemv) const {
+        const ViewShape so = shapes.get(d, out.shape()), sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape()), se = shapes.get(d, operand.shape());
+        check(wgb_gemv_op(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, m.ordering(), v.buffer()->raw, &sv,
+                          (int)op, operand.buffer()->raw, &se));
+    }
 };
 
 class OpAssign {  // op_assign.rs:43-94

@@ -163,6 +163,15 @@ class Gemv:
         check(lib().wgb_gemv(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m.buffer()._h, ctypes.byref(sm),
                              v.buffer()._h, ctypes.byref(sv)))
 
+    def dispatch_op(self, device, shapes, pass_, out, m, v, op: "OpAssignVariant", operand, variant=GemvVariant.Gemv):
+        """out = (m * v) (op) operand in one launch (wgb_gemv_op): Gemv::dispatch + OpAssign::dispatch(out, operand) fused into
+        the GEMV's store.  `operand` may be `out` itself (the residual update out = m * v + out)."""
+        out, m, v, e = as_view(out, 3), as_view(m, 3), as_view(v, 3), as_view(operand, 3)
+        so, sm, sv, se = (shapes.get(device, x.shape()).to_c() for x in (out, m, v, e))
+        check(lib().wgb_gemv_op(pass_._h, int(variant), out.buffer()._h, ctypes.byref(so), m.buffer()._h, ctypes.byref(sm),
+                                1 if m.ordering.is_row_major() else 0, v.buffer()._h, ctypes.byref(sv), int(op), e.buffer()._h,
+                                ctypes.byref(se)))
+
 
 class OpAssign:
     """op_assign.rs:43-94: `OpAssign(pipeline, variant)` -> fields `.0` / `.1` are `pipeline` / `variant`."""
