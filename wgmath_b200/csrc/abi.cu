@@ -11,6 +11,8 @@
 //   wgebra/src/linalg/gemm.rs:78-96    dimension asserts          -> WGB_ERR_DIM_MISMATCH
 //   wgebra/src/linalg/gemv.rs:77-124   dimension asserts, TrFast fallback
 //   wgebra/src/linalg/op_assign.rs:82-86, reduce.rs:100-113
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects the NVTX library
+
 #include "common.cuh"
 
 namespace wgb {
@@ -235,17 +237,20 @@ wgb_status wgb_ctx_stream(wgb_ctx *ctx, void **cuda_stream) {
 
 // --------------------------------------------------------------------------- passes
 wgb_status wgb_pass_begin(wgb_ctx *ctx, const char *label, wgb_event *begin_ts, wgb_event *end_ts, wgb_pass **out) {
-    (void)label;
     if (!ctx || !out) WGB_FAIL(WGB_ERR_INVALID, "wgb_pass_begin: null argument");
     wgb_pass *p = new wgb_pass();
     p->ctx = ctx;
     p->stream = ctx->stream;
     p->end_ts = end_ts;
+    // the reference labels every compute pass (kernel.rs:15-26, ComputePassDescriptor::label); here the label names an NVTX range
+    // around the pass's recording, which is what ncu / nsys show next to the kernels
+    p->nvtx_range = nvtxRangeStartA(label ? label : "compute_pass");
     ctx_retain(ctx);
     if (begin_ts) {
         DeviceGuard g(ctx->device);
         cudaError_t e = cudaEventRecord(begin_ts->ev, p->stream);
         if (e != cudaSuccess) {
+            nvtxRangeEnd(p->nvtx_range);
             delete p;
             ctx_release(ctx);
             WGB_FAIL(WGB_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
@@ -265,6 +270,7 @@ wgb_status wgb_pass_end(wgb_pass *pass) {
             st = WGB_ERR_CUDA;
         }
     }
+    nvtxRangeEnd(pass->nvtx_range);
     wgb_ctx *ctx = pass->ctx;
     delete pass;
     ctx_release(ctx);

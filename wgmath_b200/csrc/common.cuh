@@ -94,6 +94,7 @@ struct wgb_pass {
     cudaStream_t stream = nullptr;
     wgb_event *end_ts = nullptr;
     int last_gemm_path = 0;
+    uint64_t nvtx_range = 0;   // nvtxRangeId_t of the pass label
 };
 
 struct wgb_buffer {
