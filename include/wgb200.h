@@ -431,6 +431,18 @@ wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, 
                                       const wgb_buffer *m2, const wgb_view_shape *m2_shape, wgb_dtype in_dtype,
                                       wgb_dtype out_dtype, wgb_f32_mode f32_mode);
 
+/* The same collective with HOST operands, enqueued (the N > 1 counterpart of wgb_gemm_host_enqueue): this rank's dense
+ * column-major A block ([M_local x K], or [K x M_local] for the transposed variants) and B ([K x N]) are uploaded into one of two
+ * alternating device slots, the fused GEMM + all-gather runs once they have landed, and the result is downloaded into out_host:
+ * this rank's [M_local x N] panel (download_all == 0; the ranks of a box assemble C in host memory) or the whole gathered cube
+ * [M_local x N x nranks].  Returns once everything is queued: the upload of the next product overlaps the GEMM and the download
+ * of this one.  out_host is complete after wgb_ctx_sync(), or after wgb_gemm_host_flush() for later work on the queue.  Pinned
+ * host memory (wgb_host_alloc) is needed for the overlap.  Collective: every rank must make the same sequence of calls. */
+wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, wgb_peer_gather *pg, uint32_t M_local,
+                                                   uint32_t N, uint32_t K, void *out_host, const void *m1_local_host,
+                                                   const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype,
+                                                   wgb_f32_mode f32_mode, int download_all);
+
 #ifdef __cplusplus
 }
 #endif

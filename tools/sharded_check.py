@@ -53,6 +53,20 @@ def main():
                 gpu.queue().submit(enc.finish())
                 got = c.read()
             results[mode] = got
+            if group is not None:
+                # host-operand, enqueued form (wgb_gemm_row_sharded_fused_host_enqueue): same kernel on the same inputs, so this
+                # rank's downloaded panel must equal its panel of the gathered cube bit for bit; three products through the two
+                # alternating device slots and host buffers, then one whole-cube download
+                ha, hb = np.ascontiguousarray(O.bf16_bits(a_blk)), np.ascontiguousarray(O.bf16_bits(b_all))
+                outs = [np.zeros(m_local * N, np.uint16) for _ in range(3)]
+                for o_ in outs:
+                    op.enqueue_host_fused(dev, group, m_local, N, K, o_, ha, hb, var)
+                cube = np.zeros(m_local * N * world, np.uint16)
+                op.enqueue_host_fused(dev, group, m_local, N, K, cube, ha, hb, var, download_all=True)
+                dev.poll_wait()
+                mine = got[rank * m_local * N:(rank + 1) * m_local * N]
+                host_ok = all(np.array_equal(o_, mine) for o_ in outs) and np.array_equal(cube, got)
+                results["host_ok"] = host_ok
             dist.barrier()
             if group is None:
                 w.lib().wgb_comm_destroy(dev._h)
@@ -71,9 +85,9 @@ def main():
             a_rows = np.stack([O.to_bf16_rne(O.uniform(O.SEED_BASE + 1, 1, K, row0=int(r))) for r in rows]).astype(np.float64)
         ref = a_rows @ b_all.reshape(N, K).T.astype(np.float64)
         err = max(float(np.max(np.abs(full[rows] - ref) / np.abs(ref))), float(np.max(np.abs(full_nccl[rows] - ref) / np.abs(ref))))
-        good = same and err < 1e-2
+        good = same and err < 1e-2 and results.get("host_ok", False)
         ok &= good
-        print(f"[rank {rank}] {M}x{N}x{K} tr={int(tr)} world={world}: nccl~fused {same}, rel err vs f64 {err:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
+        print(f"[rank {rank}] {M}x{N}x{K} tr={int(tr)} world={world}: nccl~fused {same}, host-enqueue == device path {results.get('host_ok')}, rel err vs f64 {err:.3e} -> {'OK' if good else 'FAIL'}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -400,4 +400,74 @@ wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, 
     return WGB_OK;
 }
 
+// Host-buffer form of the fused sharded GEMM, enqueued (the N > 1 counterpart of wgb_gemm_host_enqueue, abi.cu): this rank's A
+// block and B are uploaded on the upload stream into one of two alternating device slots, the fused GEMM + all-gather runs on
+// the queue once they have landed, and the result leaves on the download stream — this rank's own [M_local x N] panel only
+// (download_all == 0: the ranks of one box assemble C in host memory, every byte crosses a host link once) or the whole gathered
+// cube.  The upload of product i + 1 therefore runs under the GEMM and the download of product i.  Ordering that is specific to
+// the shared gathered buffer: the queue waits for the previous product's download before it lets the next GEMM (and, for whole
+// cube downloads, the peers) overwrite what is being read.
+wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, wgb_peer_gather *pg, uint32_t M_local,
+                                                   uint32_t N, uint32_t K, void *out_host, const void *m1_local_host,
+                                                   const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
+                                                   int download_all) {
+    if (!ctx || !pg || !out_host || !m1_local_host || !m2_host)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused_host_enqueue: null argument");
+    if (pg->ctx != ctx) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused_host_enqueue: the peer group belongs to another context");
+    if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "unknown variant");
+    if (M_local == 0 || N == 0 || K == 0) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused_host_enqueue: empty operands");
+    if ((uint64_t)M_local * K > 0xFFFFFFFFull || (uint64_t)K * N > 0xFFFFFFFFull || (uint64_t)M_local * N * pg->nranks > 0xFFFFFFFFull)
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "operands exceed u32 element indexing");
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    const size_t es = dtype_size(in_dtype), os = dtype_size(out_dtype);
+    const size_t a_bytes = (size_t)M_local * K * es, b_bytes = (size_t)K * N * es, panel_bytes = (size_t)M_local * N * os;
+    DeviceGuard dg(ctx->device);
+    HostGemmState &hs = ctx->host_gemm;
+    if (!ctx->h2d_stream) WGB_CUDA(cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking));
+    for (auto &e : hs.done)
+        if (!e) WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    while (hs.evs.size() < 2) {
+        cudaEvent_t e;
+        WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hs.evs.push_back(e);
+    }
+    const size_t b_off = (a_bytes + 255) & ~(size_t)255, slot_bytes = (b_off + b_bytes + 255) & ~(size_t)255;
+    if (ctx->ws[3].bytes < 2 * slot_bytes) {   // growing frees the slots: drain everything that may still use them
+        WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        hs.pending[0] = hs.pending[1] = false;
+    }
+    void *w = nullptr;
+    WGB_TRY(workspace_reserve(ctx, 3, 2 * slot_bytes, &w));
+    const int slot = (int)(hs.calls++ & 1u);
+    if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));   // the slot's last user has finished
+    char *dA = (char *)w + (size_t)slot * slot_bytes, *dB = dA + b_off;
+    WGB_CUDA(cudaMemcpyAsync(dA, m1_local_host, a_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    WGB_CUDA(cudaMemcpyAsync(dB, m2_host, b_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    WGB_CUDA(cudaEventRecord(hs.evs[0], ctx->h2d_stream));
+    WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.evs[0], 0));
+    if (hs.pending[slot ^ 1]) WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.done[slot ^ 1], 0));   // previous download has left the gathered buffer
+    wgb_buffer bA, bB;
+    bA.ctx = bB.ctx = ctx;
+    bA.owned = bB.owned = false;
+    bA.ptr = dA; bA.bytes = a_bytes;
+    bB.ptr = dB; bB.bytes = b_bytes;
+    const wgb_view_shape s1 = tr ? wgb_view_shape{{K, M_local, 1}, K, K * M_local, 0} : wgb_view_shape{{M_local, K, 1}, M_local, M_local * K, 0};
+    const wgb_view_shape s2 = wgb_view_shape{{K, N, 1}, K, K * N, 0};
+    wgb_pass pass;
+    pass.ctx = ctx;
+    pass.stream = ctx->stream;
+    WGB_TRY(wgb_gemm_row_sharded_fused(&pass, variant, pg, &bA, &s1, &bB, &s2, in_dtype, out_dtype, mode));
+    WGB_CUDA(cudaEventRecord(hs.evs[1], ctx->stream));
+    WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, hs.evs[1], 0));
+    if (download_all)
+        WGB_CUDA(cudaMemcpyAsync(out_host, pg->local, panel_bytes * pg->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    else
+        WGB_CUDA(cudaMemcpyAsync(out_host, pg->local + (size_t)pg->rank * panel_bytes, panel_bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+    WGB_CUDA(cudaEventRecord(hs.done[slot], ctx->comm_stream));
+    hs.pending[slot] = true;
+    return WGB_OK;
+}
+
 }  // extern "C"

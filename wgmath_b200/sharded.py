@@ -131,6 +131,19 @@ class RowShardedGemm:
                                                ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[group.tensor.dtype], int(f32_mode)))
 
 
+    def enqueue_host_fused(self, device, group: "PeerGather", m_local: int, N: int, K: int, out_host, m1_local_host, m2_host,
+                           variant=GemmVariant.Gemm, in_dtype: str = "bf16", f32_mode=F32Mode.Auto, download_all: bool = False) -> None:
+        """Host operands in, host result out, enqueued (wgb_gemm_row_sharded_fused_host_enqueue): upload of the next product
+        overlaps the GEMM + gather and the download of this one.  `*_host` are numpy arrays or raw host pointers; `out_host`
+        receives this rank's [m_local x N] panel, or the whole gathered cube with download_all.  Close a batch with
+        Gemm.flush_host(device) / device.poll_wait()."""
+        def ptr(x):
+            return x if isinstance(x, ctypes.c_void_p) else x.ctypes.data_as(ctypes.c_void_p)
+        check(lib().wgb_gemm_row_sharded_fused_host_enqueue(device._h, int(variant), group._h, m_local, N, K, ptr(out_host),
+                                                            ptr(m1_local_host), ptr(m2_host), _DTYPE_CODE[in_dtype],
+                                                            _DTYPE_CODE[group.tensor.dtype], int(f32_mode), 1 if download_all else 0))
+
+
 def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
     """bench.py's N > 1 leg: bf16 (4096*P)^3, row-sharded, all-gather of C; returns the JSON fields."""
     dev = gpu.device()
@@ -172,26 +185,46 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
             "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
             "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
             "nvlink_floor_ms": comm_bytes / 770e9 * 1e3}
-    # e2e: host -> device of this rank's A block and of B, sharded GEMM + gather, device -> host of the gathered C
+    # e2e: HOST buffers in, HOST buffer out, through the C ABI, every step: this rank's A block and B go up, the sharded GEMM +
+    # gather runs, the result comes down.
+    # (a) fused mode: wgb_gemm_row_sharded_fused_host_enqueue — products queued back to back, upload of product i + 1 under the
+    #     GEMM / download of product i; each rank downloads its own [M/P x N] panel, so the ranks of the box assemble C in host
+    #     memory and every byte of C crosses a host link once
+    # (b) separate blocking calls (write A, write B, dispatch, read the whole gathered cube on every rank) — the sequence of the
+    #     reference's tests, kept as `separate_calls`
     L = lib()
     abytes, bbytes, cbytes = m_local * n * 2, n * n * 2, n * n * 2
-    ha, hb, hc = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
-    for h, nb in ((ha, abytes), (hb, bbytes), (hc, cbytes)):
+    pbytes = m_local * n * 2
+    ha, hb, hc, hp0, hp1 = (ctypes.c_void_p() for _ in range(5))
+    for h, nb in ((ha, abytes), (hb, bbytes), (hc, cbytes), (hp0, pbytes), (hp1, pbytes)):
         check(L.wgb_host_alloc(nb, ctypes.byref(h)))
     check(L.wgb_buffer_read(dev._h, a.buffer()._h, 0, ha, abytes))
     check(L.wgb_buffer_read(dev._h, b.buffer()._h, 0, hb, bbytes))
     e2e_steps = max(2, min(args.steps, 5))
 
-    def e2e_step(p, i):
+    def e2e_seq_step(p, i):
         check(L.wgb_buffer_write(dev._h, a.buffer()._h, 0, ha, abytes))
         check(L.wgb_buffer_write(dev._h, b.buffer()._h, 0, hb, bbytes))
         step_fn(p, i)
         check(L.wgb_buffer_read(dev._h, c.buffer()._h, 0, hc, cbytes))
-    e2e_sec, _ = timed(e2e_step, e2e_steps, 1)
-    for h in (ha, hb, hc):
+    seq_sec, _ = timed(e2e_seq_step, e2e_steps, 1)
+    seq = {"value": flops * e2e_steps / seq_sec / 1e12, "ms_per_step": seq_sec * 1e3 / e2e_steps,
+           "h2d_bytes_per_step": (abytes + bbytes) * ngpu, "d2h_bytes_per_step": cbytes * ngpu,
+           "call": "wgb_buffer_write x2 + sharded dispatch + wgb_buffer_read of the whole gathered cube on every rank"}
+    if group is not None:
+        def e2e_step(p, i):
+            op.enqueue_host_fused(dev, group, m_local, n, n, hp0 if i % 2 == 0 else hp1, ha, hb)
+        e2e_sec, _ = timed(e2e_step, e2e_steps, 2, before_end=lambda: check(L.wgb_gemm_host_flush(dev._h)))
+        e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (abytes + bbytes) * ngpu,
+               "d2h_bytes_per_step": pbytes * ngpu, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3 / e2e_steps,
+               "call": "wgb_gemm_row_sharded_fused_host_enqueue per step on every rank (pinned host buffers; A block + B up, fused "
+                       "GEMM + all-gather, this rank's panel of C down: the box's host memory ends with all of C), closed by "
+                       "wgb_gemm_host_flush", "separate_calls": seq}
+    else:
+        e2e = {"value": seq["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": seq["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": seq["d2h_bytes_per_step"], "steps": e2e_steps, "ms_per_step": seq["ms_per_step"], "call": seq["call"]}
+    for h in (ha, hb, hc, hp0, hp1):
         L.wgb_host_free(h)
-    e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (abytes + bbytes) * ngpu,
-           "d2h_bytes_per_step": cbytes * ngpu, "steps": e2e_steps}
     if dist is not None:
         dist.barrier()
     if group is not None:
