@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;   // optional
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -56,6 +57,7 @@ static NcclApi &nccl() {
         SYM(GroupEnd, "ncclGroupEnd");
         SYM(Send, "ncclSend");
         SYM(Recv, "ncclRecv");
+        SYM(AllGather, "ncclAllGather");
         SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
         api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Send && api.Recv;
@@ -444,7 +446,22 @@ wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_varian
     if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));   // the slot's last user has finished
     char *dA = (char *)w + (size_t)slot * slot_bytes, *dB = dA + b_off;
     WGB_CUDA(cudaMemcpyAsync(dA, m1_local_host, a_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    WGB_CUDA(cudaMemcpyAsync(dB, m2_host, b_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    // EXPERIMENTAL, off by default, NOT YET VALIDATED ON HARDWARE (written after this round's GPU budget was spent; profiles/README.md):
+    // with WGB_SHARD_B_UPLOAD=1 and an NCCL communicator on this context, every rank uploads only its 1/P column slice of B and
+    // the slices are all-gathered in place over NVLink on the upload stream, so B crosses the host links once per box instead
+    // of once per rank (the measured e2e bound at N = 8).
+    static const bool want_split_b = env_int("WGB_SHARD_B_UPLOAD", 0) != 0;
+    const int P = pg->nranks;
+    const bool split_b = want_split_b && P > 1 && ctx->comm && ctx->comm->comm && ctx->comm->nranks == P && ctx->comm->rank == pg->rank &&
+                         nccl().ok && nccl().AllGather && N % (uint32_t)P == 0;
+    if (split_b) {
+        const size_t slice = b_bytes / (size_t)P;
+        WGB_CUDA(cudaMemcpyAsync(dB + (size_t)pg->rank * slice, (const char *)m2_host + (size_t)pg->rank * slice, slice,
+                                 cudaMemcpyHostToDevice, ctx->h2d_stream));
+        WGB_NCCL(nccl().AllGather(dB + (size_t)pg->rank * slice, dB, slice, ncclInt8, ctx->comm->comm, ctx->h2d_stream));
+    } else {
+        WGB_CUDA(cudaMemcpyAsync(dB, m2_host, b_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    }
     WGB_CUDA(cudaEventRecord(hs.evs[0], ctx->h2d_stream));
     WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.evs[0], 0));
     if (hs.pending[slot ^ 1]) WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.done[slot ^ 1], 0));   // previous download has left the gathered buffer

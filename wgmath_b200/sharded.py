@@ -212,11 +212,18 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
            "h2d_bytes_per_step": (abytes + bbytes) * ngpu, "d2h_bytes_per_step": cbytes * ngpu,
            "call": "wgb_buffer_write x2 + sharded dispatch + wgb_buffer_read of the whole gathered cube on every rank"}
     if group is not None:
+        # experimental (off by default, see comm.cu): every rank uploads 1/P of B, the slices are all-gathered over NVLink
+        split_b = os.environ.get("WGB_SHARD_B_UPLOAD", "0") not in ("", "0")
+        if split_b:
+            init_comm(dev, dist, rank, ngpu)
+
         def e2e_step(p, i):
             op.enqueue_host_fused(dev, group, m_local, n, n, hp0 if i % 2 == 0 else hp1, ha, hb)
         e2e_sec, _ = timed(e2e_step, e2e_steps, 2, before_end=lambda: check(L.wgb_gemm_host_flush(dev._h)))
-        e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": (abytes + bbytes) * ngpu,
+        e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": abytes * ngpu + (bbytes if split_b else bbytes * ngpu),
                "d2h_bytes_per_step": pbytes * ngpu, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3 / e2e_steps,
+               "b_upload": "1/P slice per rank + NCCL all-gather over NVLink (WGB_SHARD_B_UPLOAD=1)" if split_b else "whole B on every rank",
                "call": "wgb_gemm_row_sharded_fused_host_enqueue per step on every rank (pinned host buffers; A block + B up, fused "
                        "GEMM + all-gather, this rank's panel of C down: the box's host memory ends with all of C), closed by "
                        "wgb_gemm_host_flush", "separate_calls": seq}
@@ -225,6 +232,9 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
                "d2h_bytes_per_step": seq["d2h_bytes_per_step"], "steps": e2e_steps, "ms_per_step": seq["ms_per_step"], "call": seq["call"]}
     for h in (ha, hb, hc, hp0, hp1):
         L.wgb_host_free(h)
+    if group is not None and split_b:
+        dev.poll_wait()
+        lib().wgb_comm_destroy(dev._h)
     if dist is not None:
         dist.barrier()
     if group is not None:
