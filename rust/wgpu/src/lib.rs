@@ -53,6 +53,15 @@ pub mod sys {
                              b: *const wgb_buffer, b_shape: *const wgb_view_shape) -> c_int;
         pub fn wgb_reduce(pass: *mut wgb_pass, op: c_int, value: *const wgb_buffer, value_shape: *const wgb_view_shape,
                           result: *mut wgb_buffer) -> c_int;
+        pub fn wgb_prefix_sum(pass: *mut wgb_pass, data: *mut wgb_buffer, data_shape: *const wgb_view_shape) -> c_int;
+        pub fn wgb_radix_sort(pass: *mut wgb_pass, input_keys: *const wgb_buffer, input_keys_shape: *const wgb_view_shape,
+                              input_values: *const wgb_buffer, input_values_shape: *const wgb_view_shape, n_sort: *const wgb_buffer,
+                              sorting_bits: u32, output_keys: *mut wgb_buffer, output_keys_shape: *const wgb_view_shape,
+                              output_values: *mut wgb_buffer, output_values_shape: *const wgb_view_shape) -> c_int;
+        pub fn wgb_gemv_op(pass: *mut wgb_pass, variant: c_int, out: *mut wgb_buffer, out_shape: *const wgb_view_shape,
+                           m: *const wgb_buffer, m_shape: *const wgb_view_shape, m_ordering: c_int, v: *const wgb_buffer,
+                           v_shape: *const wgb_view_shape, op: c_int, operand: *const wgb_buffer,
+                           operand_shape: *const wgb_view_shape) -> c_int;
         pub fn wgb_geometry_in_bytes(dim: c_int) -> u32;
         pub fn wgb_geometry_out_bytes(op: c_int, dim: c_int) -> u32;
         pub fn wgb_geometry_batch(pass: *mut wgb_pass, op: c_int, dim: c_int, input: *const wgb_buffer, in_first: u64,
