@@ -320,7 +320,9 @@ wgb_status wgb_radix_sort(wgb_pass *pass, const wgb_buffer *input_keys, const wg
  * Padding words are written as zero.  in_first / out_first are element indices into the buffers (a GpuVector view's offset).
  * In place (same buffer, same first element) is allowed for CHOLESKY and INV; any other overlap is WGB_ERR_INVALID.
  * n == 0 or a zero-sized buffer enqueues nothing (kernel.rs:111-113,144).  The QR sweeps of eig3 / eig4 are unbounded in the
- * reference (eig3.wgsl:77); here they stop after 256 sweeps. */
+ * reference (eig3.wgsl:77); here they stop after 256 sweeps.  Results are the reference's, quirks included: WGSL's sign(0) = 0 zeroes
+ * eigenvector rows for inputs with an exactly trivial Householder step (diagonal / block-diagonal matrices, eig3.wgsl:48-67); the
+ * eigenvalues are correct in every case. */
 uint32_t wgb_geometry_in_bytes(int dim);
 uint32_t wgb_geometry_out_bytes(wgb_geom_op op, int dim);
 wgb_status wgb_geometry_batch(wgb_pass *pass, wgb_geom_op op, int dim, const wgb_buffer *in, uint64_t in_first, wgb_buffer *out,
