@@ -169,7 +169,6 @@ def test_error_behaviour(gpu):
     assert "exceed the buffer" in str(e.value)
     with pytest.raises(w.WgbError):                                      # shifted in-place ranges race between warps
         run_pass(gpu, lambda p: w.WgCholesky2.from_device(dev).dispatch(dev, p, t2.rows(0, 32), t2.rows(16, 32)))
-    import ctypes
     enc = dev.create_command_encoder()
     p = enc.compute_pass("t", None)
     rc = w.lib().wgb_geometry_batch(p._h, G.GEOM_SVD, 4, t2.buffer()._h, 0, t2.buffer()._h, 0, 1)   # no 4x4 SVD in the reference
