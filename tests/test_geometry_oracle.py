@@ -333,3 +333,25 @@ def test_eig_terminates_and_is_exact_on_structured_inputs(dim):
     expect[0, 0] = 1.0
     for k in (0, 1, 2, 3):                                         # zero, I, 3I, diag: only Q[0][0] survives the sign(0) factors
         assert np.array_equal(v[k], expect), k
+
+
+def test_shared_memory_tile_pitch_is_bank_conflict_free():
+    """csrc/geometry.cu `tile_pitch<W, V>`: pitch = W if (W / V) is odd else W + V.  A warp accesses one V-word vector per lane at a
+    stride of one struct per lane; shared memory serves 128 bytes per phase (8 lanes of float4, 16 lanes of float2).  The lanes
+    of a phase must hit disjoint banks for every struct size the kernels use."""
+    def pitch(w, v):
+        return w if (w // v) % 2 == 1 else w + v
+    cases = [(12, 4), (16, 4), (20, 4), (24, 4), (28, 4), (32, 4),      # 3x3 / 4x4 inputs and outputs (float4)
+             (10, 2), (8, 2), (6, 2)]                                   # 2x2 lu / svd, qr, eig outputs (float2)
+    for w, v in cases:
+        p = pitch(w, v)
+        assert p % v == 0                                               # vector alignment inside the tile
+        lanes_per_phase = 32 // v
+        for chunk in range(w // v):
+            for phase in range(32 // lanes_per_phase):
+                banks = set()
+                for lane in range(phase * lanes_per_phase, (phase + 1) * lanes_per_phase):
+                    first = (lane * p + chunk * v) % 32
+                    lane_banks = {(first + k) % 32 for k in range(v)}
+                    assert not (banks & lane_banks), (w, v, chunk, phase, lane)
+                    banks |= lane_banks
