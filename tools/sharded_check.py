@@ -57,6 +57,10 @@ def main():
                 # host-operand, enqueued form (wgb_gemm_row_sharded_fused_host_enqueue): same kernel on the same inputs, so this
                 # rank's downloaded panel must equal its panel of the gathered cube bit for bit; three products through the two
                 # alternating device slots and host buffers, then one whole-cube download
+                # with WGB_SHARD_B_UPLOAD=1 (experimental sliced upload of B + NCCL all-gather) the path needs a communicator
+                split_b = os.environ.get("WGB_SHARD_B_UPLOAD", "0") not in ("", "0")
+                if split_b:
+                    sharded.init_comm(dev, dist, rank, world)
                 ha, hb = np.ascontiguousarray(O.bf16_bits(a_blk)), np.ascontiguousarray(O.bf16_bits(b_all))
                 outs = [np.zeros(m_local * N, np.uint16) for _ in range(3)]
                 for o_ in outs:
@@ -67,6 +71,8 @@ def main():
                 mine = got[rank * m_local * N:(rank + 1) * m_local * N]
                 host_ok = all(np.array_equal(o_, mine) for o_ in outs) and np.array_equal(cube, got)
                 results["host_ok"] = host_ok
+                if split_b:
+                    w.lib().wgb_comm_destroy(dev._h)
             dist.barrier()
             if group is None:
                 w.lib().wgb_comm_destroy(dev._h)
