@@ -340,6 +340,12 @@ wgb_status wgb_debug_tc_trace(wgb_ctx *ctx, int enable, unsigned long long *out,
 /* Which kernel family the last wgb_gemm* call on this pass dispatched to:
  * 0 none, 1 SIMT FFMA, 2 tcgen05 bf16, 3 tcgen05 tf32, 4 tcgen05 3xtf32. */
 wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);
+/* The tcgen05 kernel instantiation and plan of that call (all zero unless the path is 2..4), WGB_TC_CONFIG_WORDS ints:
+ *   [0] operand kind (0 bf16, 1 tf32)  [1] A MN-major  [2] B MN-major  [3] BLOCK_N  [4] MMA passes (3 = 3xTF32)
+ *   [5] output wgb_dtype  [6] CTAs per tile (cta_group)  [7] epilogue (0 per-lane stores, 1 TMA bulk stores)
+ *   [8] tail N-split factor  [9] tail split-K factor  [10] destinations per output block (fused all-gather: ranks)  [11] work units */
+#define WGB_TC_CONFIG_WORDS 12
+wgb_status wgb_pass_last_gemm_config(const wgb_pass *pass, int *config /* WGB_TC_CONFIG_WORDS */);
 
 /* gemv.rs:64-137.  out = m * v or tr(m) * v; v / out may carry several columns and batches. */
 wgb_status wgb_gemv(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out,
@@ -422,6 +428,21 @@ wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_bu
 #define WGB_IPC_HANDLE_BYTES 64
 typedef struct wgb_peer_gather wgb_peer_gather;
 wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, wgb_peer_gather **out);
+/* `depth` gathered buffers (1..3) that successive calls rotate through (call e uses buffer e mod depth):
+ *   1  one buffer; a peer can start storing step e only when this rank has itself reached step e (lock step);
+ *   2  peers may store step e + 1 as soon as this rank has started step e; the result of call e is valid until call e + 1 is issued;
+ *   3  same look-ahead; the result of call e stays valid until call e + 2 is issued, so with WGB_GATHER_NO_WAIT the wait for (and
+ *      the use of) step e may be queued after the GEMM of step e + 1: a slow rank no longer stalls the others at every step.
+ * All ranks must use the same depth. */
+wgb_status wgb_peer_gather_create_ex(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, int depth, wgb_peer_gather **out);
+/* Same-process connect: groups[q] is rank q's group (one context per rank; the ranks may share a device — the whole protocol then
+ * runs on a single-GPU box — or sit on several devices driven by one process).  groups[rank] must be pg itself. */
+wgb_status wgb_peer_gather_connect_local(wgb_peer_gather *pg, wgb_peer_gather *const *groups /* nranks */);
+/* The gathered buffer written by the call `calls_back` calls ago (0 = the most recent), while it is still valid (see depth). */
+wgb_status wgb_peer_gather_buffer_at(wgb_peer_gather *pg, int calls_back, wgb_buffer **out);
+/* Queue a wait for the panels of every peer of the call `calls_back` calls ago (what wgb_gemm_row_sharded_fused does itself
+ * unless WGB_GATHER_NO_WAIT is given).  Later work on the pass's queue sees the complete gathered result of that call. */
+wgb_status wgb_peer_gather_wait(wgb_pass *pass, wgb_peer_gather *pg, int calls_back);
 wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out /* WGB_IPC_HANDLE_BYTES */);
 wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles /* nranks x WGB_IPC_HANDLE_BYTES */);
 /* The local gathered buffer as a wgb_buffer (owned by the group; valid until wgb_peer_gather_destroy). */
@@ -432,6 +453,15 @@ wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, 
                                       const wgb_buffer *m1_local, const wgb_view_shape *m1_local_shape,
                                       const wgb_buffer *m2, const wgb_view_shape *m2_shape, wgb_dtype in_dtype,
                                       wgb_dtype out_dtype, wgb_f32_mode f32_mode);
+
+/* flags: WGB_GATHER_NO_WAIT = return after this rank's GEMM + peer stores are queued, without waiting for the peers' panels;
+ * pair with wgb_peer_gather_wait.  Flag waits between GPUs are bounded by WGB_PEER_TIMEOUT_MS (default 60000; 0 = unbounded):
+ * a peer that never arrives surfaces as a CUDA error on this rank instead of a hung GPU. */
+#define WGB_GATHER_NO_WAIT 1u
+wgb_status wgb_gemm_row_sharded_fused_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg,
+                                         const wgb_buffer *m1_local, const wgb_view_shape *m1_local_shape,
+                                         const wgb_buffer *m2, const wgb_view_shape *m2_shape, wgb_dtype in_dtype,
+                                         wgb_dtype out_dtype, wgb_f32_mode f32_mode, uint32_t flags);
 
 /* The same collective with HOST operands, enqueued (the N > 1 counterpart of wgb_gemm_host_enqueue): this rank's dense
  * column-major A block ([M_local x K], or [K x M_local] for the transposed variants) and B ([K x N]) are uploaded into one of two

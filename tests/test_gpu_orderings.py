@@ -36,7 +36,7 @@ def addressed(vs, rm):
 
 
 def gemm_ord_case(gpu, shapes, M, N, K, tr, ro, r1, r2, T=1, dtype="f32", out_dtype="f32", mode=None, pad=(0, 0, 0), off=(0, 0, 0),
-                  tol=F32_TOL, op=None):
+                  tol=F32_TOL, op=None, cfg_out=None):
     ar, ac = (K, M) if tr else (M, K)
     s1, n1 = view_of(ar, ac, T, r1, pad[0], off[0])
     s2, n2 = view_of(K, N, T, r2, pad[1], off[1])
@@ -71,6 +71,8 @@ def gemm_ord_case(gpu, shapes, M, N, K, tr, ro, r1, r2, T=1, dtype="f32", out_dt
         else:
             gemm.dispatch_op(gpu.device(), shapes, p, vc, va, vb, op, ve, variant=variant, f32_mode=mode)
         path.append(p.last_gemm_path())
+        if cfg_out is not None:
+            cfg_out.append(p.last_gemm_config())
     run_pass(gpu, go)
     got = tc.read()
     if out_dtype == "bf16":

@@ -58,6 +58,7 @@ def lib() -> ctypes.CDLL:
         "wgb_pass_end": ([vp], ci),
         "wgb_submit": ([vp], ci),
         "wgb_pass_last_gemm_path": ([vp, ctypes.POINTER(ci)], ci),
+        "wgb_pass_last_gemm_config": ([vp, ctypes.POINTER(ci)], ci),
         "wgb_graph_capture_begin": ([vp], ci),
         "wgb_graph_capture_end": ([vp, pvp], ci),
         "wgb_graph_launch": ([vp], ci),
@@ -103,6 +104,11 @@ def lib() -> ctypes.CDLL:
         "wgb_comm_destroy": ([vp], ci),
         "wgb_gemm_row_sharded": ([vp, ci, vp, vp, sp, vp, sp, ci, ci, ci, ci], ci),
         "wgb_peer_gather_create": ([vp, ci, ci, sz, pvp], ci),
+        "wgb_peer_gather_create_ex": ([vp, ci, ci, sz, ci, pvp], ci),
+        "wgb_peer_gather_connect_local": ([vp, pvp], ci),
+        "wgb_peer_gather_buffer_at": ([vp, ci, pvp], ci),
+        "wgb_peer_gather_wait": ([vp, vp, ci], ci),
+        "wgb_gemm_row_sharded_fused_ex": ([vp, ci, vp, vp, sp, vp, sp, ci, ci, ci, u32], ci),
         "wgb_peer_gather_export": ([vp, vp], ci),
         "wgb_peer_gather_connect": ([vp, vp], ci),
         "wgb_peer_gather_buffer": ([vp, pvp], ci),
@@ -122,7 +128,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_ctx_destroy", "wgb_ctx_sync",
             "wgb_ctx_device_info", "wgb_ctx_launch_count", "wgb_ctx_stream", "wgb_pass_begin", "wgb_pass_end",
-            "wgb_submit", "wgb_pass_last_gemm_path", "wgb_graph_capture_begin", "wgb_graph_capture_end", "wgb_graph_launch",
+            "wgb_submit", "wgb_pass_last_gemm_path", "wgb_pass_last_gemm_config", "wgb_graph_capture_begin", "wgb_graph_capture_end", "wgb_graph_launch",
             "wgb_graph_destroy", "wgb_buffer_create", "wgb_buffer_create_init", "wgb_buffer_wrap",
             "wgb_buffer_destroy", "wgb_buffer_size", "wgb_buffer_device_ptr", "wgb_buffer_write", "wgb_buffer_copy",
             "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_op", "wgb_gemm_ord", "wgb_gemm_host", "wgb_gemm_host_enqueue", "wgb_gemm_host_flush", "wgb_gemv",
@@ -131,7 +137,8 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",
             "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded", "wgb_peer_gather_create",
             "wgb_peer_gather_export", "wgb_peer_gather_connect", "wgb_peer_gather_buffer", "wgb_peer_gather_destroy",
-            "wgb_gemm_row_sharded_fused", "wgb_gemm_row_sharded_fused_host_enqueue"]
+            "wgb_gemm_row_sharded_fused", "wgb_gemm_row_sharded_fused_host_enqueue", "wgb_peer_gather_create_ex",
+            "wgb_peer_gather_connect_local", "wgb_peer_gather_buffer_at", "wgb_peer_gather_wait", "wgb_gemm_row_sharded_fused_ex"]
 
 
 def check(status: int) -> None:

@@ -43,6 +43,7 @@ wgb_status workspace_reserve(wgb_ctx *ctx, int slot, size_t bytes, void **out) {
         if (w.ptr) WGB_CUDA(cudaFree(w.ptr));
         w.ptr = nullptr;
         w.bytes = 0;
+        ++ctx->ws_generation;
         size_t want = bytes + (bytes >> 3);
         cudaError_t e = cudaMalloc(&w.ptr, want);
         if (e != cudaSuccess) {
@@ -61,6 +62,7 @@ wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters)
     if (s.partials_floats < partial_floats) {
         WGB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (s.partials) WGB_CUDA(cudaFree(s.partials));
+        ++ctx->ws_generation;
         s.partials = nullptr;
         s.partials_floats = 0;
         WGB_CUDA(cudaMalloc(&s.partials, partial_floats * sizeof(float)));
@@ -69,12 +71,33 @@ wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters)
     if (s.n_counters < counters) {
         WGB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (s.counters) WGB_CUDA(cudaFree(s.counters));
+        ++ctx->ws_generation;
         s.counters = nullptr;
         s.n_counters = 0;
         WGB_CUDA(cudaMalloc(&s.counters, counters * sizeof(unsigned int)));
         WGB_CUDA(cudaMemset(s.counters, 0, counters * sizeof(unsigned int)));
         s.n_counters = counters;
     }
+    return WGB_OK;
+}
+
+wgb_status host_gemm_slot(wgb_ctx *ctx, size_t slot_bytes, char **base, int *slot_out) {
+    HostGemmState &hs = ctx->host_gemm;
+    slot_bytes = (slot_bytes + 255) & ~(size_t)255;
+    if (ctx->ws[3].bytes / 2 < slot_bytes + 256) {   // growing frees the slots: drain everything that may still use them
+        WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
+        WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        hs.pending[0] = hs.pending[1] = false;
+        void *w = nullptr;
+        WGB_TRY(workspace_reserve(ctx, 3, 2 * (slot_bytes + 256), &w));
+    }
+    const size_t half = (ctx->ws[3].bytes / 2) & ~(size_t)255;
+    const int slot = (int)(hs.calls++ & 1u);
+    // the product that used this slot two calls ago must have left it (its download is the last user)
+    if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));
+    *base = (char *)ctx->ws[3].ptr + (size_t)slot * half;
+    *slot_out = slot;
     return WGB_OK;
 }
 
@@ -295,6 +318,12 @@ wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path) {
     return WGB_OK;
 }
 
+wgb_status wgb_pass_last_gemm_config(const wgb_pass *pass, int *config) {
+    if (!pass || !config) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    for (int i = 0; i < WGB_TC_CONFIG_WORDS; ++i) config[i] = pass->last_gemm_path >= 2 ? pass->last_tc[i] : 0;
+    return WGB_OK;
+}
+
 // --------------------------------------------------------------------------- graphs
 }  // extern "C"
 struct wgb_graph {
@@ -303,6 +332,7 @@ struct wgb_graph {
     cudaGraphExec_t exec = nullptr;
     uint64_t launches_per_replay = 0;
     uint64_t launches_at_begin = 0;
+    uint64_t ws_generation = 0;   // the context's workspace generation the recorded kernels were given pointers from
 };
 static thread_local uint64_t g_capture_launch_mark = 0;
 extern "C" {
@@ -330,6 +360,7 @@ wgb_status wgb_graph_capture_end(wgb_ctx *ctx, wgb_graph **out) {
     gr->ctx = ctx;
     gr->graph = graph;
     gr->launches_per_replay = ctx->launches.load() - g_capture_launch_mark;
+    gr->ws_generation = ctx->ws_generation;
     ctx->launches.store(g_capture_launch_mark);   // recorded, not executed
     e = cudaGraphInstantiate(&gr->exec, graph, 0);
     if (e != cudaSuccess) {
@@ -345,6 +376,11 @@ wgb_status wgb_graph_capture_end(wgb_ctx *ctx, wgb_graph **out) {
 wgb_status wgb_graph_launch(wgb_graph *graph) {
     if (!graph) WGB_FAIL(WGB_ERR_INVALID, "null graph");
     DeviceGuard g(graph->ctx->device);
+    // The recorded kernels carry raw pointers into the context's workspaces (3xTF32 operand copies, split partials, scan / sort
+    // scratch).  A later eager call with a larger problem reallocates them: replaying would touch freed memory.
+    if (graph->ws_generation != graph->ctx->ws_generation)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_graph_launch: a workspace of the context was reallocated after this graph was recorded "
+                                  "(a larger problem ran since); record the graph again");
     WGB_CUDA(cudaGraphLaunch(graph->exec, graph->ctx->stream));
     count_launch(graph->ctx, graph->launches_per_replay);
     return WGB_OK;
@@ -852,18 +888,10 @@ static wgb_status gemm_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, uint
         if (!e) WGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const size_t b_off = (a_bytes + 255) & ~(size_t)255, c_off = (b_off + b_bytes + 255) & ~(size_t)255;
     const size_t slot_bytes = (c_off + c_bytes + 255) & ~(size_t)255;
-    if (ctx->ws[3].bytes < 2 * slot_bytes) {   // growing frees the slots: drain everything that may still use them
-        WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
-        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
-        WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
-        hs.pending[0] = hs.pending[1] = false;
-    }
-    void *w = nullptr;
-    WGB_TRY(workspace_reserve(ctx, 3, 2 * slot_bytes, &w));
-    const int slot = (int)(hs.calls++ & 1u);
-    // the product that used this slot two calls ago must have left it (its download is the last user)
-    if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));
-    char *dA = (char *)w + (size_t)slot * slot_bytes, *dB = dA + b_off, *dC = dA + c_off;
+    char *w = nullptr;
+    int slot = 0;
+    WGB_TRY(host_gemm_slot(ctx, slot_bytes, &w, &slot));
+    char *dA = w, *dB = dA + b_off, *dC = dA + c_off;
     // column panels: whole 256-column tiles
     // every extra copy costs ~10-20 us of link time (measured: enqueued products 1.35 / 1.41 / 1.52 / 1.66 ms at 2 / 4 / 8 / 16
     // panels, blocking calls 1.65 / 1.58 / 1.61 / 1.66 ms): few panels when products overlap each other, more when one call

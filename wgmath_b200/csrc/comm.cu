@@ -69,6 +69,7 @@ struct CommState {
     ncclComm_t comm = nullptr;
     int nranks = 1, rank = 0;
     int sm_margin = 0;
+    bool overlapping = false;   // inside wgb_gemm_row_sharded: GEMMs leave sm_margin SMs to the concurrent NCCL exchange
     std::vector<cudaEvent_t> events;
     cudaEvent_t done = nullptr;
 };
@@ -90,7 +91,7 @@ void comm_destroy(wgb_ctx *ctx) {
     ctx->comm = nullptr;
 }
 
-int comm_sm_margin(const wgb_ctx *ctx) { return ctx->comm && ctx->comm->nranks > 1 ? ctx->comm->sm_margin : 0; }
+int comm_sm_margin(const wgb_ctx *ctx) { return ctx->comm && ctx->comm->nranks > 1 && ctx->comm->overlapping ? ctx->comm->sm_margin : 0; }
 
 static int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -188,6 +189,11 @@ wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_bu
             cs->events.push_back(e);
         }
 
+    struct Overlap {   // scoped: only the GEMMs of this call run beside NCCL CTAs
+        CommState *c;
+        explicit Overlap(CommState *c_) : c(c_) { if (c) c->overlapping = true; }
+        ~Overlap() { if (c) c->overlapping = false; }
+    } overlap(P > 1 ? cs : nullptr);
     for (uint32_t c = 0; c < nch; ++c) {
         const uint32_t n0 = c * width, nc = (N - n0) < width ? (N - n0) : width;
         GemmProblem g{};
@@ -227,18 +233,32 @@ wgb_status wgb_gemm_row_sharded(wgb_pass *pass, wgb_gemm_variant variant, wgb_bu
 
 // ------------------------------------------------------------------------------------------------------------
 // fused GEMM + all-gather over peer memory
+//
+// Protocol (all counters are monotonic call numbers, "epochs", of one group; buffer of epoch e = e mod depth):
+//   ready[q] (lives on every rank r, written by rank q): rank q's buffers for epochs <= value may be overwritten by its peers.
+//            Rank q publishes it at the start of each of its calls.  depth 1: value = this call's epoch (a peer can only start
+//            storing step e once q itself has reached step e).  depth >= 2: value = epoch + 1 — the buffer the *next* step will
+//            use was last read by consumers that q's in-order queue has already passed, so peers may run one step ahead.
+//   done[q]  (lives on every rank r, written by the last CTA of rank q's GEMM): rank q's panel of epoch `value` is complete in
+//            r's buffer.  wgb_peer_gather_wait(e) = all done[q] >= e.
+//   Validity of the result of call e: depth 1 / 2 -> until call e + 1 is issued; depth 3 -> until call e + 2 is issued, which is
+//   what lets the wait (and the consumer) trail the GEMMs by one call so that a slow rank does not stall the others every step.
 // ------------------------------------------------------------------------------------------------------------
 }  // extern "C"
 
 struct wgb_peer_gather {
     wgb_ctx *ctx = nullptr;
-    int nranks = 1, rank = 0;
-    size_t data_bytes = 0;          // gathered buffer size (256-byte multiple)
-    char *local = nullptr;          // cudaMalloc: [data_bytes][signal block]
+    int nranks = 1, rank = 0, depth = 1;
+    size_t data_bytes = 0;          // one gathered buffer (256-byte multiple)
+    char *local = nullptr;          // cudaMalloc: [depth][data_bytes][signal block]
     char *peer[wgb::kMaxPeers] = {};
+    bool ipc_opened[wgb::kMaxPeers] = {};
     bool connected = false;
     unsigned int epoch = 0;
-    wgb_buffer view;                // non-owning wgb_buffer over the local gathered buffer
+    long long timeout_cycles = 0;   // bounded flag waits (0: unbounded)
+    wgb_buffer view[3];             // non-owning wgb_buffers over the local gathered buffers
+    size_t signal_off() const { return (size_t)depth * data_bytes; }
+    char *buffer_of(unsigned int e) const { return local + (size_t)(e % (unsigned)depth) * data_bytes; }
 };
 
 namespace wgb {
@@ -246,58 +266,74 @@ namespace wgb {
 constexpr size_t kSignalBytes = 4096;
 constexpr int kReadyOff = 0, kDoneOff = 16, kCtaOff = 32;
 
-__global__ void signal_ready_kernel(FusedGather f) {
+__global__ void signal_ready_kernel(FusedGather f, unsigned int value) {
     const int q = threadIdx.x;
     if (q < f.nranks && q != f.rank) {
         __threadfence_system();
         // done_remote[q] points at rank q's done array; its ready array sits kDoneOff words before it
         unsigned int *ready_q = f.done_remote[q] - kDoneOff + kReadyOff;
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_q + f.rank), "r"(f.epoch) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ready_q + f.rank), "r"(value) : "memory");
     }
 }
-__global__ void wait_done_kernel(const unsigned int *done_local, int nranks, int rank, unsigned int epoch) {
+__global__ void wait_done_kernel(const unsigned int *done_local, int nranks, int rank, unsigned int epoch, long long timeout) {
     const int q = threadIdx.x;
     if (q < nranks && q != rank) {
         const long long t0 = clock64();
         unsigned int v;
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(done_local + q) : "memory");
-            if (clock64() - t0 > 40000000000ll) __trap();
+            if (timeout > 0 && clock64() - t0 > timeout) __trap();
         } while ((int)(v - epoch) < 0);
     }
     __threadfence_system();
+}
+
+// Flag waits are bounded so that a lost peer surfaces as a CUDA error instead of a hung GPU; WGB_PEER_TIMEOUT_MS (default 60 s,
+// 0 = wait forever) must cover the longest legitimate skew between ranks (first-call module loads, uploads ahead of a step).
+static long long peer_timeout_cycles(const wgb_ctx *ctx) {
+    const long long ms = env_int("WGB_PEER_TIMEOUT_MS", 60000);
+    return ms <= 0 ? 0 : ms * (long long)ctx->prop.clockRate;   // clockRate is in kHz = cycles per ms
 }
 }  // namespace wgb
 
 extern "C" {
 
-wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, wgb_peer_gather **out) {
+wgb_status wgb_peer_gather_create_ex(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, int depth, wgb_peer_gather **out) {
     if (!ctx || !out || nranks < 1 || nranks > wgb::kMaxPeers || rank < 0 || rank >= nranks)
         WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_create: bad argument (at most %d ranks)", wgb::kMaxPeers);
+    if (depth < 1 || depth > 3) WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_create: depth must be 1, 2 or 3");
     DeviceGuard g(ctx->device);
     wgb_peer_gather *pg = new wgb_peer_gather();
     pg->ctx = ctx;
     pg->nranks = nranks;
     pg->rank = rank;
+    pg->depth = depth;
     pg->data_bytes = (gathered_bytes + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc((void **)&pg->local, pg->data_bytes + wgb::kSignalBytes);
+    pg->timeout_cycles = wgb::peer_timeout_cycles(ctx);
+    cudaError_t e = cudaMalloc((void **)&pg->local, pg->signal_off() + wgb::kSignalBytes);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
         delete pg;
-        WGB_FAIL(WGB_ERR_OOM, "peer gather: allocation of %zu bytes failed: %s", gathered_bytes, cudaGetErrorString(e));
+        WGB_FAIL(WGB_ERR_OOM, "peer gather: allocation of %d x %zu bytes failed: %s", depth, gathered_bytes, cudaGetErrorString(e));
     }
-    cudaMemset(pg->local + pg->data_bytes, 0, wgb::kSignalBytes);
+    cudaMemset(pg->local + pg->signal_off(), 0, wgb::kSignalBytes);
     cudaDeviceSynchronize();
     pg->peer[rank] = pg->local;
     pg->connected = nranks == 1;
-    pg->view.ctx = ctx;
-    pg->view.ptr = pg->local;
-    pg->view.bytes = gathered_bytes;
-    pg->view.owned = false;
-    pg->view.usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    for (int d = 0; d < depth; ++d) {
+        pg->view[d].ctx = ctx;
+        pg->view[d].ptr = pg->local + (size_t)d * pg->data_bytes;
+        pg->view[d].bytes = gathered_bytes;
+        pg->view[d].owned = false;
+        pg->view[d].usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    }
     wgb::ctx_retain(ctx);
     *out = pg;
     return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, wgb_peer_gather **out) {
+    return wgb_peer_gather_create_ex(ctx, nranks, rank, gathered_bytes, 1, out);
 }
 
 wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out) {
@@ -320,23 +356,70 @@ wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles) {
         void *ptr = nullptr;
         WGB_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         pg->peer[q] = (char *)ptr;
+        pg->ipc_opened[q] = true;
     }
     pg->connected = true;
     return WGB_OK;
 }
 
-wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out) {
+// Same-process form of connect: the groups of all ranks live in this process (one context per rank; the ranks may share one
+// device, which is how the whole protocol is exercised on a single-GPU box, or sit on several devices driven by one process).
+wgb_status wgb_peer_gather_connect_local(wgb_peer_gather *pg, wgb_peer_gather *const *groups) {
+    if (!pg || !groups) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(pg->ctx->device);
+    for (int q = 0; q < pg->nranks; ++q) {
+        wgb_peer_gather *o = groups[q];
+        if (!o || o->nranks != pg->nranks || o->rank != q || o->depth != pg->depth || o->data_bytes != pg->data_bytes)
+            WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_connect_local: group %d does not match (ranks, rank, depth or size)", q);
+        if (q == pg->rank) {
+            if (o != pg) WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_connect_local: groups[rank] must be the group itself");
+            continue;
+        }
+        if (o->ctx->device != pg->ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(o->ctx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                WGB_FAIL(WGB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", o->ctx->device, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+        }
+        pg->peer[q] = o->local;
+        pg->ipc_opened[q] = false;
+    }
+    pg->connected = true;
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_buffer_at(wgb_peer_gather *pg, int calls_back, wgb_buffer **out) {
     if (!pg || !out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
-    *out = &pg->view;
+    if (calls_back < 0 || calls_back >= pg->depth || (unsigned)calls_back > pg->epoch)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_buffer_at: the group keeps %d result(s); %d calls back is gone", pg->depth, calls_back);
+    *out = &pg->view[(pg->epoch - (unsigned)calls_back) % (unsigned)pg->depth];
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out) { return wgb_peer_gather_buffer_at(pg, 0, out); }
+
+wgb_status wgb_peer_gather_wait(wgb_pass *pass, wgb_peer_gather *pg, int calls_back) {
+    if (!pass || !pg) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    if (calls_back < 0 || (unsigned)calls_back > pg->epoch) WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_wait: no such call");
+    if (pg->nranks == 1 || pg->epoch == 0) return WGB_OK;
+    DeviceGuard dg(pg->ctx->device);
+    unsigned int *sig = reinterpret_cast<unsigned int *>(pg->local + pg->signal_off());
+    wgb::wait_done_kernel<<<1, 32, 0, pass->stream>>>(sig + wgb::kDoneOff, pg->nranks, pg->rank, pg->epoch - (unsigned)calls_back,
+                                                      pg->timeout_cycles);
+    count_launch(pg->ctx);
+    WGB_CUDA(cudaGetLastError());
     return WGB_OK;
 }
 
 wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
     if (!pg) return WGB_OK;
     DeviceGuard g(pg->ctx->device);
+    // the host-operand form leaves downloads of the gathered buffer on the side streams
     cudaStreamSynchronize(pg->ctx->stream);
+    cudaStreamSynchronize(pg->ctx->comm_stream);
+    if (pg->ctx->h2d_stream) cudaStreamSynchronize(pg->ctx->h2d_stream);
     for (int q = 0; q < pg->nranks; ++q)
-        if (q != pg->rank && pg->peer[q]) cudaIpcCloseMemHandle(pg->peer[q]);
+        if (q != pg->rank && pg->peer[q] && pg->ipc_opened[q]) cudaIpcCloseMemHandle(pg->peer[q]);
     if (pg->local) cudaFree(pg->local);
     wgb_ctx *ctx = pg->ctx;
     delete pg;
@@ -344,11 +427,12 @@ wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
     return WGB_OK;
 }
 
-wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg, const wgb_buffer *m1,
-                                      const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2, wgb_dtype in_dtype,
-                                      wgb_dtype out_dtype, wgb_f32_mode mode) {
+wgb_status wgb_gemm_row_sharded_fused_ex(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg, const wgb_buffer *m1,
+                                         const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
+                                         wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode, uint32_t flags) {
     if (!pass || !pg || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused: null argument");
     if (!pg->connected) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused: peer group is not connected");
+    if (flags & ~(uint32_t)WGB_GATHER_NO_WAIT) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_row_sharded_fused: unknown flags 0x%x", flags);
     wgb_ctx *ctx = pass->ctx;
     const int P = pg->nranks, rank = pg->rank;
     const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
@@ -359,56 +443,72 @@ wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, 
     if (K != s2->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 cols %u vs m2 rows %u)", K, s2->size[0]);
     const size_t os = dtype_size(out_dtype), es = dtype_size(in_dtype);
     const uint64_t panel = (uint64_t)Mloc * N;
-    if (panel * P * os > pg->view.bytes)
+    if (panel * P * os > pg->view[0].bytes)
         WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_gemm_row_sharded_fused: gathered output needs %llu bytes, group holds %zu",
-                 (unsigned long long)(panel * P * os), pg->view.bytes);
+                 (unsigned long long)(panel * P * os), pg->view[0].bytes);
     WGB_TRY(check_view(m1, *s1, es, "sharded gemm m1"));
     WGB_TRY(check_view(m2, *s2, es, "sharded gemm m2"));
     if (Mloc == 0 || N == 0) return WGB_OK;
     DeviceGuard dg(ctx->device);
 
+    const unsigned int epoch = pg->epoch + 1;
+    const size_t buf_off = (size_t)(epoch % (unsigned)pg->depth) * pg->data_bytes;
     FusedGather f;
     f.nranks = P;
     f.rank = rank;
-    f.epoch = ++pg->epoch;
+    f.epoch = epoch;
+    f.timeout = pg->timeout_cycles;
     for (int q = 0; q < P; ++q) {
-        f.peer_c[q] = pg->peer[q];
-        f.done_remote[q] = reinterpret_cast<unsigned int *>(pg->peer[q] + pg->data_bytes) + wgb::kDoneOff;
+        f.peer_c[q] = pg->peer[q] + buf_off;
+        f.done_remote[q] = reinterpret_cast<unsigned int *>(pg->peer[q] + pg->signal_off()) + wgb::kDoneOff;
     }
-    unsigned int *sig = reinterpret_cast<unsigned int *>(pg->local + pg->data_bytes);
+    unsigned int *sig = reinterpret_cast<unsigned int *>(pg->local + pg->signal_off());
     f.ready_local = sig + wgb::kReadyOff;
     f.cta_counter = sig + wgb::kCtaOff;
 
-    if (P > 1) {
-        wgb::signal_ready_kernel<<<1, 32, 0, pass->stream>>>(f);   // "my queue has reached step `epoch`: you may overwrite my buffer"
-        count_launch(ctx);
-    }
     GemmProblem g{};
     g.fused = &f;
     g.tr = tr;
     g.M = Mloc; g.N = N; g.K = K; g.nmats = 1;
-    g.a = m1->ptr; g.b = m2->ptr; g.c = pg->local;
+    g.a = m1->ptr; g.b = m2->ptr; g.c = pg->local + buf_off;
     g.a_off = s1->offset; g.b_off = s2->offset;
     g.c_off = (uint64_t)rank * panel;
     g.lda = s1->stride; g.ldb = s2->stride; g.ldc = Mloc;
     g.sa = s1->stride_mat; g.sb = s2->stride_mat; g.sc = panel;
     g.in_dtype = in_dtype; g.out_dtype = out_dtype;
-    WGB_TRY(gemm_dispatch(pass, g, mode));
+    // A rank that cannot run the peer-storing kernel must fail *before* it tells its peers that it has reached this step:
+    // every later call of every rank would otherwise disagree about the epoch.
+    if (P > 1 && !gemm_fused_eligible(g, mode))
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "fused all-gather needs the tensor-core GEMM path (16-byte aligned operand views, problem >= 96^3, "
+                                      "f32 mode other than SIMT)");
+    pg->epoch = epoch;
     if (P > 1) {
-        wgb::wait_done_kernel<<<1, 32, 0, pass->stream>>>(sig + wgb::kDoneOff, P, rank, f.epoch);   // all panels have landed here
+        // "my buffers for epochs <= value may be overwritten": see the protocol note above
+        wgb::signal_ready_kernel<<<1, 32, 0, pass->stream>>>(f, pg->depth >= 2 ? epoch + 1 : epoch);
         count_launch(ctx);
-        WGB_CUDA(cudaGetLastError());
     }
+    WGB_TRY(gemm_dispatch(pass, g, mode));
+    if (P > 1 && !(flags & WGB_GATHER_NO_WAIT)) WGB_TRY(wgb_peer_gather_wait(pass, pg, 0));   // all panels have landed here
     return WGB_OK;
+}
+
+wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg, const wgb_buffer *m1,
+                                      const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2, wgb_dtype in_dtype,
+                                      wgb_dtype out_dtype, wgb_f32_mode mode) {
+    return wgb_gemm_row_sharded_fused_ex(pass, variant, pg, m1, s1, m2, s2, in_dtype, out_dtype, mode, 0);
 }
 
 // Host-buffer form of the fused sharded GEMM, enqueued (the N > 1 counterpart of wgb_gemm_host_enqueue, abi.cu): this rank's A
 // block and B are uploaded on the upload stream into one of two alternating device slots, the fused GEMM + all-gather runs on
 // the queue once they have landed, and the result leaves on the download stream — this rank's own [M_local x N] panel only
 // (download_all == 0: the ranks of one box assemble C in host memory, every byte crosses a host link once) or the whole gathered
-// cube.  The upload of product i + 1 therefore runs under the GEMM and the download of product i.  Ordering that is specific to
-// the shared gathered buffer: the queue waits for the previous product's download before it lets the next GEMM (and, for whole
-// cube downloads, the peers) overwrite what is being read.
+// cube.  The upload of product i + 1 therefore runs under the GEMM and the download of product i.
+// B crosses the host links once per box when the context has a communicator of the same ranks (wgb_comm_init_rank): every rank
+// uploads only its 1/P column slice and the slices are all-gathered in place over NVLink (ncclAllGather on the queue, between
+// the GEMMs: the persistent GEMM leaves no SM for a concurrent collective, and the step is host-link bound either way).
+// WGB_SHARD_B_UPLOAD=0 restores the whole-B upload on every rank.
+// Ordering specific to the shared gathered buffers: the queue waits for the download of the product whose buffer this call (or,
+// through the ready flag, a peer running one step ahead) is about to overwrite.
 wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_variant variant, wgb_peer_gather *pg, uint32_t M_local,
                                                    uint32_t N, uint32_t K, void *out_host, const void *m1_local_host,
                                                    const void *m2_host, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,
@@ -434,37 +534,29 @@ wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_varian
         hs.evs.push_back(e);
     }
     const size_t b_off = (a_bytes + 255) & ~(size_t)255, slot_bytes = (b_off + b_bytes + 255) & ~(size_t)255;
-    if (ctx->ws[3].bytes < 2 * slot_bytes) {   // growing frees the slots: drain everything that may still use them
-        WGB_CUDA(cudaStreamSynchronize(ctx->h2d_stream));
-        WGB_CUDA(cudaStreamSynchronize(ctx->stream));
-        WGB_CUDA(cudaStreamSynchronize(ctx->comm_stream));
-        hs.pending[0] = hs.pending[1] = false;
-    }
-    void *w = nullptr;
-    WGB_TRY(workspace_reserve(ctx, 3, 2 * slot_bytes, &w));
-    const int slot = (int)(hs.calls++ & 1u);
-    if (hs.pending[slot]) WGB_CUDA(cudaStreamWaitEvent(ctx->h2d_stream, hs.done[slot], 0));   // the slot's last user has finished
-    char *dA = (char *)w + (size_t)slot * slot_bytes, *dB = dA + b_off;
+    char *w = nullptr;
+    int slot = 0;
+    WGB_TRY(host_gemm_slot(ctx, slot_bytes, &w, &slot));
+    char *dA = w, *dB = dA + b_off;
     WGB_CUDA(cudaMemcpyAsync(dA, m1_local_host, a_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    // EXPERIMENTAL, off by default, NOT YET VALIDATED ON HARDWARE (written after this round's GPU budget was spent; profiles/README.md):
-    // with WGB_SHARD_B_UPLOAD=1 and an NCCL communicator on this context, every rank uploads only its 1/P column slice of B and
-    // the slices are all-gathered in place over NVLink on the upload stream, so B crosses the host links once per box instead
-    // of once per rank (the measured e2e bound at N = 8).
-    static const bool want_split_b = env_int("WGB_SHARD_B_UPLOAD", 0) != 0;
     const int P = pg->nranks;
-    const bool split_b = want_split_b && P > 1 && ctx->comm && ctx->comm->comm && ctx->comm->nranks == P && ctx->comm->rank == pg->rank &&
-                         nccl().ok && nccl().AllGather && N % (uint32_t)P == 0;
-    if (split_b) {
-        const size_t slice = b_bytes / (size_t)P;
+    const bool split_b = env_int("WGB_SHARD_B_UPLOAD", 1) != 0 && P > 1 && ctx->comm && ctx->comm->comm && ctx->comm->nranks == P &&
+                         ctx->comm->rank == pg->rank && nccl().ok && nccl().AllGather && N % (uint32_t)P == 0;
+    const size_t slice = b_bytes / (size_t)P;
+    if (split_b)
         WGB_CUDA(cudaMemcpyAsync(dB + (size_t)pg->rank * slice, (const char *)m2_host + (size_t)pg->rank * slice, slice,
                                  cudaMemcpyHostToDevice, ctx->h2d_stream));
-        WGB_NCCL(nccl().AllGather(dB + (size_t)pg->rank * slice, dB, slice, ncclInt8, ctx->comm->comm, ctx->h2d_stream));
-    } else {
+    else
         WGB_CUDA(cudaMemcpyAsync(dB, m2_host, b_bytes, cudaMemcpyHostToDevice, ctx->h2d_stream));
-    }
     WGB_CUDA(cudaEventRecord(hs.evs[0], ctx->h2d_stream));
     WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.evs[0], 0));
-    if (hs.pending[slot ^ 1]) WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.done[slot ^ 1], 0));   // previous download has left the gathered buffer
+    if (split_b) {
+        WGB_NCCL(nccl().AllGather(dB + (size_t)pg->rank * slice, dB, slice, ncclInt8, ctx->comm->comm, ctx->stream));
+        count_launch(ctx);
+    }
+    // the download that last read the buffer about to be handed out (depth 3: two products back, i.e. this slot's own)
+    const int reader = pg->depth == 3 ? slot : slot ^ 1;
+    if (hs.pending[reader]) WGB_CUDA(cudaStreamWaitEvent(ctx->stream, hs.done[reader], 0));
     wgb_buffer bA, bB;
     bA.ctx = bB.ctx = ctx;
     bA.owned = bB.owned = false;
@@ -478,10 +570,11 @@ wgb_status wgb_gemm_row_sharded_fused_host_enqueue(wgb_ctx *ctx, wgb_gemm_varian
     WGB_TRY(wgb_gemm_row_sharded_fused(&pass, variant, pg, &bA, &s1, &bB, &s2, in_dtype, out_dtype, mode));
     WGB_CUDA(cudaEventRecord(hs.evs[1], ctx->stream));
     WGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, hs.evs[1], 0));
+    const char *result = pg->buffer_of(pg->epoch);
     if (download_all)
-        WGB_CUDA(cudaMemcpyAsync(out_host, pg->local, panel_bytes * pg->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
+        WGB_CUDA(cudaMemcpyAsync(out_host, result, panel_bytes * pg->nranks, cudaMemcpyDeviceToHost, ctx->comm_stream));
     else
-        WGB_CUDA(cudaMemcpyAsync(out_host, pg->local + (size_t)pg->rank * panel_bytes, panel_bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
+        WGB_CUDA(cudaMemcpyAsync(out_host, result + (size_t)pg->rank * panel_bytes, panel_bytes, cudaMemcpyDeviceToHost, ctx->comm_stream));
     WGB_CUDA(cudaEventRecord(hs.done[slot], ctx->comm_stream));
     hs.pending[slot] = true;
     return WGB_OK;

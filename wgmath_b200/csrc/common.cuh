@@ -81,7 +81,8 @@ struct wgb_ctx {
     std::atomic<uint64_t> launches{0};
     std::atomic<int> refs{1};            // the caller's handle + one per live buffer / event / pass / graph / peer group (abi.cu)
     wgb::Scratch scratch;
-    wgb::Workspace ws[6];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort
+    wgb::Workspace ws[7];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort, 6: diagnostics
+    uint64_t ws_generation = 0;   // bumped whenever a workspace / scratch block is reallocated (captured graphs hold the old pointers)
     wgb::CommState *comm = nullptr;
     wgb::HostGemmState host_gemm;
     std::mutex mu;
@@ -94,6 +95,7 @@ struct wgb_pass {
     cudaStream_t stream = nullptr;
     wgb_event *end_ts = nullptr;
     int last_gemm_path = 0;
+    int last_tc[WGB_TC_CONFIG_WORDS] = {};   // configuration of the last tcgen05 GEMM launch (wgb_pass_last_gemm_config)
     uint64_t nvtx_range = 0;   // nvtxRangeId_t of the pass label
 };
 
@@ -150,6 +152,10 @@ wgb_status check_view(const wgb_buffer *b, const wgb_view_shape &s, size_t elem_
 // Grow-only device workspace slot; contents are undefined after a grow.
 wgb_status workspace_reserve(wgb_ctx *ctx, int slot, size_t bytes, void **out);
 wgb_status scratch_reserve(wgb_ctx *ctx, size_t partial_floats, size_t counters);
+// One of the two alternating device operand slots of the host-operand GEMMs (abi.cu): slots sit at stable offsets (0 and half of
+// workspace 3), so products of different sizes never overlap a slot that is still in flight; growing drains all three streams.
+// The upload stream is made to wait for the slot's previous user.
+wgb_status host_gemm_slot(wgb_ctx *ctx, size_t slot_bytes, char **base, int *slot);
 // SMs the persistent GEMM leaves free for the NCCL CTAs of an in-flight exchange (0 without a communicator).
 int comm_sm_margin(const wgb_ctx *ctx);
 
@@ -176,6 +182,7 @@ struct FusedGather {
     unsigned int *done_remote[kMaxPeers] = {};  // done array of rank q (we write entry [rank])
     unsigned int *cta_counter = nullptr;     // local: CTAs finished (left at zero)
     unsigned int epoch = 0;
+    long long timeout = 0;                   // flag-wait bound in SM cycles (0: unbounded)
 };
 
 struct GemmProblem {
@@ -212,6 +219,8 @@ wgb_status launch_gemm_simt(wgb_pass *p, const GemmProblem &g);
 // tcgen05 path. `passes`: 1 (bf16 or single-pass tf32) or 3 (3xTF32; operands pre-split).
 bool gemm_tc_eligible(const GemmProblem &g);
 wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, int *path_out);
+// true when gemm_dispatch will run the peer-storing tensor-core kernel for this problem (checked before a fused call signals its peers)
+bool gemm_fused_eligible(const GemmProblem &g, wgb_f32_mode mode);
 
 // column-panel range restriction used by the sharded GEMM (compute only n in [n_begin, n_end))
 wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode);

@@ -11,6 +11,15 @@
 
 namespace wgb {
 
+bool gemm_tc_direct_f32_ok(const GemmProblem &g);   // gemm_tc.cu
+
+bool gemm_fused_eligible(const GemmProblem &g, wgb_f32_mode mode) {
+    const uint64_t work = (uint64_t)g.M * g.N * (uint64_t)g.K;
+    if (work < (uint64_t)96 * 96 * 96 || g.K == 0 || mode == WGB_F32_SIMT || !gemm_tc_eligible(g)) return false;
+    if (g.in_dtype == WGB_F32 && (g.nmats > 65535 || (mode == WGB_F32_TF32 && !gemm_tc_direct_f32_ok(g)))) return false;
+    return true;
+}
+
 wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode) {
     const uint64_t work = (uint64_t)g.M * g.N * (uint64_t)g.K;
     // Below ~64^3 per matrix a tensor-core launch (tensor-map encode + 2 helper kernels for 3xTF32) costs more

@@ -149,7 +149,7 @@ using TmapCache = std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash>;
 
 // 3-D map: dim0 contiguous (d0 elements), dim1 stride s1 elements, dim2 (batch) stride s2 elements.
 wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
-                    uint32_t b0, uint32_t b1, CUtensorMap *out, bool atom32 = false) {
+                    uint32_t b0, uint32_t b1, CUtensorMap *out, bool atom32 = false, bool no_swizzle = false) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if (d2 <= 1) {   // single matrix: the batch stride is never used, but must still be a legal (16-byte multiple) stride
@@ -158,7 +158,7 @@ wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uin
         s2 = d0 > s1 * d1 ? d0 : s1 * d1;
         s2 = (s2 + q - 1) / q * q;
     }
-    TmapKey key{ptr, d0, d1, d2, s1, s2, b0, b1, es | (atom32 ? 0x100u : 0u)};
+    TmapKey key{ptr, d0, d1, d2, s1, s2, b0, b1, es | (atom32 ? 0x100u : 0u) | (no_swizzle ? 0x200u : 0u)};
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!ctx->tmap_cache) ctx->tmap_cache = new TmapCache();
     TmapCache &cache = *static_cast<TmapCache *>(ctx->tmap_cache);
@@ -173,7 +173,7 @@ wgb_status get_tmap(wgb_ctx *ctx, const void *ptr, uint32_t es, uint64_t d0, uin
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(out, es == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(ptr),
                      dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         WGB_FAIL(WGB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu, strides %llu / %llu B, box %u x %u", (int)r,
@@ -194,6 +194,11 @@ void tmap_cache_destroy(wgb_ctx *ctx) {
 static bool aligned_operand(const void *base, uint64_t off, uint64_t ld, uint64_t smat, uint32_t nmats, size_t es) {
     const uint64_t q = 16 / es;
     return (((uintptr_t)base + off * es) & 15u) == 0 && ld % q == 0 && (nmats <= 1 || smat % q == 0);
+}
+
+// single-pass TF32 reads the caller's f32 views in place: both need TMA alignment (3xTF32 re-materialises them dense)
+bool gemm_tc_direct_f32_ok(const GemmProblem &g) {
+    return aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4);
 }
 
 bool gemm_tc_eligible(const GemmProblem &g) {
@@ -273,10 +278,13 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     const bool prep_a = f32 && (passes == 3 || transpose_a), prep_b = f32 && (passes == 3 || transpose_b);
     if (f32 && ((!prep_a && !aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4)) ||
                 (!prep_b && !aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)))) {
+        if (g.fused && g.fused->nranks > 1)   // the FFMA kernel has no peer stores: never drop the all-gather silently
+            WGB_FAIL(WGB_ERR_UNSUPPORTED, "fused all-gather: single-pass TF32 needs 16-byte aligned operand views");
         *path_out = 1;   // single-pass TF32 reads the caller's views directly: needs TMA alignment
         return launch_gemm_simt(p, g);
     }
     if (g.nmats > 65535 && f32) {
+        if (g.fused && g.fused->nranks > 1) WGB_FAIL(WGB_ERR_UNSUPPORTED, "fused all-gather: too many matrices in the batch");
         *path_out = 1;
         return launch_gemm_simt(p, g);
     }
@@ -336,7 +344,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     }
     const bool b_mn = !f32 && g.b_nmajor;   // bf16: MN-major B read in place
 
-    TcMaps maps;
+    TcMaps maps{};
     CUtensorMap &ta = maps.a, &talo = maps.alo, &tb = maps.b, &tblo = maps.blo;
     const bool atom32 = f32 && !tr;                                     // MN-major 32-bit operand A
     const uint32_t a_box0 = tr ? block_k : (uint32_t)(128 / es);       // K-major: 128 B of K; MN-major: one 128 B atom of M
@@ -356,6 +364,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     args.c = (char *)g.c + g.c_off * dtype_size(g.out_dtype);
     args.npeers = 1;
     args.dst[0] = (char *)args.c;
+    args.mbar_timeout = 8000000000ll;
     if (g.fused && g.fused->nranks > 1) {
         const FusedGather &f = *g.fused;
         args.npeers = (uint32_t)f.nranks;
@@ -368,6 +377,8 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         }
         args.ready_local = f.ready_local;
         args.cta_counter = f.cta_counter;
+        args.peer_timeout = f.timeout;
+        args.mbar_timeout = f.timeout > 0 ? f.timeout + 8000000000ll : 0;   // the pipeline stalls behind an epilogue that waits for peers
     }
     args.ldc = g.ldc; args.sc = g.sc;
     args.M = g.M; args.N = g.N; args.K = g.K; args.nmats = g.nmats;
@@ -388,7 +399,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
             // replicas 1..n-1 go to distinct scratch panels (like distinct peers), replica 0 is the real output
             const size_t c_bytes = ((size_t)(g.nmats - 1) * g.sc + (size_t)(g.N - 1) * g.ldc + g.M) * dtype_size(g.out_dtype);
             void *scratch = nullptr;
-            if (workspace_reserve(ctx, 3, (size_t)(fake - 1) * c_bytes, &scratch) == WGB_OK) {
+            if (workspace_reserve(ctx, 6, (size_t)(fake - 1) * c_bytes, &scratch) == WGB_OK) {
                 args.npeers = (uint32_t)fake;
                 for (int r = 1; r < fake; ++r) args.dst[r] = (char *)scratch + (size_t)(r - 1) * c_bytes;
             }
@@ -420,6 +431,26 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         }
     }
 
+    // Epilogue form.  WGB_TC_EPI: 0 = per-lane global stores, 1 = shared-memory staged TMA bulk stores, unset = TMA stores when
+    // the all-gather is fused in (every output block then leaves the SM once per rank of the box).
+    {
+        const size_t os = dtype_size(g.out_dtype);
+        const int want = env_int("WGB_TC_EPI", args.npeers > 1 ? 1 : 0);
+        bool ok = want != 0 && (g.ldc * os) % 16 == 0 && (g.nmats <= 1 || (g.sc * os) % 16 == 0);
+        for (uint32_t d = 0; ok && d < args.npeers; ++d) ok = ((uintptr_t)args.dst[d] & 15u) == 0;
+        if (ok) {
+            for (uint32_t d = 0; d < args.npeers; ++d)
+                WGB_TRY(get_tmap(ctx, args.dst[d], (uint32_t)os, g.M, g.N, g.nmats, g.ldc, g.sc, 128u, (uint32_t)kEpiCols, &maps.dst.m[d],
+                                 false, true));
+            args.epi_tma = 1;
+        }
+    }
+
+    {   // what ran, for wgb_pass_last_gemm_config (tests name every kernel instantiation through it)
+        int *c = p->last_tc;
+        c[0] = f32 ? 1 : 0; c[1] = tr ? 0 : 1; c[2] = b_mn ? 1 : 0; c[3] = bn; c[4] = passes; c[5] = (int)g.out_dtype; c[6] = cg;
+        c[7] = (int)args.epi_tma; c[8] = (int)args.nsplit; c[9] = (int)args.split; c[10] = (int)args.npeers; c[11] = (int)args.total_units;
+    }
     wgb_status st;
     if (!f32) {
         if (g.out_dtype == WGB_F32) {

@@ -58,13 +58,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return done;
 }
-__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, long long limit) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > 8000000000ll) __trap();
+        if (limit > 0 && clock64() - t0 > limit) __trap();
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
+// `limit` (SM cycles, 0 = unbounded) is only read on the slow path: a plain GEMM gives up after a few seconds, a GEMM whose
+// epilogue waits for other GPUs (fused all-gather) must outlast the peer timeout.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, long long limit) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity, limit);
 }
 // One lane of a converged warp (elect.sync): the form the compiler turns into a single predicated UTCHMMA / UTMALDG instead of
 // the vote-and-retry loop it wraps around uniform-datapath instructions in code it must assume divergent.
@@ -93,6 +95,22 @@ __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap 
         "l"(tm), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Bulk tensor store smem -> global (SASS: UTMASTG).  The box is clipped against the tensor's extents, so ragged tiles need no
+// predication; the destination may be a peer GPU's memory mapped over NVLink.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *tm, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1),
+                 "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// at most N of this thread's bulk groups still have shared-memory reads outstanding
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// all of this thread's bulk groups have completed (their global writes are performed)
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -221,6 +239,7 @@ struct TcArgs {
     // tail N-split (default): tiles [full_tiles, total_tiles) are instead cut into `nsplit` column strips of `tail_bn`
     // columns, each a complete (narrower) output tile: the last wave fills the machine and needs no fix-up.
     uint32_t nsplit, tail_bn, idesc_tail;
+    uint32_t epi_tma;        // 1: the epilogue stages 128 x 32 blocks in shared memory and leaves with TMA bulk stores (dst maps)
     int ep_op;               // fused element-wise epilogue (-1: none): out = acc (op) e
     const void *ep;          // operand view base (element 0 of the view), element type = TOut
     uint64_t ep_ld, ep_sm;
@@ -230,6 +249,8 @@ struct TcArgs {
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
     uint32_t npeers, my_rank, epoch, handshake;
+    long long peer_timeout;                   // bound of the ready-flag wait in SM cycles (0: unbounded)
+    long long mbar_timeout;                   // bound of every mbarrier wait in SM cycles (0: unbounded)
     char *dst[kMaxPeers];                     // where this rank's panel lives in rank d's gathered buffer
     unsigned int *ready_local;                // ready_local[q] >= epoch: rank q's buffer may be overwritten
     unsigned int *done_remote[kMaxPeers];     // rank q's done array; entry [my_rank] <- epoch when all stores are out
@@ -244,6 +265,13 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+// Output tensor maps of the TMA-store epilogue: one per destination (the local buffer; with the fused all-gather also this
+// rank's panel inside every peer's gathered buffer).  dims = {M, N, nmats}, box = {128 rows, kEpiCols columns}, no swizzle.
+struct TcDstMaps {
+    CUtensorMap m[kMaxPeers];
+};
+constexpr int kEpiCols = 32;   // columns per staged block = one tcgen05.ld.32x32b.x32
 
 struct WorkUnit {
     uint32_t tile, kb0, kb1, split_idx;   // split_idx == 0xFFFFFFFF: whole K range
@@ -326,7 +354,8 @@ template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmBlot, const TcArgs args) {
+               const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ CUtensorMap tmBlot,
+               const __grid_constant__ TcDstMaps dmaps, const TcArgs args) {
     using Cfg = TcCfg<BN, PASSES, CG>;
     constexpr int ES = KIND == 0 ? 2 : 4;                 // operand element size
     constexpr int BLOCK_K = kRowBytes / ES;               // 64 bf16 / 32 tf32
@@ -337,8 +366,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int A_ATOM_BYTES = BLOCK_K * kRowBytes;     // one atom column: BLOCK_K rows of 128 B
     constexpr uint32_t IDESC = make_idesc(KIND, A_MN, B_MN, kBlockM * CG, BN);
     static_assert(!B_MN || KIND == 0, "MN-major B is implemented for 16-bit operands only");
-    constexpr int STAGES = Cfg::STAGES;
     constexpr bool CHUNKED = PASSES == 3;
+    // TMA-store epilogue: two staging blocks of [kEpiCols columns][128 rows] behind the barriers; the ring gives up a stage
+    // where the two do not fit beside it (BLOCK_N 256 x CTA pairs: 7 -> 6 stages).
+    constexpr int STG_BYTES = kBlockM * kEpiCols * (int)sizeof(TOut);
+    constexpr int STAGES_EPI_RAW = (kSmemLimit - Cfg::BAR_BYTES - 1024 - 2 * STG_BYTES) / Cfg::STAGE_BYTES;
+    constexpr int STAGES_EPI = STAGES_EPI_RAW < Cfg::STAGES ? STAGES_EPI_RAW : Cfg::STAGES;
+    static_assert(STAGES_EPI >= 2, "pipeline too shallow beside the epilogue staging blocks");
+    const bool tma_epi = args.epi_tma != 0;
+    const int STAGES = tma_epi ? STAGES_EPI : Cfg::STAGES;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle
@@ -350,6 +386,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
     uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
     volatile uint32_t *split_flag = tmem_ptr_smem + 1;   // epilogue-warps-only broadcast slot
+    uint8_t *staging = reinterpret_cast<uint8_t *>(bars) + Cfg::BAR_BYTES;   // [2][kEpiCols][128] TOut (TMA-store epilogue only)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned long long tr_entry = 0;
@@ -367,6 +404,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             prefetch_tmap(&tmBlo);
             prefetch_tmap(&tmBlot);
         }
+        if (tma_epi)
+            for (uint32_t d = 0; d < args.npeers; ++d) prefetch_tmap(&dmaps.m[d]);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -410,7 +449,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const CUtensorMap *tb_hi = wu.narrow ? &tmBt : &tmB, *tb_lo = wu.narrow ? &tmBlot : &tmBlo;
             int k0 = (int)(wu.kb0 * BLOCK_K);
             for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb, k0 += BLOCK_K) {
-                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1);
+                mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, args.mbar_timeout);
                 if (elect_one()) {
                     const uint32_t fb = smem_u32(full_bar + stage);
                     if (leader) mbar_arrive_expect_tx(fb, stage_tx);
@@ -471,12 +510,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 while (kb < wu.kb1) {
                     // one TMEM accumulation chain: the whole K range, or kChunkKb k-blocks for 3xTF32
                     const uint32_t chain_end = CHUNKED ? min(wu.kb1, kb + (uint32_t)kChunkKb) : wu.kb1;
-                    mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1);   // epilogue has drained this accumulator
+                    mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1, args.mbar_timeout);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     uint32_t accum = 0;   // the first MMA of a chain overwrites the accumulator
                     for (; kb < chain_end; ++kb) {
-                        mbar_wait(smem_u32(full_bar + stage), phase);
+                        mbar_wait(smem_u32(full_bar + stage), phase, args.mbar_timeout);
                         tc_fence_after();
                         if (tr_pending) {
                             tr_pending = false;
@@ -530,11 +569,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (r != args.my_rank) {
                         const long long t0 = clock64();
                         while ((int)(ld_acquire_sys(args.ready_local + r) - args.epoch) < 0)
-                            if (clock64() - t0 > 20000000000ll) __trap();
+                            if (args.peer_timeout > 0 && clock64() - t0 > args.peer_timeout) __trap();
                     }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         const uint32_t lane_base = tmem_base + ((q * 32u) << 16);
+        uint32_t staged = 0;   // blocks staged so far by this CTA (selects the staging buffer; uniform over the 128 threads)
         for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
             const WorkUnit wu = decode_unit(u, args, BN);
             uint32_t bt, mt, nt;
@@ -554,7 +594,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t nchains = CHUNKED ? (nkb + kChunkKb - 1) / kChunkKb : 1u;
             for (uint32_t ch = 0; ch < nchains; ++ch) {
                 const bool final_chain = ch + 1 == nchains;
-                mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase);
+                mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase, args.mbar_timeout);
                 tc_fence_after();
                 const uint32_t taddr = lane_base + acc * BN;
                 const uint32_t tsum = lane_base + 2 * BN;   // running sum of the chains (3xTF32 only)
@@ -585,6 +625,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (split_unit) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
+                    } else if (tma_epi) {
+                        // TMEM -> registers -> shared memory block [32 columns][128 rows] -> one bulk tensor store per
+                        // destination.  Whole 256 B (bf16) / 512 B (f32) column segments leave the SM instead of per-lane
+                        // 2 / 4-byte stores, and the epilogue warps issue 32 st.shared per block whatever the number of peers.
+                        if (args.ep_op >= 0 && row_ok) {
+                            const TOut *erow = reinterpret_cast<const TOut *>(args.ep) + (uint64_t)bt * args.ep_sm + row;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const uint32_t col = n0 + c * 32 + i;
+                                if (col < args.N)
+                                    v[c & 1][i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(v[c & 1][i]), erow + (uint64_t)col * args.ep_ld));
+                            }
+                        }
+                        uint8_t *blk = staging + (staged & 1u) * STG_BYTES;
+                        ++staged;
+                        // the stores issued from this block two blocks ago have read it (the newest group may still be reading
+                        // the other block)
+                        if (threadIdx.x == 128) bulk_wait_read<1>();
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        TOut *sp = reinterpret_cast<TOut *>(blk) + row_in_cta;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) store_out<TOut>(sp + i * kBlockM, __uint_as_float(v[c & 1][i]));
+                        fence_proxy_async_smem();
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                        if (threadIdx.x == 128) {
+                            const int r0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM), c0 = (int)(n0 + c * 32);
+                            for (uint32_t d = 0; d < args.npeers; ++d) tma_store_3d(&dmaps.m[d], smem_u32(blk), r0, c0, (int)bt);
+                            bulk_commit();
+                        }
+                        __syncwarp();
                     } else if (row_ok) {
                         if (args.ep_op >= 0) {   // fused OpAssign: out = acc (op) e, e read coalesced like the store
                             const TOut *erow = reinterpret_cast<const TOut *>(args.ep) + (uint64_t)bt * args.ep_sm + row;
@@ -654,6 +724,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
         if (args.trace && leader && threadIdx.x == 128 && cluster_id < 256) args.trace[(size_t)cluster_id * 8 + 6] = globaltimer_ns();
+        if (tma_epi && threadIdx.x == 128) {
+            // every bulk store of this CTA has been performed (not merely read out of shared memory) before the CTA may exit
+            // or count itself as done; order the async-proxy writes before the generic-proxy flag traffic below
+            bulk_wait_all();
+            fence_proxy_async_all();
+        }
         if (args.handshake) {
             // all of this CTA's peer stores are out: make them visible system-wide, count the CTA, and let the last CTA of
             // the grid publish "rank my_rank's panel is complete" to every peer
@@ -688,6 +764,7 @@ inline int env_int(const char *name, int dflt) {
 
 struct TcMaps {
     CUtensorMap a, alo, b, blo, bt, blot;   // operands (hi / lo), and B with the narrow box of the tail strips
+    TcDstMaps dst;                          // outputs (TMA-store epilogue only)
 };
 
 template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
@@ -719,7 +796,7 @@ wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = env_int("WGB_TC_PDL", 1) != 0 ? 2 : 1;
-    WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.alo, m.b, m.blo, m.bt, m.blot, args));
+    WGB_CUDA(cudaLaunchKernelEx(&cfg, kern, m.a, m.alo, m.b, m.blo, m.bt, m.blot, m.dst, args));
     count_launch(p->ctx);
     return WGB_OK;
 }

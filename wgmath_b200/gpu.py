@@ -119,6 +119,13 @@ class ComputePass:
         check(lib().wgb_pass_last_gemm_path(self._h, ctypes.byref(p)))
         return p.value
 
+    def last_gemm_config(self) -> dict:
+        """The tcgen05 kernel instantiation / plan of the last GEMM on this pass (wgb_pass_last_gemm_config)."""
+        c = (ctypes.c_int * 12)()
+        check(lib().wgb_pass_last_gemm_config(self._h, c))
+        keys = ("kind", "a_mn", "b_mn", "bn", "passes", "out_dtype", "cg", "epi_tma", "nsplit", "splitk", "dests", "units")
+        return dict(zip(keys, list(c)))
+
     def __enter__(self):
         return self
 

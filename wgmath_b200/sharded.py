@@ -65,16 +65,22 @@ def init_comm(device, dist=None, rank: int = 0, world: int = 1) -> None:
 
 
 class PeerGather:
-    """The gathered output buffer of every rank, mapped into every other rank through CUDA IPC, plus the flag block
-    the fused GEMM + all-gather kernel signals through (wgb_peer_gather_*).  `tensor` is the local gathered cube
-    [m_local, N, P] as a GpuTensor."""
+    """The gathered output buffers of every rank, mapped into every other rank, plus the flag block the fused GEMM + all-gather
+    kernel signals through (wgb_peer_gather_*).  `tensor` is the gathered cube [m_local, N, P] of the most recent call.
 
-    def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16"):
-        self._device, self.rank, self.world = device, rank, world
-        nbytes = world * m_local * N * (2 if dtype == "bf16" else 4)
+    depth = number of gathered buffers the calls rotate through (include/wgb200.h: 1 = lock step, 2 = peers may run one step
+    ahead, 3 = additionally the wait may trail the GEMMs by one call).  One process per GPU: handles travel through `dist`
+    (torch.distributed, any backend).  `PeerGather.local_group` builds all ranks inside one process instead."""
+
+    def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16", depth: int = 1, _connect=True):
+        self._device, self.rank, self.world, self.depth = device, rank, world, depth
+        self._shape, self._dtype = (m_local, N, world), dtype
+        self._nbytes = world * m_local * N * (2 if dtype == "bf16" else 4)
         h = ctypes.c_void_p()
-        check(lib().wgb_peer_gather_create(device._h, world, rank, nbytes, ctypes.byref(h)))
+        check(lib().wgb_peer_gather_create_ex(device._h, world, rank, self._nbytes, depth, ctypes.byref(h)))
         self._h = h
+        if not _connect:
+            return
         mine = (ctypes.c_char * IPC_HANDLE_BYTES)()
         check(lib().wgb_peer_gather_export(h, mine))
         handles = [None] * world
@@ -84,10 +90,32 @@ class PeerGather:
             handles = [bytes(mine)]
         blob = (ctypes.c_char * (IPC_HANDLE_BYTES * world)).from_buffer_copy(b"".join(handles))
         check(lib().wgb_peer_gather_connect(h, blob))
+
+    @classmethod
+    def local_group(cls, devices, m_local: int, N: int, dtype: str = "bf16", depth: int = 1) -> "List[PeerGather]":
+        """All ranks in this process, one device handle (context) per rank — wgb_peer_gather_connect_local.  The devices may be
+        one and the same GPU: the complete protocol (peer stores, ready / done flags, epochs) then runs on a single-GPU box."""
+        world = len(devices)
+        groups = [cls(dev, None, r, world, m_local, N, dtype, depth, _connect=False) for r, dev in enumerate(devices)]
+        arr = (ctypes.c_void_p * world)(*[g._h for g in groups])
+        for g in groups:
+            check(lib().wgb_peer_gather_connect_local(g._h, arr))
+        return groups
+
+    def tensor_at(self, calls_back: int = 0) -> GpuTensor:
+        """The gathered cube written by the call `calls_back` calls ago (while the group still keeps it)."""
         bh = ctypes.c_void_p()
-        check(lib().wgb_peer_gather_buffer(h, ctypes.byref(bh)))
+        check(lib().wgb_peer_gather_buffer_at(self._h, calls_back, ctypes.byref(bh)))
         # the group owns the wgb_buffer: never destroyed from the Python side
-        self.tensor = GpuTensor((m_local, N, world), _BorrowedBuffer(device, bh, nbytes), dtype)
+        return GpuTensor(self._shape, _BorrowedBuffer(self._device, bh, self._nbytes), self._dtype)
+
+    @property
+    def tensor(self) -> GpuTensor:
+        return self.tensor_at(0)
+
+    def wait(self, pass_, calls_back: int = 0) -> None:
+        """Queue the wait for every peer's panel of the call `calls_back` calls ago (wgb_peer_gather_wait)."""
+        check(lib().wgb_peer_gather_wait(pass_._h, self._h, calls_back))
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -123,12 +151,15 @@ class RowShardedGemm:
                                          int(f32_mode), n_chunks))
 
     def dispatch_fused(self, device, shapes, pass_, group: "PeerGather", m1_local, m2, variant=GemmVariant.Gemm,
-                       f32_mode=F32Mode.Auto) -> None:
-        """Same result in group.tensor, the all-gather fused into the GEMM epilogue (peer stores over NVLink)."""
+                       f32_mode=F32Mode.Auto, wait: bool = True) -> None:
+        """Same result in group.tensor, the all-gather fused into the GEMM epilogue (peer stores over NVLink).
+        wait=False (WGB_GATHER_NO_WAIT): only this rank's GEMM + peer stores are queued; call group.wait(pass_, calls_back)
+        before the gathered cube is read."""
         m1, b = as_view(m1_local, 3), as_view(m2, 3)
         s1, s2 = shapes.get(device, m1.shape()).to_c(), shapes.get(device, b.shape()).to_c()
-        check(lib().wgb_gemm_row_sharded_fused(pass_._h, int(variant), group._h, m1.buffer()._h, ctypes.byref(s1), b.buffer()._h,
-                                               ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[group.tensor.dtype], int(f32_mode)))
+        check(lib().wgb_gemm_row_sharded_fused_ex(pass_._h, int(variant), group._h, m1.buffer()._h, ctypes.byref(s1), b.buffer()._h,
+                                                  ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[group._dtype], int(f32_mode),
+                                                  0 if wait else 1))
 
 
     def enqueue_host_fused(self, device, group: "PeerGather", m_local: int, N: int, K: int, out_host, m1_local_host, m2_host,
@@ -141,104 +172,4 @@ class RowShardedGemm:
             return x if isinstance(x, ctypes.c_void_p) else x.ctypes.data_as(ctypes.c_void_p)
         check(lib().wgb_gemm_row_sharded_fused_host_enqueue(device._h, int(variant), group._h, m_local, N, K, ptr(out_host),
                                                             ptr(m1_local_host), ptr(m2_host), _DTYPE_CODE[in_dtype],
-                                                            _DTYPE_CODE[group.tensor.dtype], int(f32_mode), 1 if download_all else 0))
-
-
-def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks):
-    """bench.py's N > 1 leg: bf16 (4096*P)^3, row-sharded, all-gather of C; returns the JSON fields."""
-    dev = gpu.device()
-    n = 4096 * ngpu
-    m_local = n // ngpu
-    ST = w.BufferUsages.STORAGE | w.BufferUsages.COPY_SRC | w.BufferUsages.COPY_DST
-    import os
-    mode = os.environ.get("WGB_SHARD_MODE", "fused")                     # "fused" (peer stores) or "nccl"
-    a = w.TensorBuilder.matrix(m_local, n, ST).build(dev, "bf16")       # my row block of A
-    b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")             # B replicated
-    group = None
-    if mode == "fused":
-        group = PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16")
-        c = group.tensor
-    else:
-        init_comm(dev, dist, rank, ngpu)
-        c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
-    enc = dev.create_command_encoder()
-    with enc.compute_pass("init", None) as p:
-        w.fill_uniform(dev, p, a, O.SEED_BASE + 1, row0=rank * m_local)  # element (i, j) independent of the sharding
-        w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
-    dev.poll_wait()
-    op = RowShardedGemm(dev)
-    if group is not None:
-        step_fn = lambda p, i: op.dispatch_fused(dev, shapes, p, group, a, b)    # noqa: E731
-    else:
-        step_fn = lambda p, i: op.dispatch(dev, shapes, p, c, a, b)             # noqa: E731
-    sec, launches = timed(step_fn, args.steps, args.warmup)
-    flops = 2.0 * n * n * n
-    value = flops * args.steps / sec / 1e12
-    ms_step = sec * 1e3 / args.steps
-    long_run = sec > 1.0
-    peak = (peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]) * ngpu
-    comm_bytes = (ngpu - 1) * m_local * n * 2
-    kname = ("gemm_tc<bf16> (tcgen05) with the all-gather of C fused into the epilogue (peer stores over NVLink)" if group is not None
-             else "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)")
-    roof = {"bound": "tensor", "kernel": kname,
-            "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
-            "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
-            "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
-            "nvlink_floor_ms": comm_bytes / 770e9 * 1e3}
-    # e2e: HOST buffers in, HOST buffer out, through the C ABI, every step: this rank's A block and B go up, the sharded GEMM +
-    # gather runs, the result comes down.
-    # (a) fused mode: wgb_gemm_row_sharded_fused_host_enqueue — products queued back to back, upload of product i + 1 under the
-    #     GEMM / download of product i; each rank downloads its own [M/P x N] panel, so the ranks of the box assemble C in host
-    #     memory and every byte of C crosses a host link once
-    # (b) separate blocking calls (write A, write B, dispatch, read the whole gathered cube on every rank) — the sequence of the
-    #     reference's tests, kept as `separate_calls`
-    L = lib()
-    abytes, bbytes, cbytes = m_local * n * 2, n * n * 2, n * n * 2
-    pbytes = m_local * n * 2
-    ha, hb, hc, hp0, hp1 = (ctypes.c_void_p() for _ in range(5))
-    for h, nb in ((ha, abytes), (hb, bbytes), (hc, cbytes), (hp0, pbytes), (hp1, pbytes)):
-        check(L.wgb_host_alloc(nb, ctypes.byref(h)))
-    check(L.wgb_buffer_read(dev._h, a.buffer()._h, 0, ha, abytes))
-    check(L.wgb_buffer_read(dev._h, b.buffer()._h, 0, hb, bbytes))
-    e2e_steps = max(2, min(args.steps, 5))
-
-    def e2e_seq_step(p, i):
-        check(L.wgb_buffer_write(dev._h, a.buffer()._h, 0, ha, abytes))
-        check(L.wgb_buffer_write(dev._h, b.buffer()._h, 0, hb, bbytes))
-        step_fn(p, i)
-        check(L.wgb_buffer_read(dev._h, c.buffer()._h, 0, hc, cbytes))
-    seq_sec, _ = timed(e2e_seq_step, e2e_steps, 1)
-    seq = {"value": flops * e2e_steps / seq_sec / 1e12, "ms_per_step": seq_sec * 1e3 / e2e_steps,
-           "h2d_bytes_per_step": (abytes + bbytes) * ngpu, "d2h_bytes_per_step": cbytes * ngpu,
-           "call": "wgb_buffer_write x2 + sharded dispatch + wgb_buffer_read of the whole gathered cube on every rank"}
-    if group is not None:
-        # experimental (off by default, see comm.cu): every rank uploads 1/P of B, the slices are all-gathered over NVLink
-        split_b = os.environ.get("WGB_SHARD_B_UPLOAD", "0") not in ("", "0")
-        if split_b:
-            init_comm(dev, dist, rank, ngpu)
-
-        def e2e_step(p, i):
-            op.enqueue_host_fused(dev, group, m_local, n, n, hp0 if i % 2 == 0 else hp1, ha, hb)
-        e2e_sec, _ = timed(e2e_step, e2e_steps, 2, before_end=lambda: check(L.wgb_gemm_host_flush(dev._h)))
-        e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s",
-               "h2d_bytes_per_step": abytes * ngpu + (bbytes if split_b else bbytes * ngpu),
-               "d2h_bytes_per_step": pbytes * ngpu, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3 / e2e_steps,
-               "b_upload": "1/P slice per rank + NCCL all-gather over NVLink (WGB_SHARD_B_UPLOAD=1)" if split_b else "whole B on every rank",
-               "call": "wgb_gemm_row_sharded_fused_host_enqueue per step on every rank (pinned host buffers; A block + B up, fused "
-                       "GEMM + all-gather, this rank's panel of C down: the box's host memory ends with all of C), closed by "
-                       "wgb_gemm_host_flush", "separate_calls": seq}
-    else:
-        e2e = {"value": seq["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": seq["h2d_bytes_per_step"],
-               "d2h_bytes_per_step": seq["d2h_bytes_per_step"], "steps": e2e_steps, "ms_per_step": seq["ms_per_step"], "call": seq["call"]}
-    for h in (ha, hb, hc, hp0, hp1):
-        L.wgb_host_free(h)
-    if group is not None and split_b:
-        dev.poll_wait()
-        lib().wgb_comm_destroy(dev._h)
-    if dist is not None:
-        dist.barrier()
-    if group is not None:
-        group.close()
-    else:
-        lib().wgb_comm_destroy(dev._h)
-    return value, ms_step, launches, roof, e2e, "bf16"
+                                                            _DTYPE_CODE[group._dtype], int(f32_mode), 1 if download_all else 0))
