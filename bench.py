@@ -54,6 +54,35 @@ def load_peaks():
     return dict(FALLBACK_PEAKS) | {"source": "fallback"}
 
 
+def traffic_from_profile(kernel_substr: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, read from the committed summary of
+    the `ncu --set full` capture under profiles/ (newest round first).  Returns (bytes, file) or (None, None)."""
+    import glob
+    import re
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_tc_bf16_4096_ncu.txt")), reverse=True):
+        rd = wr = None
+        in_kernel = False
+        for line in open(path):
+            if line.startswith("## "):
+                if rd is not None and wr is not None:
+                    break
+                in_kernel = kernel_substr in line
+                continue
+            if not in_kernel:
+                continue
+            m = re.match(r"\s+DRAM bytes (read|written)\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                v = float(m.group(2)) * unit.get(m.group(3), 1.0)
+                if m.group(1) == "read":
+                    rd = v
+                else:
+                    wr = v
+        if rd is not None and wr is not None:
+            return rd + wr, os.path.relpath(path, ROOT)
+    return None, None
+
+
 # ------------------------------------------------------------------------------- NVML clocks
 class ClockSampler:
     """Samples SM clock + throttle reasons during timed regions (B200_PROFILING.md clocks line, via NVML)."""
@@ -61,7 +90,7 @@ class ClockSampler:
                0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
-        self.samples, self.reasons, self.max_mhz, self.ok = [], set(), None, False
+        self.samples, self.power, self.reasons, self.max_mhz, self.ok = [], [], set(), None, False
         self._active = threading.Event()
         self._stop = threading.Event()
         try:
@@ -82,6 +111,7 @@ class ClockSampler:
             if self._active.is_set():
                 try:
                     self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
                         else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
                     for bit, name in self.REASONS.items():
@@ -100,10 +130,21 @@ class ClockSampler:
     def __exit__(self, *a):
         self._active.clear()
 
-    def summary(self):
+    def mark(self):
+        """Start of a window: summary(since=mark) describes only the samples taken after it."""
+        return len(self.samples), set(self.reasons)
+
+    def summary(self, since=None):
+        if since is not None and self.ok:
+            n0, before = since
+            smp, pw = self.samples[n0:], self.power[n0:]
+            return {"sm_mhz": float(np.median(smp)) if smp else None, "sm_mhz_min": float(min(smp)) if smp else None,
+                    "sm_max_mhz": self.max_mhz, "power_w_median": float(np.median(pw)) if pw else None,
+                    "power_w_max": float(max(pw)) if pw else None, "reasons": sorted(self.reasons), "samples": len(smp)}
         if not self.ok:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "error": getattr(self, "err", "nvml unavailable")}
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "power_w_max": float(max(self.power)) if self.power else None,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
@@ -289,28 +330,46 @@ def main_gpu(args):
         flops = 2.0 * n * n * n
         nsets = 4  # 4 x (32 + 32 + 32 MiB) = 384 MiB > L2
         sets = []
-        enc = dev.create_command_encoder()
-        with enc.compute_pass("init", None) as p:
-            for s in range(nsets):
-                a = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
-                b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
-                c = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
-                w.fill_uniform(dev, p, a, O.SEED_BASE + 1)
-                w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
-                sets.append((a, b, c))
-        dev.poll_wait()
+
+        def make_sets():
+            enc = dev.create_command_encoder()
+            with enc.compute_pass("init", None) as p:
+                for s in range(nsets):
+                    a = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
+                    b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
+                    c = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")
+                    w.fill_uniform(dev, p, a, O.SEED_BASE + 1)
+                    w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
+                    sets.append((a, b, c))
+            dev.poll_wait()
+        make_sets()
 
         def step(p, i):
             a, b, c = sets[i % nsets]
             gemm.dispatch(dev, shapes, p, c, a, b)
+        main_mark = sampler.mark()
         sec, launches = timed(step, args.steps, args.warmup)
+        clocks_main = sampler.summary(since=main_mark)
         ms_step = sec * 1e3 / args.steps
         value = flops * args.steps / sec / 1e12
         enc = dev.create_command_encoder()
         with enc.compute_pass("path", None) as p:
             step(p, 0)
             gemm_path = p.last_gemm_path()
+            gemm_cfg = p.last_gemm_config()
         dev.poll_wait()
+        # ---- parity of what was just timed: sampled rows of C (set 0: bf16 in, bf16 OUT, random operands) against float64 on
+        # the same bf16-rounded inputs, the 1e-2 bound of BASELINE.json; a mismatch fails the run
+        a0, b0, c0 = sets[0]
+        rows = np.array([0, 1, 127, 128, 2049, 4095])
+        got = O.bf16_from_bits(c0.read()).reshape(n, n).T[rows].astype(np.float64)
+        A64 = np.stack([O.to_bf16_rne(O.uniform(O.SEED_BASE + 1, 1, n, row0=int(r))) for r in rows]).astype(np.float64)
+        B64 = O.to_bf16_rne(O.uniform(O.SEED_BASE + 2, n, n)).reshape(n, n).T.astype(np.float64)
+        ref = A64 @ B64
+        perr = float(np.max(np.abs(got - ref) / np.abs(ref)))
+        parity = {"checked": f"{len(rows)} rows x {n} columns of the timed product (bf16 out) vs float64 on the same bf16-rounded inputs",
+                  "max_rel_err": perr, "tol": 1e-2, "ok": bool(perr < 1e-2)}
+        del A64, B64, ref, got
 
         # ---- e2e: HOST buffers in, HOST buffer out, through the C ABI; every step uploads A and B and downloads C.
         # (a) wgb_gemm_host_enqueue: products queued back to back (wgpu's submit-now / read-later model); the download of
@@ -349,12 +408,15 @@ def main_gpu(args):
 
         dtype = "bf16"
         peak = peaks["bf16_tflops"] if sec < 1.0 else peaks["bf16_tflops_sustained"]
-        roof = {"bound": "tensor", "kernel": {2: "gemm_tc<bf16> (tcgen05)", 1: "gemm_simt (FFMA)"}.get(gemm_path, f"path {gemm_path}"),
+        kname = (f"gemm_tc_kernel<{gemm_cfg['kind']}, {gemm_cfg['a_mn']}, {gemm_cfg['b_mn']}, {gemm_cfg['bn']}, {gemm_cfg['passes']}, "
+                 f"{'__nv_bfloat16' if gemm_cfg['out_dtype'] == 1 else 'float'}, {gemm_cfg['cg']}>") if gemm_path >= 2 else "gemm_simt (FFMA)"
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of exactly this instantiation, parsed from the committed
+        # summary of the `ncu --set full` capture (algorithmic A + B + C = 100.7 MB)
+        traffic, traffic_src = traffic_from_profile(kname) if gemm_path >= 2 else (None, None)
+        roof = {"bound": "tensor", "kernel": kname + (" (tcgen05)" if gemm_path >= 2 else ""),
                 "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
                 "peak_source": f"{peaks['source']} ({'burst' if sec < 1.0 else 'sustained'})",
-                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full
-                # capture profiles/r1_gemm_tc_bf16_4096_ncu.txt (88.5 MB + 14.3 MB; algorithmic A + B + C = 100.7 MB)
-                "traffic": 102.8e6 if gemm_path == 2 else None, "traffic_unit": "bytes per launch (ncu)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "traffic_source": traffic_src,
                 "algorithmic": "2*M*N*K flop per launch"}
         e2e = {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": 2 * hbytes, "d2h_bytes_per_step": hbytes,
                "steps": e2e_steps,
@@ -365,31 +427,250 @@ def main_gpu(args):
                                  "call": "wgb_gemm_host (one blocking call per product)"},
                "separate_calls": {"value": e2e_val_seq, "ms_per_step": e2e_sec2 * 1e3 / e2e_steps,
                                   "call": "wgb_buffer_write x2 + wgb_gemm_ex + wgb_buffer_read"}}
+        secondary = None
         if not args.no_extras:
             sets.clear()
             extra = run_extras(w, O, gpu, shapes, timed, peaks, timed_graph)
+            # the other BASELINE configs in top-level form (the driver keeps top-level keys): configs[3] GEMV GB/s vs the
+            # measured copy bandwidth, configs[1] the f32 sweep's extremes
+            l12 = {r["op"]: r for r in extra["level12"]}
+            x3 = [r for r in extra["gemm_f32"] if r["mode"] == "3xtf32"]
+            secondary = {
+                "gemv_65536x4096": {"bound": "hbm", "achieved": l12["gemv 65536x4096"]["gbs"], "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                    "frac": l12["gemv 65536x4096"]["frac_of_hbm"], "ms": l12["gemv 65536x4096"]["ms"]},
+                "gemv_tr_65536x4096": {"bound": "hbm", "achieved": l12["gemv_tr 65536x4096"]["gbs"], "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                       "frac": l12["gemv_tr 65536x4096"]["frac_of_hbm"], "ms": l12["gemv_tr 65536x4096"]["ms"]},
+                "level1_worst": min(({"op": r["op"], "gbs": r["gbs"], "frac": r["frac_of_hbm"]} for r in extra["level12"]), key=lambda r: r["frac"]),
+                "gemm_f32_3xtf32": {str(r["n"]): {"tflops": r["tflops"], "frac_of_tf32_peak_div3": r["frac_of_tf32_peak"], "path": r["path"]} for r in x3},
+                "gemm_f32_3xtf32_worst_frac": min(r["frac_of_tf32_peak"] for r in x3),
+                "peak_source": peaks["source"]}
+        # ---- sustained: the same GEMM back to back for >= 2 s (power-limited regime), against the sustained cuBLAS peak.  Last
+        # of the GPU work, so that no other measurement of this run starts on a part that is already at its power limit.
+        if not sets:
+            make_sets()
+        sus_steps = max(200, int(2.2 / (ms_step / 1e3)))
+        mark = sampler.mark()
+        sus_sec, _ = timed(step, sus_steps, 3)
+        sus_val = flops * sus_steps / sus_sec / 1e12
+        roof["sustained"] = {"value": sus_val, "unit": "TFLOP/s", "seconds": sus_sec, "steps": sus_steps,
+                             "peak": peaks["bf16_tflops_sustained"], "frac": sus_val / peaks["bf16_tflops_sustained"],
+                             "peak_source": f"{peaks['source']} (sustained)", "clocks": sampler.summary(since=mark)}
+        sets.clear()
         cpu_tf, cores, desc, _, _ = cpu_gemm_sample(10.0)
         cpu = {"value": cpu_tf, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": desc}
     else:
-        from wgmath_b200 import sharded
-        res = sharded.bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks)
-        value, ms_step, launches, roof, e2e, dtype = res
+        res = bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, sampler)
+        value, ms_step, launches, roof, e2e, dtype, parity, wl_extra, clocks_main = res
         cpu = None
+        secondary = None
 
     if rank == 0:
         line = {"metric": "gemm_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": ngpu, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": workload_config(ngpu),
-                "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof}
+                "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+                "config": workload_config(ngpu) | (wl_extra if ngpu > 1 else {}),
+                "clocks": clocks_main | {"window": "the timed region of `value`", "all_timed_regions": sampler.summary()}, "e2e": e2e,
+                "gpu_launches": int(launches), "roofline": roof, "parity": parity}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if secondary is not None:
+            line["roofline_secondary"] = secondary
         if extra:
             line["extra"] = extra
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity["ok"]:
+        print(f"bench.py: PARITY FAILURE on rank {rank}: {parity}", file=sys.stderr)
+        return 3
     return 0
+
+
+def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, sampler):
+    """N > 1: bf16 (4096*P)^3, rank p owns the row block p of A and of C, B replicated, the all-gather of C fused into the GEMM
+    epilogue (TMA bulk stores into every rank's gathered buffer over NVLink).  Two timings of the same K steps:
+      pipelined (the headline `value`): three rotating gathered buffers, the wait for step e's panels queued after the GEMM of
+          step e + 1 (wgb_peer_gather_wait), the last one inside the timed region — every step's GEMM and gather complete before
+          the closing event, but a momentarily slow rank no longer stalls the other seven at every step;
+      lock step (`lockstep`): one gathered buffer, every call waits for all panels before the next GEMM starts.
+    Then parity: sampled elements of the gathered C of the timed run on EVERY rank against float64."""
+    from wgmath_b200 import sharded
+    from wgmath_b200._lib import check, lib
+    dev = gpu.device()
+    n = 4096 * ngpu
+    m_local = n // ngpu
+    ST = w.BufferUsages.STORAGE | w.BufferUsages.COPY_SRC | w.BufferUsages.COPY_DST
+    mode = os.environ.get("WGB_SHARD_MODE", "fused")                     # "fused" (peer stores) or "nccl"
+    a = w.TensorBuilder.matrix(m_local, n, ST).build(dev, "bf16")       # my row block of A
+    b = w.TensorBuilder.matrix(n, n, ST).build(dev, "bf16")             # B replicated
+    enc = dev.create_command_encoder()
+    with enc.compute_pass("init", None) as p:
+        w.fill_uniform(dev, p, a, O.SEED_BASE + 1, row0=rank * m_local)  # element (i, j) independent of the sharding
+        w.fill_uniform(dev, p, b, O.SEED_BASE + 2)
+    dev.poll_wait()
+    op = sharded.RowShardedGemm(dev)
+    flops = 2.0 * n * n * n
+    lock = None
+    cfg = {}
+    if mode == "fused":
+        group1 = sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=1)
+
+        def lock_step(p, i):
+            op.dispatch_fused(dev, shapes, p, group1, a, b)
+        lsec, _ = timed(lock_step, args.steps, args.warmup)
+        lock = {"value": flops * args.steps / lsec / 1e12, "unit": "TFLOP/s", "ms_per_step": lsec * 1e3 / args.steps,
+                "what": "one gathered buffer, every call waits for all peers' panels before the next GEMM starts"}
+        if dist is not None:
+            dist.barrier()
+        group1.close()
+        group = sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=3)
+        calls = [0]
+
+        def step_fn(p, i):
+            op.dispatch_fused(dev, shapes, p, group, a, b, wait=False)
+            if not cfg:
+                cfg.update(p.last_gemm_config())
+            if calls[0] > 0:
+                group.wait(p, 1)          # the gather of the previous call, queued behind this call's GEMM
+            calls[0] += 1
+        def closing_wait():
+            # the last call's panels: part of the timed region
+            enc2 = dev.create_command_encoder()
+            with enc2.compute_pass("gather-wait", None) as p2:
+                group.wait(p2, 0)
+        mark = sampler.mark()
+        sec, launches = timed(step_fn, args.steps, args.warmup, before_end=closing_wait)
+        clocks_main = sampler.summary(since=mark)
+        c = group.tensor_at(0)
+    else:
+        group = None
+        sharded.init_comm(dev, dist, rank, ngpu)
+        c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
+        step_fn = lambda p, i: op.dispatch(dev, shapes, p, c, a, b)             # noqa: E731
+        mark = sampler.mark()
+        sec, launches = timed(step_fn, args.steps, args.warmup)
+        clocks_main = sampler.summary(since=mark)
+    value = flops * args.steps / sec / 1e12
+    ms_step = sec * 1e3 / args.steps
+    # ---- parity, on every rank: elements (row r, column j) of the gathered cube for rows spread over every rank's panel
+    L = lib()
+    rows = sorted({0, 1, m_local - 1, m_local, n // 2 + 17, n - m_local - 1, n - 1, (5 * m_local + 4095) % n})
+    cols = sorted({0, 1, 255, 256, n // 2 - 1, n // 2, n - 257, n - 1} | {int(x) for x in np.random.default_rng(7).integers(0, n, 24)})
+    Bc = np.stack([O.to_bf16_rne(O.uniform(O.SEED_BASE + 2, n, 1, col0=j)) for j in cols]).astype(np.float64)      # [col][k]
+    Ar = np.stack([O.to_bf16_rne(O.uniform(O.SEED_BASE + 1, 1, n, row0=r)) for r in rows]).astype(np.float64)      # [row][k]
+    ref = Ar @ Bc.T
+    got = np.zeros_like(ref)
+    seg = np.zeros(m_local, np.uint16)
+    for cj, j in enumerate(cols):
+        for q in sorted({r // m_local for r in rows}):
+            off = (q * m_local * n + j * m_local) * 2
+            check(L.wgb_buffer_read(dev._h, c.buffer()._h, off, seg.ctypes.data_as(ctypes.c_void_p), seg.nbytes))
+            vals = O.bf16_from_bits(seg)
+            for ri, r in enumerate(rows):
+                if r // m_local == q:
+                    got[ri, cj] = vals[r % m_local]
+    perr = float(np.max(np.abs(got - ref) / np.abs(ref)))
+    ok_local = bool(perr < 1e-2)
+    worst, ok_all = perr, ok_local
+    if dist is not None:
+        import torch
+        t = torch.tensor([perr, 0.0 if ok_local else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst, ok_all = float(t[0].item()), bool(t[1].item() == 0.0)
+    parity = {"checked": f"{len(rows)} rows (every rank's panel) x {len(cols)} columns of the gathered C of the timed run, on every "
+                         f"one of the {ngpu} ranks, vs float64 on the same bf16-rounded inputs", "max_rel_err": worst, "tol": 1e-2,
+              "ok": ok_all, "ranks_checked": ngpu}
+    long_run = sec > 1.0
+    peak = (peaks["bf16_tflops_sustained"] if long_run else peaks["bf16_tflops"]) * ngpu
+    comm_bytes = (ngpu - 1) * m_local * n * 2
+    kname = ((f"gemm_tc_kernel<{cfg.get('kind')}, {cfg.get('a_mn')}, {cfg.get('b_mn')}, {cfg.get('bn')}, {cfg.get('passes')}, __nv_bfloat16, "
+              f"{cfg.get('cg')}> (tcgen05) with the all-gather of C fused into the epilogue: "
+              f"{'TMA bulk stores' if cfg.get('epi_tma') else 'per-lane stores'} to {cfg.get('dests')} gathered buffers over NVLink")
+             if group is not None else "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)")
+    flop_ms = flops / ngpu / (peaks["bf16_tflops_sustained" if long_run else "bf16_tflops"] * 1e12) * 1e3
+    link_ms = comm_bytes / 770e9 * 1e3
+    roof = {"bound": "tensor", "kernel": kname,
+            "achieved": value, "peak": peak, "unit": "TFLOP/s", "frac": value / peak,
+            "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
+            "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
+            "nvlink_floor_ms": link_ms, "tensor_floor_ms": flop_ms,
+            "fused_target_ms": max(flop_ms, link_ms), "frac_of_fused_target": max(flop_ms, link_ms) / ms_step}
+    if lock is not None:
+        roof["lockstep"] = lock
+    wl_extra = {"gather": ("fused into the GEMM epilogue; three rotating gathered buffers, the wait for step e queued behind the GEMM of "
+                           "step e + 1, the last wait inside the timed region" if group is not None else "NCCL send/recv, chunked")}
+    # e2e: HOST buffers in, HOST buffer out, through the C ABI, every step: this rank's A block and its 1/P column slice of B go
+    # up (the slices are all-gathered over NVLink: B crosses the host links once per box), the sharded GEMM + gather runs, this
+    # rank's panel comes down — the ranks of the box assemble C in host memory, every byte of C crosses a host link once.
+    # `separate_calls`: the reference tests' sequence (write A, write B, dispatch, read the whole gathered cube on every rank).
+    abytes, bbytes, cbytes = m_local * n * 2, n * n * 2, n * n * 2
+    pbytes = m_local * n * 2
+    ha, hb, hc, hp0, hp1 = (ctypes.c_void_p() for _ in range(5))
+    for h, nb in ((ha, abytes), (hb, bbytes), (hc, cbytes), (hp0, pbytes), (hp1, pbytes)):
+        check(L.wgb_host_alloc(nb, ctypes.byref(h)))
+    check(L.wgb_buffer_read(dev._h, a.buffer()._h, 0, ha, abytes))
+    check(L.wgb_buffer_read(dev._h, b.buffer()._h, 0, hb, bbytes))
+    e2e_steps = max(2, min(args.steps, 5))
+
+    def e2e_seq_step(p, i):
+        check(L.wgb_buffer_write(dev._h, a.buffer()._h, 0, ha, abytes))
+        check(L.wgb_buffer_write(dev._h, b.buffer()._h, 0, hb, bbytes))
+        if group is not None:
+            op.dispatch_fused(dev, shapes, p, group, a, b)
+            check(L.wgb_buffer_read(dev._h, group.tensor_at(0).buffer()._h, 0, hc, cbytes))
+        else:
+            step_fn(p, i)
+            check(L.wgb_buffer_read(dev._h, c.buffer()._h, 0, hc, cbytes))
+    seq_sec, _ = timed(e2e_seq_step, e2e_steps, 1)
+    seq = {"value": flops * e2e_steps / seq_sec / 1e12, "ms_per_step": seq_sec * 1e3 / e2e_steps,
+           "h2d_bytes_per_step": (abytes + bbytes) * ngpu, "d2h_bytes_per_step": cbytes * ngpu,
+           "call": "wgb_buffer_write x2 + sharded dispatch + wgb_buffer_read of the whole gathered cube on every rank"}
+    if group is not None:
+        split_b = os.environ.get("WGB_SHARD_B_UPLOAD", "1") not in ("", "0")
+        if split_b:
+            sharded.init_comm(dev, dist, rank, ngpu)
+
+        def e2e_step(p, i):
+            op.enqueue_host_fused(dev, group, m_local, n, n, hp0 if i % 2 == 0 else hp1, ha, hb)
+        e2e_sec, _ = timed(e2e_step, e2e_steps, 2, before_end=lambda: check(L.wgb_gemm_host_flush(dev._h)))
+        # the panel this rank downloaded in the last e2e step must be its panel of the gathered cube, bit for bit
+        dev.poll_wait()
+        last = hp0 if (2 + e2e_steps - 1) % 2 == 0 else hp1
+        mine = np.zeros(pbytes // 2, np.uint16)
+        check(L.wgb_buffer_read(dev._h, group.tensor_at(0).buffer()._h, rank * pbytes, mine.ctypes.data_as(ctypes.c_void_p), pbytes))
+        host = np.ctypeslib.as_array(ctypes.cast(last, ctypes.POINTER(ctypes.c_uint16)), shape=(pbytes // 2,))
+        e2e_same = bool(np.array_equal(host, mine))
+        if dist is not None:
+            import torch
+            t = torch.tensor([1.0 if e2e_same else 0.0], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            e2e_same = bool(t.item() == 1.0)
+        e2e = {"value": flops * e2e_steps / e2e_sec / 1e12, "unit": "TFLOP/s",
+               "h2d_bytes_per_step": abytes * ngpu + (bbytes if split_b else bbytes * ngpu),
+               "d2h_bytes_per_step": pbytes * ngpu, "steps": e2e_steps, "ms_per_step": e2e_sec * 1e3 / e2e_steps,
+               "b_upload": "1/P column slice per rank + all-gather over NVLink (ncclAllGather on the queue)" if split_b else "whole B on every rank",
+               "downloaded_panel_equals_device_result": e2e_same,
+               "call": "wgb_gemm_row_sharded_fused_host_enqueue per step on every rank (pinned host buffers; A block + B slice up, "
+                       "all-gather of B, fused GEMM + all-gather of C, this rank's panel of C down: the box's host memory ends with "
+                       "all of C), closed by wgb_gemm_host_flush", "separate_calls": seq}
+        if not e2e_same:
+            parity["ok"] = False
+            parity["e2e_panel_mismatch"] = True
+    else:
+        split_b = False
+        e2e = {"value": seq["value"], "unit": "TFLOP/s", "h2d_bytes_per_step": seq["h2d_bytes_per_step"],
+               "d2h_bytes_per_step": seq["d2h_bytes_per_step"], "steps": e2e_steps, "ms_per_step": seq["ms_per_step"], "call": seq["call"]}
+    for h in (ha, hb, hc, hp0, hp1):
+        L.wgb_host_free(h)
+    dev.poll_wait()
+    if dist is not None:
+        dist.barrier()
+    if group is None or split_b:
+        lib().wgb_comm_destroy(dev._h)
+    if group is not None:
+        group.close()
+    return value, ms_step, launches, roof, e2e, "bf16", parity, wl_extra, clocks_main
 
 
 def run_extras(w, O, gpu, shapes, timed, peaks, timed_graph):

@@ -447,6 +447,9 @@ wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out /* WGB_I
 wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles /* nranks x WGB_IPC_HANDLE_BYTES */);
 /* The local gathered buffer as a wgb_buffer (owned by the group; valid until wgb_peer_gather_destroy). */
 wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out);
+/* Tear-down across processes is two-phase (CUDA IPC: importers unmap before the exporter frees): every rank disconnects, the
+ * ranks meet at a barrier of their launcher, every rank destroys.  wgb_peer_gather_destroy alone disconnects first. */
+wgb_status wgb_peer_gather_disconnect(wgb_peer_gather *pg);
 wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg);
 /* Same contract and output layout as wgb_gemm_row_sharded, the all-gather fused into the GEMM epilogue. */
 wgb_status wgb_gemm_row_sharded_fused(wgb_pass *pass, wgb_gemm_variant variant, wgb_peer_gather *pg,

@@ -489,6 +489,12 @@ def test_cfg3_bf16_gemm_4096_properties(gpu, shapes):
     A = np.stack([O.to_bf16_rne(O.uniform(SEED_A, 1, n, row0=int(r))) for r in rows]).astype(np.float64)
     B = cm(O.to_bf16_rne(O.uniform(SEED_B, n, n)), n, n).astype(np.float64)
     assert rel_err(got[rows, :], A @ B) < 1e-4           # f32 output of bf16 inputs: only accumulation error
+    # the bench configuration itself: bf16 OUT, random operands, whatever BLOCK_N / CTA group the heuristic picks (256 / 2)
+    cfg = []
+    run_pass(gpu, lambda p: (gemm.dispatch(dev, shapes, p, out, a, b), cfg.append(p.last_gemm_config())))
+    assert (cfg[0]["bn"], cfg[0]["cg"], cfg[0]["out_dtype"]) == (256, 2, 1)
+    got16 = cm(O.bf16_from_bits(out.read()), n, n)
+    assert rel_err(got16[rows, :], A @ B) < BF16_TOL
     run_pass(gpu, lambda p: gemm.dispatch_tr(dev, shapes, p, outf, a, b))
     gt = cm(outf.read(), n, n)
     cols = np.stack([O.to_bf16_rne(O.uniform(SEED_A, n, 1, col0=int(r))) for r in rows]).astype(np.float64)   # columns of A = rows of tr(A)
@@ -552,6 +558,57 @@ def test_gemm_host_enqueue_keeps_products_apart(gpu, shapes):
     out = np.full(M * N, -1.0, np.float32)
     gemm.dispatch_host(dev, M, N, K, out, ins[0][0], ins[0][1])
     assert rel_err(cm(out, M, N), cm(ins[0][0], M, K).astype(np.float64) @ cm(ins[0][1], K, N).astype(np.float64)) < F32_TOL
+
+
+def test_gemm_host_enqueue_sizes_change_while_products_are_in_flight(gpu, shapes):
+    """Large products followed at once by small ones (and back): the two device operand slots sit at fixed offsets, so a small
+    product's slot can never land inside a large product that is still multiplying or downloading."""
+    dev = gpu.device()
+    gemm = w.Gemm.from_device(dev)
+    jobs = []
+    big, small = (1536, 2048, 1024), (128, 264, 136)
+    for i, (M, N, K) in enumerate([big, small, small, big, small, big, big, small]):
+        A, B = O.uniform(SEED_A + 32 * i, M, K), O.uniform(SEED_B + 32 * i, K, N)
+        out = np.full(M * N, -1.0, np.float32)
+        gemm.enqueue_host(dev, M, N, K, out, A, B)
+        jobs.append((M, N, K, A, B, out))
+    dev.poll_wait()
+    for M, N, K, A, B, out in jobs:
+        ref = cm(A, M, K).astype(np.float64) @ cm(B, K, N).astype(np.float64)
+        assert rel_err(cm(out, M, N), ref) < F32_TOL, (M, N, K)
+
+
+def test_graph_refuses_to_replay_after_a_workspace_reallocation(gpu, shapes):
+    """A recorded 3xTF32 GEMM carries pointers into the context's operand-split workspace.  A larger eager product reallocates
+    it; replaying the old graph would read freed memory, so wgb_graph_launch must fail instead (and a fresh recording works)."""
+    dev = w.GpuInstance.new().device()          # own context: its workspaces start empty
+    sh = w.ViewShapeBuffers.new()
+    gemm = w.Gemm.from_device(dev)
+
+    def mats(n):
+        ta = w.TensorBuilder.matrix(n, n, STORAGE).build_init(dev, O.uniform(SEED_A, n, n))
+        tb = w.TensorBuilder.matrix(n, n, STORAGE).build_init(dev, O.uniform(SEED_B, n, n))
+        return ta, tb, w.TensorBuilder.matrix(n, n, STORAGE).build(dev)
+
+    def run(fn):
+        enc = dev.create_command_encoder()
+        with enc.compute_pass("t", None) as p:
+            fn(p)
+    a, b, c = mats(256)
+    run(lambda p: gemm.dispatch_generic(dev, sh, p, c, a, b, w.GemmVariant.Gemm, f32_mode=w.F32Mode.X3Tf32))   # warm
+    with dev.capture() as cap:
+        run(lambda p: gemm.dispatch_generic(dev, sh, p, c, a, b, w.GemmVariant.Gemm, f32_mode=w.F32Mode.X3Tf32))
+    cap.graph.launch()
+    want = c.read()
+    a2, b2, c2 = mats(1024)
+    run(lambda p: gemm.dispatch_generic(dev, sh, p, c2, a2, b2, w.GemmVariant.Gemm, f32_mode=w.F32Mode.X3Tf32))   # grows the workspace
+    dev.poll_wait()
+    with pytest.raises(w.WgbError, match="reallocated"):
+        cap.graph.launch()
+    with dev.capture() as cap2:
+        run(lambda p: gemm.dispatch_generic(dev, sh, p, c, a, b, w.GemmVariant.Gemm, f32_mode=w.F32Mode.X3Tf32))
+    cap2.graph.launch()
+    np.testing.assert_array_equal(c.read(), want)
 
 
 @pytest.mark.parametrize("op", [w.OpAssignVariant.Add, w.OpAssignVariant.Sub, w.OpAssignVariant.Mul, w.OpAssignVariant.Div])

@@ -411,7 +411,10 @@ wgb_status wgb_peer_gather_wait(wgb_pass *pass, wgb_peer_gather *pg, int calls_b
     return WGB_OK;
 }
 
-wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
+// First half of tearing a group down across processes: drain this rank's queues and unmap the peers' buffers.  CUDA requires
+// every importer to have closed its mapping before the exporter frees the memory, so the ranks call this, meet at a barrier of
+// their launcher, and only then call wgb_peer_gather_destroy.
+wgb_status wgb_peer_gather_disconnect(wgb_peer_gather *pg) {
     if (!pg) return WGB_OK;
     DeviceGuard g(pg->ctx->device);
     // the host-operand form leaves downloads of the gathered buffer on the side streams
@@ -419,7 +422,19 @@ wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
     cudaStreamSynchronize(pg->ctx->comm_stream);
     if (pg->ctx->h2d_stream) cudaStreamSynchronize(pg->ctx->h2d_stream);
     for (int q = 0; q < pg->nranks; ++q)
-        if (q != pg->rank && pg->peer[q] && pg->ipc_opened[q]) cudaIpcCloseMemHandle(pg->peer[q]);
+        if (q != pg->rank && pg->peer[q]) {
+            if (pg->ipc_opened[q]) cudaIpcCloseMemHandle(pg->peer[q]);
+            pg->peer[q] = nullptr;
+            pg->ipc_opened[q] = false;
+        }
+    pg->connected = pg->nranks == 1;
+    return WGB_OK;
+}
+
+wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
+    if (!pg) return WGB_OK;
+    wgb_peer_gather_disconnect(pg);
+    DeviceGuard g(pg->ctx->device);
     if (pg->local) cudaFree(pg->local);
     wgb_ctx *ctx = pg->ctx;
     delete pg;

@@ -74,6 +74,7 @@ class PeerGather:
 
     def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16", depth: int = 1, _connect=True):
         self._device, self.rank, self.world, self.depth = device, rank, world, depth
+        self._dist = dist if (_connect and world > 1) else None
         self._shape, self._dtype = (m_local, N, world), dtype
         self._nbytes = world * m_local * N * (2 if dtype == "bf16" else 4)
         h = ctypes.c_void_p()
@@ -117,14 +118,19 @@ class PeerGather:
         """Queue the wait for every peer's panel of the call `calls_back` calls ago (wgb_peer_gather_wait)."""
         check(lib().wgb_peer_gather_wait(pass_._h, self._h, calls_back))
 
-    def close(self):
+    def close(self, collective: bool = True):
+        """Collective across the ranks of a multi-process group: everyone unmaps its peers, meets at a barrier, then frees
+        (CUDA IPC requires the importers to let go before the exporter frees)."""
         h, self._h = getattr(self, "_h", None), None
         if h:
+            lib().wgb_peer_gather_disconnect(h)
+            if collective and self._dist is not None:
+                self._dist.barrier()
             lib().wgb_peer_gather_destroy(h)
 
     def __del__(self):
         try:
-            self.close()
+            self.close(collective=False)
         except Exception:
             pass
 
