@@ -327,6 +327,21 @@ struct TcCfg {
     static_assert(STAGES >= 2, "pipeline too shallow");
 };
 
+// TMA-store epilogue: two staging blocks of [kEpiCols columns][128 rows] of TOut behind the barriers.  The ring gives up a
+// stage where the two do not fit beside it (BLOCK_N 256 x CTA pairs: 7 -> 6 stages); the launch asks for the larger of the
+// two shared-memory footprints.
+template <int BN, int PASSES, int CG, typename TOut>
+struct TcEpi {
+    using Cfg = TcCfg<BN, PASSES, CG>;
+    static constexpr int STG_BYTES = kBlockM * kEpiCols * (int)sizeof(TOut);
+    static constexpr int STAGES_RAW = (kSmemLimit - Cfg::BAR_BYTES - 1024 - 2 * STG_BYTES) / Cfg::STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW < Cfg::STAGES ? STAGES_RAW : Cfg::STAGES;
+    static constexpr int SMEM_BYTES_EPI = STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + 2 * STG_BYTES + 1024;
+    static constexpr int SMEM_BYTES = SMEM_BYTES_EPI > Cfg::SMEM_BYTES ? SMEM_BYTES_EPI : Cfg::SMEM_BYTES;
+    static_assert(STAGES >= 2, "pipeline too shallow beside the epilogue staging blocks");
+    static_assert(SMEM_BYTES <= kSmemLimit, "shared-memory budget exceeded");
+};
+
 // Tile index -> (batch, m-tile, n-tile); groups of kSuperM m-tiles sweep N together.
 __device__ __forceinline__ void tile_coords(uint32_t t, const TcArgs &a, uint32_t &bt, uint32_t &mt, uint32_t &nt) {
     const uint32_t per_batch = a.tiles_m * a.tiles_n;
@@ -367,14 +382,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint32_t IDESC = make_idesc(KIND, A_MN, B_MN, kBlockM * CG, BN);
     static_assert(!B_MN || KIND == 0, "MN-major B is implemented for 16-bit operands only");
     constexpr bool CHUNKED = PASSES == 3;
-    // TMA-store epilogue: two staging blocks of [kEpiCols columns][128 rows] behind the barriers; the ring gives up a stage
-    // where the two do not fit beside it (BLOCK_N 256 x CTA pairs: 7 -> 6 stages).
-    constexpr int STG_BYTES = kBlockM * kEpiCols * (int)sizeof(TOut);
-    constexpr int STAGES_EPI_RAW = (kSmemLimit - Cfg::BAR_BYTES - 1024 - 2 * STG_BYTES) / Cfg::STAGE_BYTES;
-    constexpr int STAGES_EPI = STAGES_EPI_RAW < Cfg::STAGES ? STAGES_EPI_RAW : Cfg::STAGES;
-    static_assert(STAGES_EPI >= 2, "pipeline too shallow beside the epilogue staging blocks");
+    using Epi = TcEpi<BN, PASSES, CG, TOut>;
+    constexpr int STG_BYTES = Epi::STG_BYTES;
     const bool tma_epi = args.epi_tma != 0;
-    const int STAGES = tma_epi ? STAGES_EPI : Cfg::STAGES;
+    const int STAGES = tma_epi ? Epi::STAGES : Cfg::STAGES;
 
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128-byte swizzle
@@ -769,12 +780,12 @@ struct TcMaps {
 
 template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
 wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
-    using Cfg = TcCfg<BN, PASSES, CG>;
+    constexpr int SMEM_BYTES = TcEpi<BN, PASSES, CG, TOut>::SMEM_BYTES;
     auto kern = gemm_tc_kernel<KIND, A_MN, B_MN, BN, PASSES, TOut, CG>;
     static bool attr_set[64] = {};   // per instantiation, per device
     const int dev = p->ctx->device & 63;
     if (!attr_set[dev]) {
-        WGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        WGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set[dev] = true;
     }
     uint32_t sms = (uint32_t)p->ctx->prop.multiProcessorCount;
@@ -785,7 +796,7 @@ wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CG);
     cfg.blockDim = dim3(kNumThreads);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = p->stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
