@@ -447,6 +447,9 @@ wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out /* WGB_I
 wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles /* nranks x WGB_IPC_HANDLE_BYTES */);
 /* The local gathered buffer as a wgb_buffer (owned by the group; valid until wgb_peer_gather_destroy). */
 wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out);
+/* Diagnostics: the flag block of this rank read on a private stream (usable while the queues are stuck behind a missing peer):
+ * out[0..8) ready[q], out[8..16) done[q], out[16] CTA counter, out[17] calls made on this rank. */
+wgb_status wgb_peer_gather_debug_flags(wgb_peer_gather *pg, unsigned int *out /* 18 words */);
 /* Tear-down across processes is two-phase (CUDA IPC: importers unmap before the exporter frees): every rank disconnects, the
  * ranks meet at a barrier of their launcher, every rank destroys.  wgb_peer_gather_destroy alone disconnects first. */
 wgb_status wgb_peer_gather_disconnect(wgb_peer_gather *pg);

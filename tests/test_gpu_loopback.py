@@ -13,7 +13,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.gpu
 def test_fused_gather_protocol_on_one_gpu():
-    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", WGB_PEER_TIMEOUT_MS="20000")
+    # (EAGER: no kernel is loaded for the first time while another rank's GEMM spins on a flag, see comm.cu)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", WGB_PEER_TIMEOUT_MS="20000", CUDA_MODULE_LOADING="EAGER")
     for k in ("WGB_TC_EPI", "WGB_TC_BN", "WGB_TC_CG", "WGB_TC_NSPLIT", "WGB_TC_SPLITK"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "loopback_check.py")], capture_output=True, text=True,

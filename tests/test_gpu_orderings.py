@@ -36,11 +36,11 @@ def addressed(vs, rm):
 
 
 def gemm_ord_case(gpu, shapes, M, N, K, tr, ro, r1, r2, T=1, dtype="f32", out_dtype="f32", mode=None, pad=(0, 0, 0), off=(0, 0, 0),
-                  tol=F32_TOL, op=None, cfg_out=None):
+                  tol=F32_TOL, op=None, cfg_out=None, out_extra=12):
     ar, ac = (K, M) if tr else (M, K)
     s1, n1 = view_of(ar, ac, T, r1, pad[0], off[0])
     s2, n2 = view_of(K, N, T, r2, pad[1], off[1])
-    so, no = view_of(M, N, T, ro, pad[2], off[2], extra=12)
+    so, no = view_of(M, N, T, ro, pad[2], off[2], extra=out_extra)
     A, B = O.uniform(SEED_A, n1), O.uniform(SEED_B, n2)
     if dtype == "bf16":
         A, B = O.to_bf16_rne(A), O.to_bf16_rne(B)

@@ -55,7 +55,7 @@ def test_tc_instantiation(gpu, shapes, monkeypatch, inst):
             monkeypatch.setenv(k, v)
         cfg = []
         path = gemm_ord_case(gpu, shapes, sh["M"], sh["N"], sh["K"], route["tr"], 0, 0, b_mn, T=sh["T"], dtype="f32" if f32 else "bf16",
-                             out_dtype=out, mode=mode, pad=sh["pad"], off=sh["off"], tol=tol, cfg_out=cfg)
+                             out_dtype=out, mode=mode, pad=sh["pad"], off=sh["off"], tol=tol, cfg_out=cfg, out_extra=16)
         assert path == (2 if not f32 else 4 if passes == 3 else 3)
         c = cfg[0]
         got = (("tf32" if c["kind"] else "bf16"), c["a_mn"], c["b_mn"], c["bn"], c["passes"], "bf16" if c["out_dtype"] == 1 else "f32", c["cg"])

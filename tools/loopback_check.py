@@ -14,6 +14,9 @@ import sys
 
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 os.environ.setdefault("WGB_PEER_TIMEOUT_MS", "20000")
+# every kernel loaded up front: with lazy loading a first launch may synchronise the context, which never happens while another
+# rank of this same process spins on a flag that a later launch must set
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import numpy as np  # noqa: E402
 
@@ -27,6 +30,7 @@ ST = w.BufferUsages.STORAGE | w.BufferUsages.COPY_SRC | w.BufferUsages.COPY_DST
 
 
 def run_case(P, depth, epi, tr, m_local, N, K, steps, deferred, out_dtype="bf16", in_dtype="bf16"):
+    print(f"... P={P} depth={depth} epi={epi} tr={int(tr)} {m_local}x{N}x{K} steps={steps} deferred={deferred}", flush=True)
     os.environ["WGB_TC_EPI"] = str(epi)
     gpus = [w.GpuInstance.new(0) for _ in range(P)]
     devs = [g.device() for g in gpus]
@@ -72,6 +76,11 @@ def run_case(P, depth, epi, tr, m_local, N, K, steps, deferred, out_dtype="bf16"
             snap[r][steps - 1].copy_from(None, groups[r].tensor_at(0))
     for p in passes:
         p.end()
+    if os.environ.get("LOOPBACK_DEBUG"):
+        import time
+        time.sleep(float(os.environ["LOOPBACK_DEBUG"]))
+        for r, g in enumerate(groups):
+            print(f"  [debug] rank {r} flags after {os.environ['LOOPBACK_DEBUG']} s: {g.debug_flags()}", flush=True)
     for d in devs:
         d.poll_wait()
     ok = True
@@ -119,6 +128,8 @@ def main():
     ]
     if quick:
         cases = cases[:2] + cases[8:10]
+    if os.environ.get("LOOPBACK_CASES"):
+        cases = [cases[int(i)] for i in os.environ["LOOPBACK_CASES"].split(",")]
     ok = True
     for c in cases:
         ok &= run_case(*c)

@@ -310,6 +310,13 @@ wgb_status wgb_peer_gather_create_ex(wgb_ctx *ctx, int nranks, int rank, size_t 
     pg->depth = depth;
     pg->data_bytes = (gathered_bytes + 255) & ~(size_t)255;
     pg->timeout_cycles = wgb::peer_timeout_cycles(ctx);
+    {   // Load the flag kernels now.  With lazy module loading the first launch of a kernel may synchronise the context; if that
+        // first launch came while a GEMM of this process spins on a flag that only a later launch can set (several ranks driven
+        // by one host thread), the process would deadlock.
+        cudaFuncAttributes fa;
+        (void)cudaFuncGetAttributes(&fa, wgb::signal_ready_kernel);
+        (void)cudaFuncGetAttributes(&fa, wgb::wait_done_kernel);
+    }
     cudaError_t e = cudaMalloc((void **)&pg->local, pg->signal_off() + wgb::kSignalBytes);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
@@ -408,6 +415,27 @@ wgb_status wgb_peer_gather_wait(wgb_pass *pass, wgb_peer_gather *pg, int calls_b
                                                       pg->timeout_cycles);
     count_launch(pg->ctx);
     WGB_CUDA(cudaGetLastError());
+    return WGB_OK;
+}
+
+// Diagnostics: a snapshot of this rank's flag block taken on a private stream, so it can be read while the queues are busy
+// (or stuck): out[0..8) = ready[q], out[8..16) = done[q], out[16] = CTA counter, out[17] = this rank's call count (host side).
+wgb_status wgb_peer_gather_debug_flags(wgb_peer_gather *pg, unsigned int *out /* 18 words */) {
+    if (!pg || !out) WGB_FAIL(WGB_ERR_INVALID, "null argument");
+    DeviceGuard g(pg->ctx->device);
+    cudaStream_t s = nullptr;
+    WGB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    unsigned int host[64] = {};
+    cudaError_t e = cudaMemcpyAsync(host, pg->local + pg->signal_off(), sizeof host, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaStreamDestroy(s);
+    if (e != cudaSuccess) WGB_FAIL(WGB_ERR_CUDA, "flag snapshot failed: %s", cudaGetErrorString(e));
+    for (int q = 0; q < 8; ++q) {
+        out[q] = host[wgb::kReadyOff + q];
+        out[8 + q] = host[wgb::kDoneOff + q];
+    }
+    out[16] = host[wgb::kCtaOff];
+    out[17] = pg->epoch;
     return WGB_OK;
 }
 

@@ -609,15 +609,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t taddr = lane_base + acc * BN;
                 const uint32_t tsum = lane_base + 2 * BN;   // running sum of the chains (3xTF32 only)
-                uint32_t v[2][32];
-                tmem_ld32(taddr, v[0]);
-#pragma unroll
-                for (int c = 0; c < BN / 32; ++c) {
-                    if (c >= nblk) break;
+                // The 32-column blocks are processed in pairs by a loop that is NOT unrolled: the two register blocks keep static
+                // names (cur / nxt swap roles inside the pair) while the code stays a quarter of the fully unrolled form — the
+                // epilogue runs once per tile, so its instruction footprint is fetched cold every time.
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                auto block = [&](const int c, uint32_t (&cur)[32], uint32_t (&nxt)[32]) {
                     uint32_t sprev[32];
                     if (CHUNKED && ch > 0) tmem_ld32(tsum + c * 32, sprev);
                     tmem_ld_wait();
-                    if (c + 1 < nblk) tmem_ld32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+                    if (c + 1 < nblk) tmem_ld32(taddr + (c + 1) * 32, nxt);
                     else {
                         // all TMEM reads of this accumulator are done: hand it back to the MMA issuer
                         tc_fence_before();
@@ -629,13 +630,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (CHUNKED && ch > 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) v[c & 1][i] = __float_as_uint(__uint_as_float(v[c & 1][i]) + __uint_as_float(sprev[i]));
+                        for (int i = 0; i < 32; ++i) cur[i] = __float_as_uint(__uint_as_float(cur[i]) + __uint_as_float(sprev[i]));
                     }
                     if (CHUNKED && !final_chain) {
-                        tmem_st32(tsum + c * 32, v[c & 1]);
+                        tmem_st32(tsum + c * 32, cur);
                     } else if (split_unit) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(v[c & 1][i]));
+                        for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(cur[i]));
                     } else if (tma_epi) {
                         // TMEM -> registers -> shared memory block [32 columns][128 rows] -> one bulk tensor store per
                         // destination.  Whole 256 B (bf16) / 512 B (f32) column segments leave the SM instead of per-lane
@@ -646,7 +647,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) {
                                 const uint32_t col = n0 + c * 32 + i;
                                 if (col < args.N)
-                                    v[c & 1][i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(v[c & 1][i]), erow + (uint64_t)col * args.ep_ld));
+                                    cur[i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(cur[i]), erow + (uint64_t)col * args.ep_ld));
                             }
                         }
                         uint8_t *blk = staging + (staged & 1u) * STG_BYTES;
@@ -657,7 +658,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                         TOut *sp = reinterpret_cast<TOut *>(blk) + row_in_cta;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) store_out<TOut>(sp + i * kBlockM, __uint_as_float(v[c & 1][i]));
+                        for (int i = 0; i < 32; ++i) store_out<TOut>(sp + i * kBlockM, __uint_as_float(cur[i]));
                         fence_proxy_async_smem();
                         asm volatile("bar.sync 1, 128;" ::: "memory");
                         if (threadIdx.x == 128) {
@@ -673,7 +674,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             for (int i = 0; i < 32; ++i) {
                                 const uint32_t col = n0 + c * 32 + i;
                                 if (col < args.N)
-                                    v[c & 1][i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(v[c & 1][i]), erow + (uint64_t)col * args.ep_ld));
+                                    cur[i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(cur[i]), erow + (uint64_t)col * args.ep_ld));
                             }
                         }
                         for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
@@ -681,10 +682,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int i = 0; i < 32; ++i) {
                                 const uint32_t col = n0 + c * 32 + i;
-                                if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(v[c & 1][i]));
+                                if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(cur[i]));
                             }
                         }
                     }
+                };
+#pragma unroll 1
+                for (int c = 0; c < nblk; c += 2) {
+                    block(c, v0, v1);
+                    if (c + 1 < nblk) block(c + 1, v1, v0);
                 }
                 if (CHUNKED && !final_chain) tmem_st_wait();
                 acc ^= 1;

@@ -118,6 +118,13 @@ class PeerGather:
         """Queue the wait for every peer's panel of the call `calls_back` calls ago (wgb_peer_gather_wait)."""
         check(lib().wgb_peer_gather_wait(pass_._h, self._h, calls_back))
 
+    def debug_flags(self) -> dict:
+        """Snapshot of this rank's flag block (wgb_peer_gather_debug_flags): readable while the queues are busy or stuck."""
+        out = (ctypes.c_uint32 * 18)()
+        check(lib().wgb_peer_gather_debug_flags(self._h, out))
+        v = list(out)
+        return {"ready": v[:self.world], "done": v[8:8 + self.world], "cta_counter": v[16], "calls": v[17]}
+
     def close(self, collective: bool = True):
         """Collective across the ranks of a multi-process group: everyone unmaps its peers, meets at a barrier, then frees
         (CUDA IPC requires the importers to let go before the exporter frees)."""
