@@ -291,9 +291,11 @@ def main_gpu(args):
         sec = ms.value / 1e3
         if dist is not None:
             import torch
-            t = torch.tensor([sec], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            sec = float(t.item())
+            mine = torch.tensor([sec], device="cuda")
+            every = [torch.zeros_like(mine) for _ in range(world)]
+            dist.all_gather(every, mine)
+            timed.per_rank_ms = [float(x.item()) * 1e3 / max(steps, 1) for x in every]   # of the last timed region
+            sec = max(float(x.item()) for x in every)
         return sec, dev.launch_count() - n0
 
     def timed_graph(fn, steps, warmup):
@@ -520,6 +522,7 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
             op.dispatch_fused(dev, shapes, p, group1, a, b)
         lsec, _ = timed(lock_step, args.steps, args.warmup)
         lock = {"value": flops * args.steps / lsec / 1e12, "unit": "TFLOP/s", "ms_per_step": lsec * 1e3 / args.steps,
+                "ms_per_step_by_rank": getattr(timed, "per_rank_ms", None),
                 "what": "one gathered buffer, every call waits for all peers' panels before the next GEMM starts"}
         if dist is not None:
             dist.barrier()
@@ -542,9 +545,11 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
         mark = sampler.mark()
         sec, launches = timed(step_fn, args.steps, args.warmup, before_end=closing_wait)
         clocks_main = sampler.summary(since=mark)
+        by_rank = getattr(timed, "per_rank_ms", None)
         c = group.tensor_at(0)
     else:
         group = None
+        by_rank = None
         sharded.init_comm(dev, dist, rank, ngpu)
         c = w.TensorBuilder.tensor((m_local, n, ngpu), ST).build(dev, "bf16")
         step_fn = lambda p, i: op.dispatch(dev, shapes, p, c, a, b)             # noqa: E731
@@ -595,7 +600,8 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
             "peak_source": f"{peaks['source']} ({'sustained' if long_run else 'burst'}) x {ngpu} GPUs", "traffic": None,
             "algorithmic": "2*M*N*K flop per step over all ranks", "nvlink_bytes_in_per_gpu_per_step": comm_bytes,
             "nvlink_floor_ms": link_ms, "tensor_floor_ms": flop_ms,
-            "fused_target_ms": max(flop_ms, link_ms), "frac_of_fused_target": max(flop_ms, link_ms) / ms_step}
+            "fused_target_ms": max(flop_ms, link_ms), "frac_of_fused_target": max(flop_ms, link_ms) / ms_step,
+            "ms_per_step_by_rank": by_rank}
     if lock is not None:
         roof["lockstep"] = lock
     wl_extra = {"gather": ("fused into the GEMM epilogue; three rotating gathered buffers, the wait for step e queued behind the GEMM of "

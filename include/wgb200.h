@@ -435,6 +435,15 @@ wgb_status wgb_peer_gather_create(wgb_ctx *ctx, int nranks, int rank, size_t gat
  *      the use of) step e may be queued after the GEMM of step e + 1: a slow rank no longer stalls the others at every step.
  * All ranks must use the same depth. */
 wgb_status wgb_peer_gather_create_ex(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, int depth, wgb_peer_gather **out);
+/* A group over memory the CALLER allocated symmetrically on every rank and mapped both ways: peer_bases[q] = this process's mapping
+ * of rank q's region (peer_bases[rank] = the local one), multicast_base = the same region through an NVSwitch multicast object
+ * bound on all ranks, or NULL.  With a multicast mapping the fused epilogue stores every output block ONCE (multimem.st) and the
+ * switch delivers it to all ranks; without, it stores once per rank.  The region holds wgb_peer_gather_region_bytes() bytes on
+ * every rank; the library never frees or unmaps it.  The ranks must synchronise (a barrier of their launcher) between creating
+ * the group and the first product.  (cuMemCreate / cuMulticast* directly, or torch's symmetric memory in the Python mirror.) */
+size_t wgb_peer_gather_region_bytes(size_t gathered_bytes, int depth);
+wgb_status wgb_peer_gather_create_external(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, int depth,
+                                           void *const *peer_bases /* nranks */, void *multicast_base, wgb_peer_gather **out);
 /* Same-process connect: groups[q] is rank q's group (one context per rank; the ranks may share a device — the whole protocol then
  * runs on a single-GPU box — or sit on several devices driven by one process).  groups[rank] must be pg itself. */
 wgb_status wgb_peer_gather_connect_local(wgb_peer_gather *pg, wgb_peer_gather *const *groups /* nranks */);
@@ -447,6 +456,11 @@ wgb_status wgb_peer_gather_export(wgb_peer_gather *pg, void *handle_out /* WGB_I
 wgb_status wgb_peer_gather_connect(wgb_peer_gather *pg, const void *handles /* nranks x WGB_IPC_HANDLE_BYTES */);
 /* The local gathered buffer as a wgb_buffer (owned by the group; valid until wgb_peer_gather_destroy). */
 wgb_status wgb_peer_gather_buffer(wgb_peer_gather *pg, wgb_buffer **out);
+/* Diagnostics: link micro-benchmark.  The SMs stream `bytes` of `src` to ndst destinations `iters` times; mode 0 = st.global.v4 to
+ * unicast addresses (local or peer mappings), 1 = multimem.st to one multicast address (dsts[0]), 2 = TMA bulk stores (16 KiB) to
+ * unicast addresses.  ctas <= 0: two CTAs per SM.  Returns the time of one pass. */
+wgb_status wgb_debug_link_stream(wgb_ctx *ctx, int mode, void *const *dsts, int ndst, const void *src, size_t bytes, int ctas,
+                                 int iters, float *ms_per_iter);
 /* Diagnostics: the flag block of this rank read on a private stream (usable while the queues are stuck behind a missing peer):
  * out[0..8) ready[q], out[8..16) done[q], out[16] CTA counter, out[17] calls made on this rank. */
 wgb_status wgb_peer_gather_debug_flags(wgb_peer_gather *pg, unsigned int *out /* 18 words */);

@@ -20,8 +20,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-FUSED_FORMS = (("tma-d1", 1, 1, False), ("stg-d1", 0, 1, False), ("tma-d2", 1, 2, False), ("tma-d3-deferred", 1, 3, True),
-               ("stg-d3-deferred", 0, 3, True))
+# (name, WGB_TC_EPI, depth, deferred wait, symmetric memory + multicast mapping)
+FUSED_FORMS = (("tma-d1", 1, 1, False, False), ("stg-d1", 0, 1, False, False), ("tma-d2", 1, 2, False, False),
+               ("tma-d3-deferred", 1, 3, True, False), ("stg-d3-deferred", 0, 3, True, False),
+               ("mc-d1", 2, 1, False, True), ("mc-d3-deferred", 2, 3, True, True), ("tma-d2-symmetric", 1, 2, False, True))
 
 
 def main():
@@ -72,9 +74,12 @@ def main():
         dist.barrier()
         w.lib().wgb_comm_destroy(dev._h)
         # ---- fused forms
-        for name, epi, depth, deferred in FUSED_FORMS:
+        for name, epi, depth, deferred, symmetric in FUSED_FORMS:
             os.environ["WGB_TC_EPI"] = str(epi)
-            group = sharded.PeerGather(dev, dist, rank, world, m_local, N, "bf16", depth=depth)
+            group = sharded.PeerGather(dev, dist, rank, world, m_local, N, "bf16", depth=depth, symmetric=symmetric)
+            if symmetric and epi == 2 and not group.multicast:
+                if rank == 0:
+                    print(f"(no multicast mapping on this box: form {name} falls back to TMA stores)", flush=True)
             snaps = [w.TensorBuilder.tensor((m_local, N, world), ST).build(dev, "bf16") for _ in range(steps)]
             enc = dev.create_command_encoder()
             with enc.compute_pass("fused", None) as p:
@@ -130,6 +135,7 @@ def main():
         base = results["tma-d1"]
         forms_equal = all(np.array_equal(results[name][s], base[s]) for name, *_ in FUSED_FORMS for s in range(steps))
         epi_ran = results["tma-d1:cfg"]["epi_tma"] == 1 and results["stg-d1:cfg"]["epi_tma"] == 0 and results["tma-d1:cfg"]["dests"] == world
+        mc_ran = results["mc-d1:cfg"]["epi_tma"] == 2 and results["mc-d3-deferred:cfg"]["epi_tma"] == 2
         err = 0.0
         same = True
         rows = np.array(sorted({0, 1, m_local - 1, m_local % M, M // 2, M - 1, (7 * m_local + 13) % M}))
@@ -150,7 +156,7 @@ def main():
         good = forms_equal and epi_ran and same and err < 1e-2 and results.get("host_ok_splitb0", False) and results.get("host_ok_splitb1", False)
         ok &= good
         print(f"[rank {rank}] {M}x{N}x{K} tr={int(tr)} world={world} steps={steps}: fused forms bit-identical {forms_equal} "
-              f"(tma/stg epilogues ran: {epi_ran}), nccl~fused {same}, host-enqueue == device path (whole B / sliced B + all-gather): "
+              f"(tma/stg epilogues ran: {epi_ran}, multicast epilogue ran: {mc_ran}), nccl~fused {same}, host-enqueue == device path (whole B / sliced B + all-gather): "
               f"{results.get('host_ok_splitb0')} / {results.get('host_ok_splitb1')}, rel err vs f64 {err:.3e} -> {'OK' if good else 'FAIL'}",
               flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")

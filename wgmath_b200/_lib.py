@@ -114,7 +114,10 @@ def lib() -> ctypes.CDLL:
         "wgb_peer_gather_buffer": ([vp, pvp], ci),
         "wgb_peer_gather_destroy": ([vp], ci),
         "wgb_peer_gather_disconnect": ([vp], ci),
+        "wgb_peer_gather_region_bytes": ([sz, ci], sz),
+        "wgb_peer_gather_create_external": ([vp, ci, ci, sz, ci, pvp, vp, pvp], ci),
         "wgb_peer_gather_debug_flags": ([vp, ctypes.POINTER(u32)], ci),
+        "wgb_debug_link_stream": ([vp, ci, pvp, ci, vp, sz, ci, ci, ctypes.POINTER(ctypes.c_float)], ci),
         "wgb_gemm_row_sharded_fused": ([vp, ci, vp, vp, sp, vp, sp, ci, ci, ci], ci),
         "wgb_gemm_row_sharded_fused_host_enqueue": ([vp, ci, vp, u32, u32, u32, vp, vp, vp, ci, ci, ci, ci], ci),
     }
@@ -139,7 +142,7 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",
             "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded", "wgb_peer_gather_create",
             "wgb_peer_gather_export", "wgb_peer_gather_connect", "wgb_peer_gather_buffer", "wgb_peer_gather_destroy",
-            "wgb_gemm_row_sharded_fused", "wgb_gemm_row_sharded_fused_host_enqueue", "wgb_peer_gather_create_ex", "wgb_peer_gather_disconnect", "wgb_peer_gather_debug_flags",
+            "wgb_gemm_row_sharded_fused", "wgb_gemm_row_sharded_fused_host_enqueue", "wgb_peer_gather_create_ex", "wgb_peer_gather_disconnect", "wgb_peer_gather_debug_flags", "wgb_debug_link_stream", "wgb_peer_gather_region_bytes", "wgb_peer_gather_create_external",
             "wgb_peer_gather_connect_local", "wgb_peer_gather_buffer_at", "wgb_peer_gather_wait", "wgb_gemm_row_sharded_fused_ex"]
 
 

@@ -250,8 +250,10 @@ struct wgb_peer_gather {
     wgb_ctx *ctx = nullptr;
     int nranks = 1, rank = 0, depth = 1;
     size_t data_bytes = 0;          // one gathered buffer (256-byte multiple)
-    char *local = nullptr;          // cudaMalloc: [depth][data_bytes][signal block]
+    char *local = nullptr;          // [depth][data_bytes][signal block]: cudaMalloc, or the caller's symmetric allocation
     char *peer[wgb::kMaxPeers] = {};
+    char *mc = nullptr;             // multicast mapping of the same allocation (external groups only; null: none)
+    bool external = false;          // memory and mappings belong to the caller (wgb_peer_gather_create_external)
     bool ipc_opened[wgb::kMaxPeers] = {};
     bool connected = false;
     unsigned int epoch = 0;
@@ -327,6 +329,56 @@ wgb_status wgb_peer_gather_create_ex(wgb_ctx *ctx, int nranks, int rank, size_t 
     cudaDeviceSynchronize();
     pg->peer[rank] = pg->local;
     pg->connected = nranks == 1;
+    for (int d = 0; d < depth; ++d) {
+        pg->view[d].ctx = ctx;
+        pg->view[d].ptr = pg->local + (size_t)d * pg->data_bytes;
+        pg->view[d].bytes = gathered_bytes;
+        pg->view[d].owned = false;
+        pg->view[d].usage = WGB_USAGE_STORAGE | WGB_USAGE_COPY_SRC | WGB_USAGE_COPY_DST;
+    }
+    wgb::ctx_retain(ctx);
+    *out = pg;
+    return WGB_OK;
+}
+
+size_t wgb_peer_gather_region_bytes(size_t gathered_bytes, int depth) {
+    return (size_t)(depth < 1 ? 1 : depth) * ((gathered_bytes + 255) & ~(size_t)255) + wgb::kSignalBytes;
+}
+
+// A group over memory the caller allocated symmetrically on every rank (same size, same layout) and mapped both ways: peer_bases[q]
+// = this process's unicast mapping of rank q's region, multicast_base = the region through an NVSwitch multicast object bound on
+// all ranks (or null).  Any allocator that can do this works (cuMem* + cuMulticast* directly; torch's symmetric memory in the
+// Python mirror).  The region must hold wgb_peer_gather_region_bytes() bytes; nothing is freed or unmapped by the library.
+wgb_status wgb_peer_gather_create_external(wgb_ctx *ctx, int nranks, int rank, size_t gathered_bytes, int depth, void *const *peer_bases,
+                                           void *multicast_base, wgb_peer_gather **out) {
+    if (!ctx || !out || !peer_bases || nranks < 1 || nranks > wgb::kMaxPeers || rank < 0 || rank >= nranks)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_create_external: bad argument (at most %d ranks)", wgb::kMaxPeers);
+    if (depth < 1 || depth > 3) WGB_FAIL(WGB_ERR_INVALID, "wgb_peer_gather_create_external: depth must be 1, 2 or 3");
+    for (int q = 0; q < nranks; ++q)
+        if (!peer_bases[q] || ((uintptr_t)peer_bases[q] & 255u)) WGB_FAIL(WGB_ERR_INVALID, "peer base %d is null or not 256-byte aligned", q);
+    if ((uintptr_t)multicast_base & 255u) WGB_FAIL(WGB_ERR_INVALID, "multicast base is not 256-byte aligned");
+    DeviceGuard g(ctx->device);
+    wgb_peer_gather *pg = new wgb_peer_gather();
+    pg->ctx = ctx;
+    pg->nranks = nranks;
+    pg->rank = rank;
+    pg->depth = depth;
+    pg->external = true;
+    pg->data_bytes = (gathered_bytes + 255) & ~(size_t)255;
+    pg->timeout_cycles = wgb::peer_timeout_cycles(ctx);
+    cudaFuncAttributes fa;
+    (void)cudaFuncGetAttributes(&fa, wgb::signal_ready_kernel);
+    (void)cudaFuncGetAttributes(&fa, wgb::wait_done_kernel);
+    pg->local = (char *)peer_bases[rank];
+    for (int q = 0; q < nranks; ++q) pg->peer[q] = (char *)peer_bases[q];
+    pg->mc = (char *)multicast_base;
+    cudaError_t e = cudaMemset(pg->local + pg->signal_off(), 0, wgb::kSignalBytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        delete pg;
+        WGB_FAIL(WGB_ERR_CUDA, "wgb_peer_gather_create_external: cannot clear the flag block: %s", cudaGetErrorString(e));
+    }
+    pg->connected = true;   // (the caller synchronises the ranks after creation: a peer's first flag must not be cleared by a late memset)
     for (int d = 0; d < depth; ++d) {
         pg->view[d].ctx = ctx;
         pg->view[d].ptr = pg->local + (size_t)d * pg->data_bytes;
@@ -418,6 +470,93 @@ wgb_status wgb_peer_gather_wait(wgb_pass *pass, wgb_peer_gather *pg, int calls_b
     return WGB_OK;
 }
 
+}  // extern "C"
+namespace wgb {
+// ------------------------------------------------------------------------------------------------------------
+// Link micro-benchmark (diagnostics): how fast can the SMs of one GPU push a buffer to `ndst` destinations —
+//   mode 0  st.global.v4 (16 B per lane, 512 B per warp instruction) to unicast addresses (local or peer mappings)
+//   mode 1  multimem.st.global.v4.f32 to ONE multicast address (NVSwitch replicates to every GPU of the group)
+//   mode 2  cp.async.bulk shared -> global (TMA bulk stores, 16 KiB each) to unicast addresses
+// Each CTA streams its slice of `src` once per destination.  Used to size the fused all-gather (profiles/).
+// ------------------------------------------------------------------------------------------------------------
+struct LinkDsts {
+    char *p[kMaxPeers];
+};
+__global__ void __launch_bounds__(256) link_stream_kernel(int mode, LinkDsts dsts, int ndst, const char *__restrict__ src, size_t bytes) {
+    extern __shared__ __align__(128) unsigned char link_smem[];
+    const size_t chunk = 16384;
+    const size_t nchunks = bytes / chunk;
+    if (mode == 2) {
+        // fill two staging buffers once (the payload does not matter for the rate), then keep two bulk groups in flight
+        for (int i = threadIdx.x; i < (int)(2 * chunk / 16); i += blockDim.x)
+            reinterpret_cast<uint4 *>(link_smem)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t k = 0;
+            for (size_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++k) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                const uint32_t s = (uint32_t)__cvta_generic_to_shared(link_smem + (k & 1u) * chunk);
+                for (int d = 0; d < ndst; ++d)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dsts.p[(d + blockIdx.x) % ndst] + c * chunk),
+                                 "r"(s), "r"((uint32_t)chunk)
+                                 : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        return;
+    }
+    const size_t n16 = bytes / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(reinterpret_cast<const uint4 *>(src) + i);
+        if (mode == 1) {
+            asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dsts.p[0] + i * 16), "f"(__uint_as_float(v.x)),
+                         "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                         : "memory");
+        } else {
+            for (int d = 0; d < ndst; ++d) {
+                uint4 *q = reinterpret_cast<uint4 *>(dsts.p[(d + blockIdx.x) % ndst]) + i;
+                asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(q), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+        }
+    }
+}
+}  // namespace wgb
+extern "C" {
+
+wgb_status wgb_debug_link_stream(wgb_ctx *ctx, int mode, void *const *dsts, int ndst, const void *src, size_t bytes, int ctas, int iters,
+                                 float *ms_per_iter) {
+    if (!ctx || !dsts || !src || !ms_per_iter || ndst < 1 || ndst > wgb::kMaxPeers || mode < 0 || mode > 2 || iters < 1)
+        WGB_FAIL(WGB_ERR_INVALID, "wgb_debug_link_stream: bad argument");
+    if (bytes % 32768 != 0) WGB_FAIL(WGB_ERR_INVALID, "wgb_debug_link_stream: bytes must be a multiple of 32 KiB");
+    DeviceGuard g(ctx->device);
+    wgb::LinkDsts d{};
+    for (int i = 0; i < ndst; ++i) d.p[i] = (char *)dsts[i];
+    if (ctas <= 0) ctas = ctx->prop.multiProcessorCount * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+        WGB_CUDA(cudaFuncSetAttribute(wgb::link_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768));
+        attr_set = true;
+    }
+    cudaEvent_t e0, e1;
+    WGB_CUDA(cudaEventCreate(&e0));
+    WGB_CUDA(cudaEventCreate(&e1));
+    wgb::link_stream_kernel<<<ctas, 256, 32768, ctx->stream>>>(mode, d, ndst, (const char *)src, bytes);   // warm-up
+    WGB_CUDA(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < iters; ++i) wgb::link_stream_kernel<<<ctas, 256, 32768, ctx->stream>>>(mode, d, ndst, (const char *)src, bytes);
+    WGB_CUDA(cudaEventRecord(e1, ctx->stream));
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) WGB_FAIL(WGB_ERR_CUDA, "wgb_debug_link_stream: %s", cudaGetErrorString(e));
+    count_launch(ctx, iters + 1);
+    *ms_per_iter = ms / iters;
+    return WGB_OK;
+}
+
 // Diagnostics: a snapshot of this rank's flag block taken on a private stream, so it can be read while the queues are busy
 // (or stuck): out[0..8) = ready[q], out[8..16) = done[q], out[16] = CTA counter, out[17] = this rank's call count (host side).
 wgb_status wgb_peer_gather_debug_flags(wgb_peer_gather *pg, unsigned int *out /* 18 words */) {
@@ -463,7 +602,7 @@ wgb_status wgb_peer_gather_destroy(wgb_peer_gather *pg) {
     if (!pg) return WGB_OK;
     wgb_peer_gather_disconnect(pg);
     DeviceGuard g(pg->ctx->device);
-    if (pg->local) cudaFree(pg->local);
+    if (pg->local && !pg->external) cudaFree(pg->local);
     wgb_ctx *ctx = pg->ctx;
     delete pg;
     wgb::ctx_release(ctx);
@@ -501,6 +640,7 @@ wgb_status wgb_gemm_row_sharded_fused_ex(wgb_pass *pass, wgb_gemm_variant varian
     f.rank = rank;
     f.epoch = epoch;
     f.timeout = pg->timeout_cycles;
+    f.mc_c = pg->mc ? pg->mc + buf_off : nullptr;
     for (int q = 0; q < P; ++q) {
         f.peer_c[q] = pg->peer[q] + buf_off;
         f.done_remote[q] = reinterpret_cast<unsigned int *>(pg->peer[q] + pg->signal_off()) + wgb::kDoneOff;

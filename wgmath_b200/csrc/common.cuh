@@ -178,6 +178,7 @@ constexpr int kMaxPeers = 8;
 struct FusedGather {
     int nranks = 1, rank = 0;
     void *peer_c[kMaxPeers] = {};            // gathered buffer of rank q (peer mapping; [rank] is the local one)
+    void *mc_c = nullptr;                    // the same buffer through the group's NVSwitch multicast mapping (null: none)
     unsigned int *ready_local = nullptr;     // ready_local[q]: rank q may be written into for epoch >= value
     unsigned int *done_remote[kMaxPeers] = {};  // done array of rank q (we write entry [rank])
     unsigned int *cta_counter = nullptr;     // local: CTAs finished (left at zero)

@@ -363,6 +363,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     TcArgs args{};
     args.c = (char *)g.c + g.c_off * dtype_size(g.out_dtype);
     args.npeers = 1;
+    args.store_mask = 0xFFFFFFFFu;
     args.dst[0] = (char *)args.c;
     args.mbar_timeout = 8000000000ll;
     if (g.fused && g.fused->nranks > 1) {
@@ -378,6 +379,11 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         args.ready_local = f.ready_local;
         args.cta_counter = f.cta_counter;
         args.peer_timeout = f.timeout;
+        if (env_int("WGB_FUSED_ROTATE", 1) != 0) args.first_dst = (uint32_t)((f.rank + 1) % f.nranks);
+        // diagnostics only (results on the skipped ranks are garbage): which destinations the epilogue really stores to
+        const int mask = env_int("WGB_FUSED_DEBUG_STORE_MASK", -1);
+        if (mask == -2) args.store_mask = 1u << f.rank;              // local copy only: the GEMM and the handshake without NVLink traffic
+        else if (mask >= 0) args.store_mask = (uint32_t)mask;
         args.mbar_timeout = f.timeout > 0 ? f.timeout + 8000000000ll : 0;   // the pipeline stalls behind an epilogue that waits for peers
     }
     args.ldc = g.ldc; args.sc = g.sc;
@@ -435,10 +441,24 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     // the all-gather is fused in (every output block then leaves the SM once per rank of the box).
     {
         const size_t os = dtype_size(g.out_dtype);
-        const int want = env_int("WGB_TC_EPI", args.npeers > 1 ? 1 : 0);
+        const bool fused = g.fused && g.fused->nranks > 1;
+        const bool mc_ok = fused && g.fused->mc_c != nullptr;
+        // fused all-gather: multicast stores when the group has a multicast mapping, else TMA bulk stores to every rank
+        int want = env_int("WGB_TC_EPI", fused ? (mc_ok ? 2 : 1) : 0);
+        if (want == 2 && !mc_ok) want = fused ? 1 : 0;
         bool ok = want != 0 && (g.ldc * os) % 16 == 0 && (g.nmats <= 1 || (g.sc * os) % 16 == 0);
         for (uint32_t d = 0; ok && d < args.npeers; ++d) ok = ((uintptr_t)args.dst[d] & 15u) == 0;
-        if (ok) {
+        if (ok && want == 2) {
+            // 16-byte pieces must not straddle the last row: M a multiple of the piece (8 bf16 / 4 f32 rows)
+            char *mc = (char *)g.fused->mc_c + g.c_off * os;
+            if (((uintptr_t)mc & 15u) == 0 && (g.M * os) % 16 == 0) {
+                args.epi_tma = 2;
+                args.mc_dst = mc;
+            } else {
+                want = 1;
+            }
+        }
+        if (ok && want == 1) {
             for (uint32_t d = 0; d < args.npeers; ++d)
                 WGB_TRY(get_tmap(ctx, args.dst[d], (uint32_t)os, g.M, g.N, g.nmats, g.ldc, g.sc, 128u, (uint32_t)kEpiCols, &maps.dst.m[d],
                                  false, true));

@@ -111,6 +111,12 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // generic-proxy shared-memory writes -> visible to the async proxy (TMA) that reads them next
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// 16 bytes to a multicast address: the NVSwitch writes them at the same offset of every GPU bound to the multicast object
+__device__ __forceinline__ void multimem_st16(void *mc_addr, const uint4 &v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
@@ -240,6 +246,9 @@ struct TcArgs {
     // columns, each a complete (narrower) output tile: the last wave fills the machine and needs no fix-up.
     uint32_t nsplit, tail_bn, idesc_tail;
     uint32_t epi_tma;        // 1: the epilogue stages 128 x 32 blocks in shared memory and leaves with TMA bulk stores (dst maps)
+                             // 2: same staging, the block leaves with multimem.st to mc_dst (NVSwitch multicast: one store
+                             //    instruction lands in the gathered buffer of every rank, this one included)
+    char *mc_dst;            // multicast address of element 0 of this rank's output view (epi_tma == 2)
     int ep_op;               // fused element-wise epilogue (-1: none): out = acc (op) e
     const void *ep;          // operand view base (element 0 of the view), element type = TOut
     uint64_t ep_ld, ep_sm;
@@ -249,6 +258,9 @@ struct TcArgs {
     unsigned int *counters;  // [tail tile][cta rank] arrival tickets (left at zero)
     // fused all-gather over peer memory (npeers == 1: plain GEMM, dst[0] == c)
     uint32_t npeers, my_rank, epoch, handshake;
+    uint32_t first_dst;                       // destination the store loops start with: rank + 1, so that at any moment the ranks of
+                                              // a box aim at different peers (no hot ingress port), the local copy last
+    uint32_t store_mask;                      // diagnostics (WGB_FUSED_DEBUG_STORE_MASK): bit d clear = skip destination d
     long long peer_timeout;                   // bound of the ready-flag wait in SM cycles (0: unbounded)
     long long mbar_timeout;                   // bound of every mbarrier wait in SM cycles (0: unbounded)
     char *dst[kMaxPeers];                     // where this rank's panel lives in rank d's gathered buffer
@@ -415,7 +427,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             prefetch_tmap(&tmBlo);
             prefetch_tmap(&tmBlot);
         }
-        if (tma_epi)
+        if (args.epi_tma == 1)
             for (uint32_t d = 0; d < args.npeers; ++d) prefetch_tmap(&dmaps.m[d]);
     }
     if (warp == 1 && lane == 0) {
@@ -661,9 +673,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         for (int i = 0; i < 32; ++i) store_out<TOut>(sp + i * kBlockM, __uint_as_float(cur[i]));
                         fence_proxy_async_smem();
                         asm volatile("bar.sync 1, 128;" ::: "memory");
-                        if (threadIdx.x == 128) {
+                        if (args.epi_tma == 2) {
+                            // multicast: every thread re-reads 16-byte pieces of the staged block (a column of the block is
+                            // 128 rows = 16 (bf16) / 32 (f32) pieces) and stores each ONCE; the switch replicates it
+                            constexpr int PPC = kBlockM * (int)sizeof(TOut) / 16;          // pieces per column
+                            constexpr int EPP = 16 / (int)sizeof(TOut);                    // elements per piece
+                            const uint32_t r0 = mt * (kBlockM * CG) + cta_rank * kBlockM, c0 = n0 + c * 32;
+                            char *mbase = args.mc_dst + ((uint64_t)bt * args.sc + r0) * sizeof(TOut);
+#pragma unroll
+                            for (int j = 0; j < kEpiCols * PPC / 128; ++j) {
+                                const uint32_t p = (threadIdx.x - 128) + 128 * j;
+                                const uint32_t col = p / PPC, piece = p % PPC;
+                                if (c0 + col < args.N && r0 + piece * EPP < args.M)
+                                    multimem_st16(mbase + ((uint64_t)(c0 + col) * args.ldc) * sizeof(TOut) + piece * 16,
+                                                  *reinterpret_cast<const uint4 *>(blk + (col * PPC + piece) * 16));
+                            }
+                        } else if (threadIdx.x == 128) {
                             const int r0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM), c0 = (int)(n0 + c * 32);
-                            for (uint32_t d = 0; d < args.npeers; ++d) tma_store_3d(&dmaps.m[d], smem_u32(blk), r0, c0, (int)bt);
+                            uint32_t d = args.first_dst;
+                            for (uint32_t i = 0; i < args.npeers; ++i) {
+                                if ((args.store_mask >> d) & 1u) tma_store_3d(&dmaps.m[d], smem_u32(blk), r0, c0, (int)bt);
+                                if (++d == args.npeers) d = 0;
+                            }
                             bulk_commit();
                         }
                         __syncwarp();
@@ -677,13 +708,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     cur[i] = __float_as_uint(epilogue_apply<TOut>(args.ep_op, __uint_as_float(cur[i]), erow + (uint64_t)col * args.ep_ld));
                             }
                         }
-                        for (uint32_t d = 0; d < args.npeers; ++d) {   // npeers == 1 unless the all-gather is fused in
-                            TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
+                        uint32_t d = args.first_dst;
+                        for (uint32_t k = 0; k < args.npeers; ++k) {   // npeers == 1 unless the all-gather is fused in
+                            if ((args.store_mask >> d) & 1u) {
+                                TOut *crow = reinterpret_cast<TOut *>(args.dst[d]) + crow_off;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const uint32_t col = n0 + c * 32 + i;
-                                if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(cur[i]));
+                                for (int i = 0; i < 32; ++i) {
+                                    const uint32_t col = n0 + c * 32 + i;
+                                    if (col < args.N) store_out<TOut>(crow + (uint64_t)col * args.ldc, __uint_as_float(cur[i]));
+                                }
                             }
+                            if (++d == args.npeers) d = 0;
                         }
                     }
                 };

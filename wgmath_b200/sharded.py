@@ -72,12 +72,32 @@ class PeerGather:
     ahead, 3 = additionally the wait may trail the GEMMs by one call).  One process per GPU: handles travel through `dist`
     (torch.distributed, any backend).  `PeerGather.local_group` builds all ranks inside one process instead."""
 
-    def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16", depth: int = 1, _connect=True):
+    def __init__(self, device, dist, rank: int, world: int, m_local: int, N: int, dtype: str = "bf16", depth: int = 1, _connect=True,
+                 symmetric: bool = False):
         self._device, self.rank, self.world, self.depth = device, rank, world, depth
         self._dist = dist if (_connect and world > 1) else None
         self._shape, self._dtype = (m_local, N, world), dtype
         self._nbytes = world * m_local * N * (2 if dtype == "bf16" else 4)
+        self.multicast = False
         h = ctypes.c_void_p()
+        if symmetric:
+            # Symmetric allocation + NVSwitch multicast mapping through torch's symmetric-memory allocator (plumbing: it creates
+            # the cuMem allocations, exchanges the handles between the processes and binds the multicast object); the library
+            # only receives pointers (wgb_peer_gather_create_external).  With a multicast mapping the fused epilogue stores each
+            # output block once and the switch replicates it.
+            import torch
+            import torch.distributed._symmetric_memory as symm_mem
+            region = lib().wgb_peer_gather_region_bytes(self._nbytes, depth)
+            t = symm_mem.empty(region, dtype=torch.uint8, device=f"cuda:{device.ordinal}")
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            bases = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            mc = int(hdl.multicast_ptr or 0)
+            check(lib().wgb_peer_gather_create_external(device._h, world, rank, self._nbytes, depth, bases, ctypes.c_void_p(mc or None),
+                                                        ctypes.byref(h)))
+            self._h, self._symm, self.multicast = h, (t, hdl), mc != 0
+            torch.cuda.synchronize()
+            dist.barrier()          # every rank's flag block is cleared before anyone's first product
+            return
         check(lib().wgb_peer_gather_create_ex(device._h, world, rank, self._nbytes, depth, ctypes.byref(h)))
         self._h = h
         if not _connect:
@@ -134,6 +154,7 @@ class PeerGather:
             if collective and self._dist is not None:
                 self._dist.barrier()
             lib().wgb_peer_gather_destroy(h)
+            self._symm = None
 
     def __del__(self):
         try:
