@@ -516,18 +516,20 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
     lock = None
     cfg = {}
     if mode == "fused":
-        group1 = sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=1)
+        # gathered buffers in symmetric memory with an NVSwitch multicast mapping when the box offers one (every output block is
+        # then stored once and replicated by the switch); otherwise CUDA-IPC peer mappings and one TMA bulk store per rank
+        symmetric = os.environ.get("WGB_SHARD_SYMMETRIC", "1") not in ("", "0")
+        sym_note = None
 
-        def lock_step(p, i):
-            op.dispatch_fused(dev, shapes, p, group1, a, b)
-        lsec, _ = timed(lock_step, args.steps, args.warmup)
-        lock = {"value": flops * args.steps / lsec / 1e12, "unit": "TFLOP/s", "ms_per_step": lsec * 1e3 / args.steps,
-                "ms_per_step_by_rank": getattr(timed, "per_rank_ms", None),
-                "what": "one gathered buffer, every call waits for all peers' panels before the next GEMM starts"}
-        if dist is not None:
-            dist.barrier()
-        group1.close()
-        group = sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=3)
+        def make_group(depth):
+            nonlocal symmetric, sym_note
+            if symmetric:
+                try:
+                    return sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=depth, symmetric=True)
+                except Exception as e:      # no symmetric-memory support here: every rank takes the same fallback
+                    symmetric, sym_note = False, repr(e)[:200]
+            return sharded.PeerGather(dev, dist, rank, ngpu, m_local, n, "bf16", depth=depth)
+        group = make_group(3)
         calls = [0]
 
         def step_fn(p, i):
@@ -547,6 +549,7 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
         clocks_main = sampler.summary(since=mark)
         by_rank = getattr(timed, "per_rank_ms", None)
         c = group.tensor_at(0)
+        multicast = bool(group.multicast)
     else:
         group = None
         by_rank = None
@@ -558,6 +561,19 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
         clocks_main = sampler.summary(since=mark)
     value = flops * args.steps / sec / 1e12
     ms_step = sec * 1e3 / args.steps
+    if mode == "fused":
+        # the same steps in lock step (one gathered buffer, the wait inside every call): what the deferral is worth.  Measured
+        # after the headline, i.e. on parts that are already warm.
+        group1 = make_group(1)
+
+        def lock_step(p, i):
+            op.dispatch_fused(dev, shapes, p, group1, a, b)
+        lsec, _ = timed(lock_step, args.steps, args.warmup)
+        lock = {"value": flops * args.steps / lsec / 1e12, "unit": "TFLOP/s", "ms_per_step": lsec * 1e3 / args.steps,
+                "ms_per_step_by_rank": getattr(timed, "per_rank_ms", None),
+                "what": "one gathered buffer, every call waits for all peers' panels before the next GEMM starts; measured after the "
+                        "headline run (warm parts)"}
+        group1.close()
     # ---- parity, on every rank: elements (row r, column j) of the gathered cube for rows spread over every rank's panel
     L = lib()
     rows = sorted({0, 1, m_local - 1, m_local, n // 2 + 17, n - m_local - 1, n - 1, (5 * m_local + 4095) % n})
@@ -591,7 +607,8 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
     comm_bytes = (ngpu - 1) * m_local * n * 2
     kname = ((f"gemm_tc_kernel<{cfg.get('kind')}, {cfg.get('a_mn')}, {cfg.get('b_mn')}, {cfg.get('bn')}, {cfg.get('passes')}, __nv_bfloat16, "
               f"{cfg.get('cg')}> (tcgen05) with the all-gather of C fused into the epilogue: "
-              f"{'TMA bulk stores' if cfg.get('epi_tma') else 'per-lane stores'} to {cfg.get('dests')} gathered buffers over NVLink")
+              f"{ {0: 'per-lane stores to', 1: 'TMA bulk stores to', 2: 'multimem.st (NVSwitch multicast), one store for'}[cfg.get('epi_tma', 0)]}"
+              f" {cfg.get('dests')} gathered buffers over NVLink")
              if group is not None else "gemm_tc<bf16> (tcgen05) + chunked all-gather of C (NCCL send/recv over NVLink)")
     flop_ms = flops / ngpu / (peaks["bf16_tflops_sustained" if long_run else "bf16_tflops"] * 1e12) * 1e3
     link_ms = comm_bytes / 770e9 * 1e3
@@ -606,6 +623,11 @@ def bench_row_sharded(w, O, gpu, shapes, dist, ngpu, rank, args, timed, peaks, s
         roof["lockstep"] = lock
     wl_extra = {"gather": ("fused into the GEMM epilogue; three rotating gathered buffers, the wait for step e queued behind the GEMM of "
                            "step e + 1, the last wait inside the timed region" if group is not None else "NCCL send/recv, chunked")}
+    if group is not None:
+        wl_extra["gathered_memory"] = ("symmetric memory + NVSwitch multicast mapping" if multicast else
+                                       "symmetric memory, no multicast mapping" if symmetric else "cudaMalloc + CUDA IPC peer mappings")
+        if sym_note:
+            wl_extra["symmetric_memory_unavailable"] = sym_note
     # e2e: HOST buffers in, HOST buffer out, through the C ABI, every step: this rank's A block and its 1/P column slice of B go
     # up (the slices are all-gathered over NVLink: B crosses the host links once per box), the sharded GEMM + gather runs, this
     # rank's panel comes down — the ranks of the box assemble C in host memory, every byte of C crosses a host link once.

@@ -343,8 +343,9 @@ wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);
 /* The tcgen05 kernel instantiation and plan of that call (all zero unless the path is 2..4), WGB_TC_CONFIG_WORDS ints:
  *   [0] operand kind (0 bf16, 1 tf32)  [1] A MN-major  [2] B MN-major  [3] BLOCK_N  [4] MMA passes (3 = 3xTF32)
  *   [5] output wgb_dtype  [6] CTAs per tile (cta_group)  [7] epilogue (0 per-lane stores, 1 TMA bulk stores)
- *   [8] tail N-split factor  [9] tail split-K factor  [10] destinations per output block (fused all-gather: ranks)  [11] work units */
-#define WGB_TC_CONFIG_WORDS 12
+ *   [8] tail N-split factor  [9] tail split-K factor  [10] destinations per output block (fused all-gather: ranks)  [11] work units
+ *   [12] 3xTF32 operand split inside the GEMM (1) or by the split kernels (0) */
+#define WGB_TC_CONFIG_WORDS 13
 wgb_status wgb_pass_last_gemm_config(const wgb_pass *pass, int *config /* WGB_TC_CONFIG_WORDS */);
 
 /* gemv.rs:64-137.  out = m * v or tr(m) * v; v / out may carry several columns and batches. */

@@ -51,29 +51,6 @@ def test_gpu_prefix_sum_sub_view_leaves_the_rest_untouched(gpu):
     np.testing.assert_array_equal(t.read(), ref)
 
 
-@pytest.mark.parametrize("n", [(1 << 20), (1 << 20) + 1, 3 * (1 << 20) + 12345, (1 << 24) + 7])
-def test_gpu_prefix_sum_single_pass_lookback_variant(gpu, monkeypatch, n):
-    """WGB_SCAN_LOOKBACK=1: the single-pass decoupled look-back scan (16384-element tiles, 64-descriptor window) must give the
-    same bits as the three-step scan and as the oracle — full tiles, a ragged last tile, an unaligned sub-view, and twice in a
-    row on the same workspace (the ticket and the descriptors are reset per call)."""
-    monkeypatch.setenv("WGB_SCAN_LOOKBACK", "1")
-    rng = np.random.default_rng(n)
-    v = rng.integers(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
-    ps = w.WgPrefixSum.from_device(gpu.device())
-    ws = w.PrefixSumWorkspace.new()
-    ref = seq_exclusive(v)
-    for _ in range(2):
-        t = vec_u32(gpu, v)
-        run_pass(gpu, lambda p: ps.dispatch(gpu.device(), p, ws, t))
-        np.testing.assert_array_equal(t.read(), ref)
-    first = 4099                                            # unaligned start inside a larger buffer: scalar loads and stores
-    t = vec_u32(gpu, v)
-    run_pass(gpu, lambda p: ps.dispatch(gpu.device(), p, ws, t.rows(first, n - first - 5)))
-    want = v.copy()
-    want[first:n - 5] = seq_exclusive(v[first:n - 5])
-    np.testing.assert_array_equal(t.read(), want)
-
-
 def test_gpu_prefix_sum_empty_is_a_noop(gpu):
     t = vec_u32(gpu, np.arange(8, dtype=np.uint32))
     ps = w.WgPrefixSum.from_device(gpu.device())

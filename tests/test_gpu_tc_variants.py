@@ -46,9 +46,12 @@ def test_tc_instantiation(gpu, shapes, monkeypatch, inst):
     tol = (1e-5 if passes == 3 else 2e-3) if f32 else (1e-2 if out == "bf16" else 1e-4)
     # how a kernel with a K-major A is reached: the transposed variant; for f32 also the non-transposed product through the
     # transposing operand prep (WGB_TF32_MN_DIRECT=0)
-    routes = [dict(tr=not a_mn, env={"WGB_TF32_MN_DIRECT": "1"})]
+    routes = [dict(tr=not a_mn, env={"WGB_TF32_MN_DIRECT": "1", "WGB_TF32_FUSED_SPLIT": "0"}, fs=0)]
     if f32 and not a_mn:
-        routes.append(dict(tr=False, env={"WGB_TF32_MN_DIRECT": "0"}))
+        routes.append(dict(tr=False, env={"WGB_TF32_MN_DIRECT": "0", "WGB_TF32_FUSED_SPLIT": "1"}, fs=0))   # transposing prep: no in-kernel split
+    if passes == 3:
+        # the FS kernels (operand split inside the GEMM, raw f32 tiles by TMA) are separate instantiations of the same family
+        routes.append(dict(tr=not a_mn, env={"WGB_TF32_MN_DIRECT": "1", "WGB_TF32_FUSED_SPLIT": "1"}, fs=1))
     seen = set()
     for route, (plan, plan_env), epi, sh in itertools.product(routes, TAIL_PLANS.items(), (0, 1), SHAPES):
         for k, v in {**route["env"], **plan_env, "WGB_TC_EPI": str(epi)}.items():
@@ -61,6 +64,7 @@ def test_tc_instantiation(gpu, shapes, monkeypatch, inst):
         got = (("tf32" if c["kind"] else "bf16"), c["a_mn"], c["b_mn"], c["bn"], c["passes"], "bf16" if c["out_dtype"] == 1 else "f32", c["cg"])
         assert got == inst, f"forced {inst_id(inst)} but {got} ran"
         assert c["epi_tma"] == epi
+        assert c["fused_split"] == route["fs"]
         if plan == "none":
             assert c["nsplit"] == 1 and c["splitk"] == 1
         seen.add((plan, c["nsplit"] > 1, c["splitk"] > 1))

@@ -275,7 +275,19 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     // An N-contiguous (row-major) f32 m2 is always re-materialised K-major by the transposing prep; a bf16 one is read in
     // place as an MN-major B operand.
     const bool transpose_b = f32 && g.b_nmajor;
-    const bool prep_a = f32 && (passes == 3 || transpose_a), prep_b = f32 && (passes == 3 || transpose_b);
+    // 3xTF32 with the operand split inside the GEMM (FS kernels): the raw f32 views are TMA-loaded as they are, so both must meet
+    // TMA's alignment rules and need no transposing prep; anything else is re-materialised as dense hi / lo copies by the
+    // split kernels first (WGB_TF32_FUSED_SPLIT=0 forces that form)
+    // Which one: both forms are shared-memory-bandwidth bound at BLOCK_N = 128 (per k-block the three MMA passes read 96 KB, TMA
+    // writes 48 KB of hi / lo or 24 KB of raw tiles, and the in-kernel split adds 24 KB read + 24 KB written through the LSU,
+    // which measured 1.5x slower per k-block), so the in-kernel split wins only while the two split launches (~7 us) cost more than
+    // that: measured 13.3 vs 17.3 us at 256^3, 19.3 vs 21.1 at 512^3, 35.4 vs 35.9 at 1024^3, 132 vs 115 at 2048^3
+    // (profiles/README.md).  WGB_TF32_FUSED_SPLIT = 0 / 1 forces one form, unset = by size.
+    const int fs_env = env_int("WGB_TF32_FUSED_SPLIT", -1);
+    const bool fs_wanted = fs_env >= 0 ? fs_env != 0 : (uint64_t)g.M * g.N * g.K <= ((uint64_t)1 << 30);
+    const bool fused_split = f32 && passes == 3 && !transpose_a && !transpose_b && fs_wanted &&
+                             aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4) && aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4);
+    const bool prep_a = f32 && !fused_split && (passes == 3 || transpose_a), prep_b = f32 && !fused_split && (passes == 3 || transpose_b);
     if (f32 && ((!prep_a && !aligned_operand(g.a, g.a_off, g.lda, g.sa, g.nmats, 4)) ||
                 (!prep_b && !aligned_operand(g.b, g.b_off, g.ldb, g.sb, g.nmats, 4)))) {
         if (g.fused && g.fused->nranks > 1)   // the FFMA kernel has no peer stores: never drop the all-gather silently
@@ -352,7 +364,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     WGB_TRY(get_tmap(ctx, a_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &ta, atom32));
     if (b_mn) WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.N, g.K, g.nmats, ldb, sb, (uint32_t)(128 / es), block_k, &tb));   // one 128 B atom of N
     else WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tb));
-    if (passes == 3) {
+    if (passes == 3 && !fused_split) {
         WGB_TRY(get_tmap(ctx, alo_ptr, (uint32_t)es, a_rows, a_cols, g.nmats, lda, sa, a_box0, a_box1, &talo, atom32));
         WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, (uint32_t)(bn / cg), &tblo));
     } else {
@@ -411,6 +423,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
             }
         }
     }
+    args.fused_split = fused_split ? 1u : 0u;
     args.ep_op = g.ep_op;
     args.ep = g.e ? (const char *)g.e + g.e_off * dtype_size(g.out_dtype) : nullptr;
     args.ep_ld = g.lde;
@@ -422,7 +435,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
     maps.blot = tblo;
     if (args.nsplit > 1 && !b_mn) {   // (MN-major B: the box is one atom whatever the strip width)
         WGB_TRY(get_tmap(ctx, b_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.bt));
-        if (passes == 3) WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.blot));
+        if (passes == 3 && !fused_split) WGB_TRY(get_tmap(ctx, blo_ptr, (uint32_t)es, g.K, g.N, g.nmats, ldb, sb, block_k, args.tail_bn / (uint32_t)cg, &maps.blot));
         else maps.blot = maps.bt;
     }
     if (args.split > 1) {
@@ -470,6 +483,7 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         int *c = p->last_tc;
         c[0] = f32 ? 1 : 0; c[1] = tr ? 0 : 1; c[2] = b_mn ? 1 : 0; c[3] = bn; c[4] = passes; c[5] = (int)g.out_dtype; c[6] = cg;
         c[7] = (int)args.epi_tma; c[8] = (int)args.nsplit; c[9] = (int)args.split; c[10] = (int)args.npeers; c[11] = (int)args.total_units;
+        c[12] = (int)args.fused_split;
     }
     wgb_status st;
     if (!f32) {

@@ -58,6 +58,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
         : "memory");
     return done;
 }
+// cluster-scope acquire: the barrier is also arrived on (release.cluster) by the other CTA of the pair, whose shared-memory
+// writes the waiter's MMAs go on to read
+__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, long long limit) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity))
+        if (limit > 0 && clock64() - t0 > limit) __trap();
+}
 __device__ __forceinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, long long limit) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity))
@@ -252,6 +271,7 @@ struct TcArgs {
     int ep_op;               // fused element-wise epilogue (-1: none): out = acc (op) e
     const void *ep;          // operand view base (element 0 of the view), element type = TOut
     uint64_t ep_ld, ep_sm;
+    uint32_t fused_split;    // 3xTF32: the kernel splits the raw f32 tiles itself (FS instantiation) instead of reading hi / lo copies
     uint32_t debug_skip;     // diagnostics only (WGB_TC_DEBUG_SKIP): bit 0 = do not load A tiles, bit 1 = do not load B tiles
     unsigned long long *trace;   // diagnostics (wgb_debug_tc_trace): 8 words per cluster, null = off
     float *ws;               // [tail tile][split][cta rank][BN][128] f32 partial accumulators
@@ -322,6 +342,9 @@ constexpr int kSmemLimit = 227 * 1024;
 // data, i.e. -2.2e-5 at K = 2048).  The parity-gated 3xTF32 path therefore accumulates at most kChunkKb k-blocks
 // (256 k) per TMEM chain and the epilogue adds the chunks in f32 round-to-nearest into a running sum kept in TMEM.
 constexpr int kChunkKb = 8;
+// FS kernels: lo = x - trunc(x) is never negative, so the two cross terms are biased the same way as the main one and the
+// truncation bias per chain triples; chains of half the length keep the result where the pre-split form has it.
+constexpr int kChunkKbFs = 4;
 
 template <int BN, int PASSES, int CG>
 struct TcCfg {
@@ -377,7 +400,11 @@ __device__ __forceinline__ void store_out<__nv_bfloat16>(__nv_bfloat16 *p, float
 
 // KIND: 0 = bf16 (kind::f16), 1 = tf32.  A_MN: operand A is MN-major (the non-transposed product).
 // B_MN: operand B is MN-major, i.e. N is its contiguous axis (a row-major m2; bf16 only, f32 operands are re-materialised).
-template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
+// FS ("fused split", 3xTF32 only): TMA loads the caller's RAW f32 tiles; warps 2 and 3 write lo = x - trunc_tf32(x) beside them
+// (same swizzled layout, element for element) and the MMAs use the raw tile as `hi` — the tensor core reads an f32 operand by
+// truncating it to TF32 (measured: tools/tf32_input_probe.py), so hi + lo = x exactly.  No operand pre-pass, no dense hi / lo
+// copies in HBM.
+template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG, bool FS = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -393,7 +420,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int A_ATOM_BYTES = BLOCK_K * kRowBytes;     // one atom column: BLOCK_K rows of 128 B
     constexpr uint32_t IDESC = make_idesc(KIND, A_MN, B_MN, kBlockM * CG, BN);
     static_assert(!B_MN || KIND == 0, "MN-major B is implemented for 16-bit operands only");
+    static_assert(!FS || (PASSES == 3 && KIND == 1), "the in-kernel operand split belongs to 3xTF32");
     constexpr bool CHUNKED = PASSES == 3;
+    constexpr int CHUNK_KB = FS ? kChunkKbFs : kChunkKb;
     using Epi = TcEpi<BN, PASSES, CG, TOut>;
     constexpr int STG_BYTES = Epi::STG_BYTES;
     const bool tma_epi = args.epi_tma != 0;
@@ -407,7 +436,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t *empty_bar = bars + STAGES;          // [STAGES]
     uint64_t *tmem_full_bar = bars + 2 * STAGES;  // [2]
     uint64_t *tmem_empty_bar = bars + 2 * STAGES + 2;  // [2]
-    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 4);
+    uint64_t *conv_bar = bars + 2 * STAGES + 4;   // [STAGES]  (FS: lo tiles written by the converter warps of both CTAs)
+    uint32_t *tmem_ptr_smem = reinterpret_cast<uint32_t *>(bars + 3 * STAGES + 4);
     volatile uint32_t *split_flag = tmem_ptr_smem + 1;   // epilogue-warps-only broadcast slot
     uint8_t *staging = reinterpret_cast<uint8_t *>(bars) + Cfg::BAR_BYTES;   // [2][kEpiCols][128] TOut (TMA-store epilogue only)
 
@@ -422,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmBt);
-        if (PASSES == 3) {
+        if (PASSES == 3 && !FS) {
             prefetch_tmap(&tmAlo);
             prefetch_tmap(&tmBlo);
             prefetch_tmap(&tmBlot);
@@ -434,6 +464,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(full_bar + s), 1);    // one arrive.expect_tx (leader producer) + TMA bytes
             mbar_init(smem_u32(empty_bar + s), 1);   // one tcgen05.commit
+            if (FS) mbar_init(smem_u32(conv_bar + s), CG);   // one arrive per CTA of the pair: its converter warp for this k-block
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(tmem_full_bar + s), 1);         // one tcgen05.commit
@@ -467,18 +498,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m0 = (int)(mt * (kBlockM * CG) + cta_rank * kBlockM);
             const uint32_t b_rows = wu.bn / CG;      // rows of the B tile this CTA loads
             const int n0 = (int)(nt * BN + wu.n_off + cta_rank * b_rows);
-            const uint32_t stage_tx = (uint32_t)Cfg::SETS * (((skip & 1u) ? 0u : (uint32_t)kATileBytes) +
-                                                             ((skip & 2u) ? 0u : b_rows * kRowBytes)) * CG;
+            // FS: only the raw tiles are loaded, and each CTA's copies complete on its OWN barrier (its converter warps wait there)
+            const uint32_t stage_tx = FS ? (uint32_t)kATileBytes + b_rows * kRowBytes
+                                         : (uint32_t)Cfg::SETS * (((skip & 1u) ? 0u : (uint32_t)kATileBytes) +
+                                                                  ((skip & 2u) ? 0u : b_rows * kRowBytes)) * CG;
+            constexpr bool TMA2 = CG == 2 && !FS;    // cta_group::2 form: completion signalled on the leader's barrier
             const CUtensorMap *tb_hi = wu.narrow ? &tmBt : &tmB, *tb_lo = wu.narrow ? &tmBlot : &tmBlo;
             int k0 = (int)(wu.kb0 * BLOCK_K);
             for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb, k0 += BLOCK_K) {
                 mbar_wait(smem_u32(empty_bar + stage), phase ^ 1, args.mbar_timeout);
                 if (elect_one()) {
                     const uint32_t fb = smem_u32(full_bar + stage);
-                    if (leader) mbar_arrive_expect_tx(fb, stage_tx);
+                    if (leader || FS) mbar_arrive_expect_tx(fb, stage_tx);
                     const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
 #pragma unroll
-                    for (int set = 0; set < Cfg::SETS; ++set) {
+                    for (int set = 0; set < (FS ? 1 : Cfg::SETS); ++set) {
                         const CUtensorMap *ta = set == 0 ? &tmA : &tmAlo;
                         const CUtensorMap *tb = set == 0 ? tb_hi : tb_lo;
                         const uint32_t sa = sbase + set * kATileBytes;
@@ -487,20 +521,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else if (A_MN) {
 #pragma unroll
                             for (int at = 0; at < A_ATOMS; ++at) {
-                                if (CG == 2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
+                                if (TMA2) tma_load_3d_2sm(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
                                 else tma_load_3d(sa + at * A_ATOM_BYTES, ta, fb, m0 + at * A_ATOM_ELEMS, k0, (int)bt);
                             }
                         } else {
-                            if (CG == 2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
+                            if (TMA2) tma_load_3d_2sm(sa, ta, fb, k0, m0, (int)bt);
                             else tma_load_3d(sa, ta, fb, k0, m0, (int)bt);
                         }
                         if (skip & 2u) {
                         } else if (B_MN) {   // 128-byte atoms along N, each BLOCK_K rows deep
                             for (uint32_t at = 0; at * A_ATOM_ELEMS < b_rows; ++at) {
-                                if (CG == 2) tma_load_3d_2sm(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
+                                if (TMA2) tma_load_3d_2sm(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
                                 else tma_load_3d(sb + at * A_ATOM_BYTES, tb, fb, n0 + (int)(at * A_ATOM_ELEMS), k0, (int)bt);
                             }
-                        } else if (CG == 2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
+                        } else if (TMA2) tma_load_3d_2sm(sb, tb, fb, k0, n0, (int)bt);
                         else tma_load_3d(sb, tb, fb, k0, n0, (int)bt);
                     }
                 }
@@ -532,13 +566,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t kb = wu.kb0;
                 while (kb < wu.kb1) {
                     // one TMEM accumulation chain: the whole K range, or kChunkKb k-blocks for 3xTF32
-                    const uint32_t chain_end = CHUNKED ? min(wu.kb1, kb + (uint32_t)kChunkKb) : wu.kb1;
+                    const uint32_t chain_end = CHUNKED ? min(wu.kb1, kb + (uint32_t)CHUNK_KB) : wu.kb1;
                     mbar_wait(smem_u32(tmem_empty_bar + acc), acc_phase ^ 1, args.mbar_timeout);   // epilogue has drained this accumulator
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * BN;
                     uint32_t accum = 0;   // the first MMA of a chain overwrites the accumulator
                     for (; kb < chain_end; ++kb) {
-                        mbar_wait(smem_u32(full_bar + stage), phase, args.mbar_timeout);
+                        if (FS) mbar_wait_cluster(smem_u32(conv_bar + stage), phase, args.mbar_timeout);   // raw tiles landed AND lo tiles written
+                        else mbar_wait(smem_u32(full_bar + stage), phase, args.mbar_timeout);
                         tc_fence_after();
                         if (tr_pending) {
                             tr_pending = false;
@@ -581,6 +616,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 t[4] = (unsigned long long)clock64() - tr_c0; t[5] = tr_kb; t[7] = tr_units;
             }
         }
+    } else if (FS && (warp == 2 || warp == 3)) {
+        // ===================================== operand split (FS): lo = x - trunc_tf32(x) ===========
+        // Warp 2 takes the even k-blocks, warp 3 the odd ones, so two stages are being split at any time and the shared-memory
+        // latencies of one overlap the arithmetic of the other.  A warp walks the raw A and B tiles of its stage 16 bytes per lane,
+        // eight chunks in flight, and writes the lo tiles at the same offsets (the swizzle is a permutation of 16-byte chunks
+        // inside a tile, identical for raw and lo).  lo is left unrounded: the tensor core truncates it like every f32 operand,
+        // an error of 2^-11 of lo = 2^-21 of x at most.
+        uint32_t stage = 0, phase = 0, count = 0;
+        const uint32_t mine = warp - 2;
+        auto split8 = [](uint32_t raw_addr, uint32_t lo_addr, uint32_t n, uint32_t stride) {   // n <= 8 chunks, `stride` bytes apart
+            uint32_t x[8][4];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((uint32_t)q < n)
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x[q][0]), "=r"(x[q][1]), "=r"(x[q][2]), "=r"(x[q][3])
+                                 : "r"(raw_addr + q * stride) : "memory");
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((uint32_t)q < n) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) x[q][e] = __float_as_uint(__uint_as_float(x[q][e]) - __uint_as_float(x[q][e] & 0xFFFFE000u));
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr + q * stride), "r"(x[q][0]), "r"(x[q][1]), "r"(x[q][2]),
+                                 "r"(x[q][3]) : "memory");
+                }
+        };
+        for (uint32_t u = cluster_id; u < args.total_units; u += num_clusters) {
+            const WorkUnit wu = decode_unit(u, args, BN);
+            const uint32_t b_chunks = (wu.bn / CG) * (kRowBytes / 16);      // 16-byte chunks of this CTA's B tile
+            for (uint32_t kb = wu.kb0; kb < wu.kb1; ++kb, ++count) {
+                if ((count & 1u) == mine) {
+                    mbar_wait(smem_u32(full_bar + stage), phase, args.mbar_timeout);
+                    const uint32_t sbase = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t a_raw = sbase + lane * 16, b_raw = sbase + 2 * kATileBytes + lane * 16;
+                    // A: 1024 chunks = 4 rounds of 8 x 32 lanes; B: b_chunks (a multiple of 32) in rounds of up to 8 x 32
+#pragma unroll
+                    for (uint32_t r = 0; r < (uint32_t)kATileBytes / (16 * 32 * 8); ++r)
+                        split8(a_raw + r * 4096, a_raw + kATileBytes + r * 4096, 8, 512);
+                    for (uint32_t c0 = 0; c0 < b_chunks; c0 += 256) {
+                        const uint32_t left = (b_chunks - c0) / 32;
+                        split8(b_raw + c0 * 16, b_raw + Cfg::B_TILE_BYTES + c0 * 16, left < 8 ? left : 8, 512);
+                    }
+                    fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 2) mbar_arrive_cluster(smem_u32(conv_bar + stage), 0);
+                        else mbar_arrive(smem_u32(conv_bar + stage));
+                    }
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
     } else if (warp >= 4) {
         // ===================================== epilogue: TMEM -> registers -> global ==============
         const uint32_t q = warp & 3;   // TMEM lane quarter this warp may access
@@ -614,7 +700,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float *wsp = split_unit ? args.ws + (((uint64_t)slot * args.split + wu.split_idx) * CG + cta_rank) * (uint64_t)(BN * kBlockM) + row_in_cta
                                     : nullptr;
             const uint32_t nkb = wu.kb1 - wu.kb0;
-            const uint32_t nchains = CHUNKED ? (nkb + kChunkKb - 1) / kChunkKb : 1u;
+            const uint32_t nchains = CHUNKED ? (nkb + CHUNK_KB - 1) / CHUNK_KB : 1u;
             for (uint32_t ch = 0; ch < nchains; ++ch) {
                 const bool final_chain = ch + 1 == nchains;
                 mbar_wait(smem_u32(tmem_full_bar + acc), acc_phase, args.mbar_timeout);
@@ -819,10 +905,10 @@ struct TcMaps {
     TcDstMaps dst;                          // outputs (TMA-store epilogue only)
 };
 
-template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG>
+template <int KIND, bool A_MN, bool B_MN, int BN, int PASSES, typename TOut, int CG, bool FS = false>
 wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
     constexpr int SMEM_BYTES = TcEpi<BN, PASSES, CG, TOut>::SMEM_BYTES;
-    auto kern = gemm_tc_kernel<KIND, A_MN, B_MN, BN, PASSES, TOut, CG>;
+    auto kern = gemm_tc_kernel<KIND, A_MN, B_MN, BN, PASSES, TOut, CG, FS>;
     static bool attr_set[64] = {};   // per instantiation, per device
     const int dev = p->ctx->device & 63;
     if (!attr_set[dev]) {
@@ -856,6 +942,10 @@ wgb_status launch_cfg(wgb_pass *p, const TcMaps &m, TcArgs args) {
 template <int KIND, bool A_MN, bool B_MN, int PASSES, typename TOut>
 wgb_status launch_sel(wgb_pass *p, int bn, int cg, const TcMaps &m, const TcArgs &args) {
     if constexpr (PASSES == 3) {   // 3xTF32: BLOCK_N = 128 only (two accumulator stages + running sum in TMEM)
+        if (args.fused_split) {
+            if (cg == 2) return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 2, true>(p, m, args);
+            return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 1, true>(p, m, args);
+        }
         if (cg == 2) return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 2>(p, m, args);
         return launch_cfg<KIND, A_MN, B_MN, 128, PASSES, TOut, 1>(p, m, args);
     } else {

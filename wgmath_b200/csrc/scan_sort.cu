@@ -28,23 +28,6 @@ namespace wgb {
 
 namespace {
 
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p) {
-    unsigned int v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // exclusive prefix sum: reduce, scan the partials, scan with carry-in
 // ---------------------------------------------------------------------------------------------
@@ -58,7 +41,9 @@ __device__ __forceinline__ void st_relaxed_u32(unsigned int *p, unsigned int v) 
 // Why not a single pass: two decoupled look-back variants were built and measured first (profiles/README.md) — at B200
 // bandwidth ~100 tiles start per microsecond while a descriptor round trip through L2 costs most of one, so every tile
 // waits on hundreds of predecessors: 2.4 TB/s (one-warp window), 2.4 TB/s (whole-CTA window), 2.9 TB/s (two-level group
-// descriptors) against 4.4-5.1 TB/s for the same kernels with the look-back switched off.
+// descriptors) against 4.4-5.1 TB/s for the same kernels with the look-back switched off.  A fourth variant (16384-element
+// tiles, 64-descriptor window, ticketed tiles) was validated bit-exact in round 2 and measured 159 us vs 131 us for the three-step
+// form at n = 2^26 (3.4 vs 4.1 TB/s of algorithmic bytes): also retired (profiles/README.md).
 constexpr int kScanRounds = 8;                         // 128-bit accesses per lane and warp tile
 constexpr int kScanWarpTile = kScanRounds * 128;       // 1024 elements per warp tile
 constexpr int kScanThreads = 256;
@@ -169,139 +154,6 @@ __global__ void __launch_bounds__(1024) scan_small_kernel(uint32_t *__restrict__
     for (int q = 0; q < 4; ++q) {
         if ((uint32_t)t * 4 + q < n) data[t * 4 + q] = run;
         run += v[q];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL single-pass scan (WGB_SCAN_LOOKBACK=1; off by default; written after this round's GPU budget was spent and NOT
-// YET RUN ON HARDWARE).  Decoupled look-back again, but sized by what the retired variants taught: with 4096-element tiles a
-// B200 starts ~770 tiles per microsecond while one look-back hop (an L2 round trip) takes ~0.6 us, so a 32-wide window cannot
-// keep up with the tile rate and every tile ends up walking hundreds of predecessors.  Here a tile is 16384 elements (512
-// threads x 8 x uint4, two CTAs per SM), which cuts the tile rate to ~48 per microsecond, and the window is 64 descriptors
-// per hop, so a tile normally finds an inclusive prefix within one or two hops.  8 bytes of HBM traffic per element.
-// desc[tile] = (state << 32) | value; state 0 = not published, 1 = tile aggregate, 2 = inclusive prefix up to the tile.  Tiles are
-// handed out by an atomic ticket, so a tile only ever waits for tiles whose CTAs are already running; spins are bounded (trap).
-// ---------------------------------------------------------------------------------------------
-constexpr int kLbThreads = 512;
-constexpr int kLbRounds = 8;
-constexpr int kLbWarps = kLbThreads / 32;
-constexpr int kLbTile = kLbThreads * 4 * kLbRounds;   // 16384 elements
-constexpr unsigned long long kLbAggregate = 1ull << 32, kLbPrefix = 2ull << 32;
-
-__device__ __forceinline__ unsigned long long lb_poll(const unsigned long long *desc, long long idx) {
-    if (idx < 0) return kLbPrefix;   // before tile 0: prefix 0
-    unsigned long long d;
-    unsigned int spins = 0;
-    do {
-        d = ld_relaxed_u64(desc + idx);
-        if (++spins > (1u << 26)) __trap();
-    } while ((d >> 32) == 0);
-    return d;
-}
-
-__global__ void __launch_bounds__(kLbThreads, 2) scan_lookback_kernel(uint32_t *__restrict__ data, uint64_t n,
-                                                                      unsigned long long *__restrict__ desc,
-                                                                      unsigned int *__restrict__ ticket, uint32_t tiles) {
-    __shared__ uint32_t s_tile, s_excl;
-    __shared__ uint32_t s_wt[kLbRounds * kLbWarps];   // warp totals in (round, warp) order = element order
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    // a re-execution of the kernel alone (profiler kernel replay) finds the ticket already past the last tile: nothing to do,
-    // and above all nothing to write behind the descriptor array
-    if (tile >= tiles) return;
-    const uint64_t base = (uint64_t)tile * kLbTile;
-    const bool full = base + kLbTile <= n && (reinterpret_cast<uintptr_t>(data) & 15u) == 0;
-
-    uint4 v[kLbRounds];
-    uint32_t before[kLbRounds];   // sum of the elements of this round that precede this thread's four, inside its warp
-#pragma unroll
-    for (int r = 0; r < kLbRounds; ++r) {
-        const uint64_t i = base + (uint64_t)r * (kLbThreads * 4) + (uint64_t)t * 4;
-        if (full) {
-            v[r] = __ldcs(reinterpret_cast<const uint4 *>(data + i));
-        } else {
-            v[r].x = i + 0 < n ? data[i + 0] : 0u;
-            v[r].y = i + 1 < n ? data[i + 1] : 0u;
-            v[r].z = i + 2 < n ? data[i + 2] : 0u;
-            v[r].w = i + 3 < n ? data[i + 3] : 0u;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < kLbRounds; ++r) {
-        const uint32_t sum = v[r].x + v[r].y + v[r].z + v[r].w;
-        uint32_t x = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        before[r] = x - sum;
-        if (lane == 31) s_wt[r * kLbWarps + warp] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // 128 warp totals -> exclusive offsets (four consecutive entries per lane); lane 31 ends up with the tile aggregate
-        uint32_t w4[4], local = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            w4[q] = s_wt[lane * 4 + q];
-            local += w4[q];
-        }
-        uint32_t x = local;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
-        }
-        uint32_t run = x - local;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            s_wt[lane * 4 + q] = run;
-            run += w4[q];
-        }
-        const uint32_t aggregate = __shfl_sync(0xFFFFFFFFu, x, 31);
-        uint32_t exclusive = 0;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(desc, kLbPrefix | aggregate);
-        } else {
-            if (lane == 0) st_relaxed_u64(desc + tile, kLbAggregate | aggregate);
-            long long pred = (long long)tile - 1;
-            while (true) {
-                const unsigned long long d1 = lb_poll(desc, pred - lane), d2 = lb_poll(desc, pred - 32 - lane);
-                const unsigned p1 = __ballot_sync(0xFFFFFFFFu, (d1 >> 32) == 2), p2 = __ballot_sync(0xFFFFFFFFu, (d2 >> 32) == 2);
-                const int first1 = p1 ? __ffs(p1) - 1 : 31;                      // nearest predecessor holding a full prefix
-                const int first2 = p1 ? -1 : (p2 ? __ffs(p2) - 1 : 31);          // the far half only counts if the near one has none
-                uint32_t x2 = (lane <= first1 ? (uint32_t)d1 : 0u) + (lane <= first2 ? (uint32_t)d2 : 0u);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xFFFFFFFFu, x2, o);
-                exclusive += x2;
-                if (p1 || p2) break;
-                pred -= 64;
-            }
-            if (lane == 0) st_relaxed_u64(desc + tile, kLbPrefix | (uint32_t)(exclusive + aggregate));
-        }
-        if (lane == 0) s_excl = exclusive;
-    }
-    __syncthreads();
-    const uint32_t tile_excl = s_excl;
-#pragma unroll
-    for (int r = 0; r < kLbRounds; ++r) {
-        const uint64_t i = base + (uint64_t)r * (kLbThreads * 4) + (uint64_t)t * 4;
-        uint4 o;
-        o.x = tile_excl + s_wt[r * kLbWarps + warp] + before[r];
-        o.y = o.x + v[r].x;
-        o.z = o.y + v[r].y;
-        o.w = o.z + v[r].z;
-        if (full) {
-            __stcs(reinterpret_cast<uint4 *>(data + i), o);
-        } else {
-            if (i + 0 < n) data[i + 0] = o.x;
-            if (i + 1 < n) data[i + 1] = o.y;
-            if (i + 2 < n) data[i + 2] = o.z;
-            if (i + 3 < n) data[i + 3] = o.w;
-        }
     }
 }
 
@@ -563,20 +415,6 @@ static wgb_status scan_in_place(wgb_pass *p, uint32_t *data, uint64_t n, uint32_
 
 wgb_status launch_prefix_sum(wgb_pass *p, uint32_t *data, uint64_t n) {
     if (n == 0) return WGB_OK;
-    const char *lb_env = getenv("WGB_SCAN_LOOKBACK");
-    const bool lookback = lb_env && atoi(lb_env) != 0;
-    if (lookback && n >= ((uint64_t)1 << 20)) {   // single-pass variant (see scan_lookback_kernel); tests/test_gpu_scan_sort.py
-        const uint64_t tiles = (n + kLbTile - 1) / kLbTile;
-        void *w = nullptr;
-        const size_t bytes = (size_t)(tiles + 2) * 8;
-        WGB_TRY(workspace_reserve(p->ctx, 4, bytes, &w));
-        WGB_CUDA(cudaMemsetAsync(w, 0, bytes, p->stream));
-        unsigned long long *desc = reinterpret_cast<unsigned long long *>(w) + 1;
-        scan_lookback_kernel<<<(unsigned)tiles, kLbThreads, 0, p->stream>>>(data, n, desc, reinterpret_cast<unsigned int *>(w), (uint32_t)tiles);
-        WGB_CUDA(cudaGetLastError());
-        count_launch(p->ctx);
-        return WGB_OK;
-    }
     void *w = nullptr;
     WGB_TRY(workspace_reserve(p->ctx, 4, scan_workspace_elems(n) * 4 + 16, &w));
     return scan_in_place(p, data, n, reinterpret_cast<uint32_t *>(w));

@@ -121,9 +121,9 @@ class ComputePass:
 
     def last_gemm_config(self) -> dict:
         """The tcgen05 kernel instantiation / plan of the last GEMM on this pass (wgb_pass_last_gemm_config)."""
-        c = (ctypes.c_int * 12)()
+        c = (ctypes.c_int * 13)()
         check(lib().wgb_pass_last_gemm_config(self._h, c))
-        keys = ("kind", "a_mn", "b_mn", "bn", "passes", "out_dtype", "cg", "epi_tma", "nsplit", "splitk", "dests", "units")
+        keys = ("kind", "a_mn", "b_mn", "bn", "passes", "out_dtype", "cg", "epi_tma", "nsplit", "splitk", "dests", "units", "fused_split")
         return dict(zip(keys, list(c)))
 
     def __enter__(self):
