@@ -337,6 +337,13 @@ wgb_status wgb_geometry_batch(wgb_pass *pass, wgb_geom_op op, int dim, const wgb
  *   [7] work units processed.  enable == 0 frees the trace buffer. */
 wgb_status wgb_debug_tc_trace(wgb_ctx *ctx, int enable, unsigned long long *out, size_t max_records, size_t *n_records);
 
+/* Gemv -> Reduce fused: result = reduce_op over the elements of m * v (or tr(m) * v), the reference's
+ * Gemv::dispatch + Reduce::dispatch chain (gemv.rs:64-137, reduce.rs:100-113) in one launch.  The product vector is never written to
+ * a caller buffer; the scalar is bit-identical to the two-dispatch chain through a 16-byte aligned `out`.  One matrix, one vector. */
+wgb_status wgb_gemv_reduce(wgb_pass *pass, wgb_gemv_variant variant, wgb_reduce_op reduce_op, wgb_buffer *result,
+                           const wgb_buffer *m, const wgb_view_shape *m_shape, wgb_ordering m_ord, const wgb_buffer *v,
+                           const wgb_view_shape *v_shape);
+
 /* Which kernel family the last wgb_gemm* call on this pass dispatched to:
  * 0 none, 1 SIMT FFMA, 2 tcgen05 bf16, 3 tcgen05 tf32, 4 tcgen05 3xtf32. */
 wgb_status wgb_pass_last_gemm_path(const wgb_pass *pass, int *path);

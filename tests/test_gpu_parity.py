@@ -713,6 +713,34 @@ def test_gemv_fused_residual_update_and_errors(gpu, shapes):
     np.testing.assert_array_equal(out.read(), e.read())
 
 
+@pytest.mark.parametrize("rop", list(w.ReduceOp))
+@pytest.mark.parametrize("variant,R,Cc", [(w.GemvVariant.Gemv, 1024, 1024), (w.GemvVariant.GemvTr, 1024, 1024), (w.GemvVariant.Gemv, 200, 3000),
+                                          (w.GemvVariant.GemvTr, 5000, 24), (w.GemvVariant.Gemv, 70001, 36), (w.GemvVariant.GemvTr, 96, 70001),
+                                          (w.GemvVariant.Gemv, 5, 7), (w.GemvVariant.Gemv, 300001, 8)])
+def test_gemv_fused_reduce_equals_the_two_dispatch_chain(gpu, shapes, rop, variant, R, Cc):
+    """wgb_gemv_reduce == Gemv::dispatch into `out`, then Reduce::dispatch(out, result) (gemv.rs:64-137, reduce.rs:100-113), bit for
+    bit — every reduce op, both variants, shapes with and without the split of the reduction axis, an output vector large enough
+    for a multi-CTA reduce tree, and one beyond what the fused tail emulates (falls back to the second launch)."""
+    dev = gpu.device()
+    tr = variant == w.GemvVariant.GemvTr
+    m = upload(gpu, O.uniform(SEED_A, R, Cc) + np.float32(0.5), (R, Cc))
+    nv, nout = (R, Cc) if tr else (Cc, R)
+    v = upload(gpu, O.uniform(SEED_V, nv) * np.float32(2.0 / nv if rop == w.ReduceOp.Prod else 1.0), (nv,))   # Prod: factors near 1
+    out = w.TensorBuilder.vector(nout, STORAGE).build(dev)
+    r_chain, r_fused = w.TensorBuilder.scalar(STORAGE).build(dev), w.TensorBuilder.scalar(STORAGE).build(dev)
+    gemv, red = w.Gemv.from_device(dev), w.Reduce.new(dev, rop)
+    n0 = dev.launch_count()
+    run_pass(gpu, lambda p: (gemv.dispatch_generic(dev, shapes, p, out, m, v, variant), red.dispatch(dev, shapes, p, out, r_chain)))
+    n1 = dev.launch_count()
+    run_pass(gpu, lambda p: gemv.dispatch_reduce(dev, shapes, p, r_fused, m, v, rop, variant))
+    n2 = dev.launch_count()
+    a, b = r_chain.read(), r_fused.read()
+    assert a.tobytes() == b.tobytes(), (a, b)
+    assert rop == w.ReduceOp.Prod or np.isfinite(a[0])
+    if nout <= 200000:
+        assert n2 - n1 == 1 and n1 - n0 == 2      # one launch instead of two
+
+
 def test_graph_capture_replays_a_dispatch_chain(gpu, shapes):
     """wgb_graph_*: record gemm -> op_assign -> reduce once, replay it, same result as the eager sequence."""
     dev = gpu.device()

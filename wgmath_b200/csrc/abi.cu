@@ -765,6 +765,44 @@ wgb_status wgb_gemv_op(wgb_pass *pass, wgb_gemv_variant variant, wgb_buffer *out
                        op >= 0 ? (const float *)e->ptr : nullptr, op >= 0 ? &se_used : nullptr);
 }
 
+// Gemv -> Reduce in one launch (the reference chain is Gemv::dispatch then Reduce::dispatch on the product
+// vector, gemv.rs:64-137 + reduce.rs:100-113).  The product never reaches a caller buffer: it goes to a context scratch vector and
+// the last CTA of the GEMV reduces it with exactly the tree wgb_reduce would use, so the scalar is bit-identical to the two-dispatch
+// chain (with a 16-byte aligned `out`).
+wgb_status wgb_gemv_reduce(wgb_pass *pass, wgb_gemv_variant variant, wgb_reduce_op rop, wgb_buffer *result, const wgb_buffer *m,
+                           const wgb_view_shape *sm, wgb_ordering m_ord, const wgb_buffer *v, const wgb_view_shape *sv) {
+    if (!pass || !result || !m || !sm || !v || !sv) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_reduce: null argument");
+    if ((int)variant < 0 || (int)variant > WGB_GEMV_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_reduce: unknown variant %d", (int)variant);
+    if ((int)rop < 0 || (int)rop > WGB_RED_SQNORM) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_reduce: unknown reduce op %d", (int)rop);
+    if (bad_ordering(m_ord)) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemv_reduce: unknown ordering %d", (int)m_ord);
+    if (sm->size[2] != 1 || sv->size[1] != 1 || sv->size[2] != 1)
+        WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemv_reduce: one matrix and one vector (the reference reduces a GpuVectorView)");
+    bool tr = variant == WGB_GEMV_TR || variant == WGB_GEMV_TR_FAST;
+    const uint32_t m_rows = tr ? sm->size[1] : sm->size[0];
+    const uint32_t m_cols = tr ? sm->size[0] : sm->size[1];
+    if (m_cols != sv->size[0])  // gemv.rs:89
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemv: dimension mismatch. (matrix cols %u vs vector rows %u)", m_cols, sv->size[0]);
+    if (any_zero_buffer({result, m, v}) || m_rows == 0) return WGB_OK;
+    if (result->bytes < 4) WGB_FAIL(WGB_ERR_OUT_OF_BOUNDS, "wgb_gemv_reduce: result buffer smaller than one f32");
+    wgb_view_shape sm_used = *sm;
+    if (m_ord == WGB_ROW_MAJOR) {
+        sm_used = transposed_shape(*sm);
+        tr = !tr;
+    }
+    WGB_TRY(check_view(m, sm_used, 4, "gemv m"));
+    WGB_TRY(check_view(v, *sv, 4, "gemv v", true));
+    wgb_ctx *ctx = pass->ctx;
+    DeviceGuard g(ctx->device);
+    void *w = nullptr;
+    WGB_TRY(workspace_reserve(ctx, 7, (size_t)m_rows * 4 + 16, &w));
+    const wgb_view_shape so{{m_rows, 1, 1}, m_rows, m_rows, 0};
+    const bool fuse = m_cols > 0 && (uint32_t)reduce_grid_for(ctx, (int)rop, m_rows) <= kGemvReduceMaxGrid;
+    WGB_TRY(launch_gemv(pass, tr, (float *)w, so, (const float *)m->ptr, sm_used, (const float *)v->ptr, *sv, -1, nullptr, nullptr,
+                        fuse ? (int)rop : -1, (float *)result->ptr));
+    if (!fuse) return launch_reduce(pass, (int)rop, (const float *)w, nullptr, m_rows, (float *)result->ptr);   // same tree, second launch
+    return WGB_OK;
+}
+
 static wgb_status gemm_common(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so,
                               const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2, const wgb_view_shape *s2,
                               wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode, int ep_op, const wgb_buffer *e,

@@ -81,7 +81,8 @@ struct wgb_ctx {
     std::atomic<uint64_t> launches{0};
     std::atomic<int> refs{1};            // the caller's handle + one per live buffer / event / pass / graph / peer group (abi.cu)
     wgb::Scratch scratch;
-    wgb::Workspace ws[7];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort, 6: diagnostics
+    wgb::Workspace ws[8];   // 0/1: 3xTF32 operand splits, 2: split-K partials, 3: host GEMM slots, 4: scan, 5: sort, 6: diagnostics,
+                            // 7: the product vector of a fused Gemv -> Reduce
     uint64_t ws_generation = 0;   // bumped whenever a workspace / scratch block is reallocated (captured graphs hold the old pointers)
     wgb::CommState *comm = nullptr;
     wgb::HostGemmState host_gemm;
@@ -170,7 +171,10 @@ wgb_status launch_radix_sort(wgb_pass *p, const uint32_t *keys_in, const uint32_
                              uint32_t sorting_bits, uint32_t *keys_out, uint32_t *vals_out);
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
                        const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv, int op = -1,
-                       const float *operand = nullptr, const wgb_view_shape *operand_shape = nullptr);
+                       const float *operand = nullptr, const wgb_view_shape *operand_shape = nullptr, int red_op = -1,
+                       float *red_result = nullptr);
+int reduce_grid_for(wgb_ctx *ctx, int op, uint64_t n);   // the grid wgb_reduce launches for n elements (level1.cu)
+constexpr uint32_t kGemvReduceMaxGrid = 2048;            // largest such grid the fused Gemv -> Reduce tail emulates (gemv.cu)
 
 // Fused all-gather of the GEMM output over peer (NVLink-mapped) memory: the epilogue stores every output element
 // into the gathered buffer of every rank, then the last CTA publishes a completion flag to each peer.

@@ -23,6 +23,7 @@
 //
 // Algorithmic bytes per launch: 4 * (M*K + K*C + M*C) per matrix.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace wgb {
 
@@ -30,6 +31,7 @@ static constexpr int kThreads = 256;
 static constexpr int kWarps = 8;
 static constexpr int kTileRows = 128;
 static constexpr int kStage = 512;  // columns of v staged per step
+static constexpr int kTStage = 2048;  // gemv_tr: rows of v staged per step (8 KB per output column)
 
 struct GemvArgs {
     const float *m, *v;
@@ -47,7 +49,40 @@ struct GemvArgs {
     int op;             // < 0: out = result (gemv.wgsl:88); else out = result (op) e — the fused OpAssign step (op_assign.wgsl:14-47)
     const float *e;     // operand of the fused step, indexed like out with its own strides
     uint64_t lde, se;
+    // fused Gemv -> Reduce (wgb_gemv_reduce; C == 1, one matrix): `out` is an internal scratch vector, and the last CTA to store its
+    // part of it reduces it exactly as wgb_reduce would (reduce.cuh: reduce_in_one_cta) into red_result
+    int red_op;                 // < 0: none
+    float *red_result;
+    unsigned int *red_counter;  // CTAs that have stored their outputs (left at zero)
+    uint32_t red_tiles, red_grid;
 };
+
+constexpr uint32_t kRedMaxGrid = kGemvReduceMaxGrid;   // per-CTA partials of the emulated reduce launch kept in shared memory
+
+// Tail of both kernels in fused-reduce mode; called by every CTA that has just stored final outputs (all threads of the CTA).
+__device__ __forceinline__ void fused_reduce_tail(const GemvArgs &a) {
+    __shared__ float red[32];
+    __shared__ float vpart[kRedMaxGrid];
+    __shared__ bool red_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) red_last = atomicAdd(a.red_counter, 1u) == a.red_tiles - 1;
+    __syncthreads();
+    if (!red_last) return;
+    __threadfence();
+    float r;
+    switch (a.red_op) {
+    case WGB_RED_MIN: r = reduce_in_one_cta<WGB_RED_MIN>(a.out, a.M, a.red_grid, red, vpart); break;
+    case WGB_RED_MAX: r = reduce_in_one_cta<WGB_RED_MAX>(a.out, a.M, a.red_grid, red, vpart); break;
+    case WGB_RED_SUM: r = reduce_in_one_cta<WGB_RED_SUM>(a.out, a.M, a.red_grid, red, vpart); break;
+    case WGB_RED_PROD: r = reduce_in_one_cta<WGB_RED_PROD>(a.out, a.M, a.red_grid, red, vpart); break;
+    default: r = reduce_in_one_cta<WGB_RED_SQNORM>(a.out, a.M, a.red_grid, red, vpart); break;
+    }
+    if (threadIdx.x == 0) {
+        *a.red_result = r;
+        *a.red_counter = 0u;
+    }
+}
 
 // The single store of an output element (t = matrix, c = output column, r = row).  With a fused op this is OpAssign's
 // `a[i] = a[i] op b[i]` (op_assign.wgsl:41-47) applied to a = the GEMV result the unfused chain would have written to `out`
@@ -157,7 +192,10 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(GemvArgs a) {
             a.partials[((tile_id * a.nsplit + blockIdx.y) * NV + c) * kTileRows + rl] = s;
         }
     }
-    if (!split) return;
+    if (!split) {
+        if (NV == 1 && a.red_op >= 0) fused_reduce_tail(a);
+        return;
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -174,6 +212,7 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(GemvArgs a) {
         if (row0 + rl < a.M && c < nv) store_out(a, t, c0 + c, row0 + rl, s);
     }
     if (threadIdx.x == 0) a.counters[tile_id] = 0u;
+    if (NV == 1 && a.red_op >= 0) fused_reduce_tail(a);
 }
 
 __device__ __forceinline__ float dot4(const float4 &x, const float4 &y, float acc) {
@@ -202,35 +241,51 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
 #pragma unroll
     for (int c = 0; c < NV; ++c) acc[c] = 0.f;
 
-    if (valid) {
-        if (VEC) {
-            const uint32_t nvec = (r1 - r0) >> 2;  // r0 is a multiple of 4 (chunk is)
-            const float *cb = col + r0;
-            const float *vb = vp + r0;
-            uint32_t i = lane;
-            for (; i + 96 < nvec; i += 128) {
-                float4 x[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = __ldcs(reinterpret_cast<const float4 *>(cb) + i + 32 * u);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int c = 0; c < NV; ++c)
-                        if (c < nv) acc[c] = dot4(x[u], __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i + 32 * u), acc[c]);
-            }
-            for (; i < nvec; i += 32) {
-                const float4 x = __ldcs(reinterpret_cast<const float4 *>(cb) + i);
+    if (VEC) {
+        // v is staged in shared memory kTStage rows at a time (all 8 warps = 8 columns of m consume the same rows), so the only
+        // global loads in the loop are the 128-bit streaming reads of m, eight in flight per lane (4 KB per warp).
+        __shared__ float4 vs[NV][kTStage / 4];
+        const uint32_t nvec = (r1 - r0) >> 2;  // r0 is a multiple of 4 (chunk is)
+        const float *cb = col + r0;
+        const float *vb = vp + r0;
+        for (uint32_t s0 = 0; s0 < nvec; s0 += kTStage / 4) {
+            const uint32_t ns = min((uint32_t)kTStage / 4, nvec - s0);
+            __syncthreads();   // the previous stage has been consumed
+            for (uint32_t i = threadIdx.x; i < ns; i += kThreads)
 #pragma unroll
                 for (int c = 0; c < NV; ++c)
-                    if (c < nv) acc[c] = dot4(x, __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + i), acc[c]);
+                    if (c < nv) vs[c][i] = __ldg(reinterpret_cast<const float4 *>(vb + (uint64_t)c * a.ldv) + s0 + i);
+            __syncthreads();
+            if (valid) {
+                const float4 *xb = reinterpret_cast<const float4 *>(cb) + s0;
+                uint32_t i = lane;
+                for (; i + 224 < ns; i += 256) {
+                    float4 x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) x[u] = __ldcs(xb + i + 32 * u);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+#pragma unroll
+                        for (int c = 0; c < NV; ++c)
+                            if (c < nv) acc[c] = dot4(x[u], vs[c][i + 32 * u], acc[c]);
+                }
+                for (; i < ns; i += 32) {
+                    const float4 x = __ldcs(xb + i);
+#pragma unroll
+                    for (int c = 0; c < NV; ++c)
+                        if (c < nv) acc[c] = dot4(x, vs[c][i], acc[c]);
+                }
             }
+        }
+        if (valid)
             for (uint32_t r = r0 + (nvec << 2) + lane; r < r1; r += 32) {
                 const float x = col[r];
 #pragma unroll
                 for (int c = 0; c < NV; ++c)
                     if (c < nv) acc[c] = fmaf(x, vp[(uint64_t)c * a.ldv + r], acc[c]);
             }
-        } else {
+    } else if (valid) {
+        {
             uint32_t r = r0 + lane;
             for (; r + 96 < r1; r += 128) {
                 float x[4];
@@ -261,6 +316,7 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
 #pragma unroll
             for (int c = 0; c < NV; ++c)
                 if (c < nv) store_out(a, t, c0 + c, j, acc[c]);
+        if (NV == 1 && a.red_op >= 0) fused_reduce_tail(a);
         return;
     }
     const uint64_t tile_id = (uint64_t)z * gridDim.x + blockIdx.x;
@@ -284,6 +340,7 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(GemvArgs a) {
         if (jj < a.M && c < nv) store_out(a, t, c0 + c, jj, s);
     }
     if (threadIdx.x == 0) a.counters[tile_id] = 0u;
+    if (NV == 1 && a.red_op >= 0) fused_reduce_tail(a);
 }
 
 template <bool TR, bool VEC, int NV>
@@ -313,12 +370,15 @@ __global__ void gemv_empty_k_kernel(GemvArgs a, uint32_t nmats) {   // K == 0 wi
     }
 }
 
+int reduce_grid_for(wgb_ctx *ctx, int op, uint64_t n);   // level1.cu
+
 wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &so, const float *m,
                        const wgb_view_shape &sm, const float *v, const wgb_view_shape &sv, int op, const float *operand,
-                       const wgb_view_shape *se) {
+                       const wgb_view_shape *se, int red_op, float *red_result) {
     wgb_ctx *ctx = p->ctx;
     GemvArgs a{};
     a.op = op;
+    a.red_op = -1;
     if (op >= 0) {
         a.e = operand + se->offset;
         a.lde = se->stride;
@@ -385,13 +445,21 @@ wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &s
             nsplit = 1;
             chunk = (a.K + 31u) & ~31u;
         } else {
-            WGB_TRY(scratch_reserve(ctx, need, tiles_x * zdim));
+            WGB_TRY(scratch_reserve(ctx, need, tiles_x * zdim + 1));   // (+ 1: the last slot is the fused-reduce ticket)
         }
     }
     a.nsplit = (uint32_t)nsplit;
     a.chunk = chunk;
     a.partials = ctx->scratch.partials;
     a.counters = ctx->scratch.counters;
+    if (red_op >= 0) {
+        // fused Gemv -> Reduce: only reached with C == 1, one matrix, K > 0 and a grid the tail can emulate (checked by the caller)
+        a.red_op = red_op;
+        a.red_result = red_result;
+        a.red_counter = ctx->scratch.counters + (ctx->scratch.n_counters - 1);
+        a.red_tiles = (uint32_t)tiles_x;
+        a.red_grid = (uint32_t)reduce_grid_for(ctx, red_op, a.M);
+    }
     if (tiles_x > 0x7fffffffull) WGB_FAIL(WGB_ERR_UNSUPPORTED, "gemv: too many row tiles");
 
     for (uint64_t z0 = 0; z0 < zdim; z0 += 65535) {

@@ -12,10 +12,12 @@
 // Algorithmic bytes: op_assign 12 B/elem (8 for Copy), reduce 4 B/elem, dot 8 B/elem,
 // column reduce 4 B/elem.
 #include "common.cuh"
+#include "reduce.cuh"
 
 namespace wgb {
 
 static constexpr int kThreads = 256;
+static_assert(kThreads == kRedThreads, "reduce.cuh assumes the level-1 CTA size");
 
 __device__ __forceinline__ float4 ld_stream4(const float *p) {
     return __ldcs(reinterpret_cast<const float4 *>(p));
@@ -129,107 +131,7 @@ wgb_status launch_op_assign(wgb_pass *p, int op, float *a, const float *b, uint6
     return WGB_OK;
 }
 
-// ---------------------------------------------------------------------------- reduce / dot
-// OP 0..4 = wgb_reduce_op, 5 = dot.
-template <int OP>
-__device__ __forceinline__ float red_init() {   // reduce.rs:30-38 / reduce.wgsl:32-46
-    if (OP == WGB_RED_MIN) return 3.4e38f;
-    if (OP == WGB_RED_MAX) return -3.4e38f;
-    if (OP == WGB_RED_PROD) return 1.0f;
-    return 0.0f;
-}
-template <int OP>
-__device__ __forceinline__ float red_elem(float acc, float x, float y) {   // workspace_fn
-    if (OP == WGB_RED_MIN) return fminf(acc, x);
-    if (OP == WGB_RED_MAX) return fmaxf(acc, x);
-    if (OP == WGB_RED_SUM) return acc + x;
-    if (OP == WGB_RED_PROD) return acc * x;
-    if (OP == WGB_RED_SQNORM) return fmaf(x, x, acc);
-    return fmaf(x, y, acc);  // dot
-}
-template <int OP>
-__device__ __forceinline__ float red_comb(float a, float b) {   // reduce_fn (SqNorm and dot combine by sum)
-    if (OP == WGB_RED_MIN) return fminf(a, b);
-    if (OP == WGB_RED_MAX) return fmaxf(a, b);
-    if (OP == WGB_RED_PROD) return a * b;
-    return a + b;
-}
-
-template <int OP>
-__device__ __forceinline__ float warp_reduce(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = red_comb<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// Block-wide combine; result valid in thread 0.
-template <int OP>
-__device__ __forceinline__ float block_reduce(float v, float *smem /* >= 32 floats */) {
-    v = warp_reduce<OP>(v);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) smem[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        const int nw = (blockDim.x + 31) >> 5;
-        v = lane < nw ? smem[lane] : red_init<OP>();
-        v = warp_reduce<OP>(v);
-    }
-    __syncthreads();
-    return v;
-}
-
-// Accumulate x[0..n) (and y for dot) into a per-thread partial, cooperatively over `nthreads` threads.
-template <int OP, bool Y_ALIGNED>
-__device__ __forceinline__ float thread_partial(const float *__restrict__ x, const float *__restrict__ y, uint64_t n,
-                                                uint64_t tid, uint64_t nthreads) {
-    constexpr bool DOT = OP == 5;
-    const uint32_t mis = (uint32_t)(((uintptr_t)x & 15u) >> 2);
-    uint64_t head = mis ? 4u - mis : 0u;
-    if (head > n) head = n;
-    const uint64_t nvec = (n - head) >> 2;
-    const uint64_t tail0 = head + (nvec << 2);
-    float acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = red_init<OP>();
-    if (tid < head) acc[0] = red_elem<OP>(acc[0], x[tid], DOT ? y[tid] : 0.f);
-    if (tail0 + tid < n) acc[1] = red_elem<OP>(acc[1], x[tail0 + tid], DOT ? y[tail0 + tid] : 0.f);
-    // pointer-bumping main loop: U independent 16-byte requests per stream in flight per thread
-    constexpr int U = DOT ? 2 : 4;
-    const float *px = x + head + 4 * tid;
-    const float *py = DOT ? y + head + 4 * tid : nullptr;
-    const uint64_t step4 = 4 * nthreads;
-    auto ldy = [](const float *q) {
-        if (Y_ALIGNED) return ld_stream4(q);
-        return make_float4(__ldcs(q), __ldcs(q + 1), __ldcs(q + 2), __ldcs(q + 3));
-    };
-    auto fold = [&](const float4 &a, const float4 &b) {
-        acc[0] = red_elem<OP>(acc[0], a.x, b.x);
-        acc[1] = red_elem<OP>(acc[1], a.y, b.y);
-        acc[2] = red_elem<OP>(acc[2], a.z, b.z);
-        acc[3] = red_elem<OP>(acc[3], a.w, b.w);
-    };
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    uint64_t i = tid;
-    for (; i + (U - 1) * nthreads < nvec; i += U * nthreads) {
-        float4 a[U], b[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            a[u] = ld_stream4(px + u * step4);
-            b[u] = DOT ? ldy(py + u * step4) : zero;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) fold(a[u], b[u]);
-        px += U * step4;
-        if (DOT) py += U * step4;
-    }
-    for (; i < nvec; i += nthreads) {
-        fold(ld_stream4(px), DOT ? ldy(py) : zero);
-        px += step4;
-        if (DOT) py += step4;
-    }
-    return red_comb<OP>(red_comb<OP>(acc[0], acc[1]), red_comb<OP>(acc[2], acc[3]));
-}
-
+// ---------------------------------------------------------------------------- reduce / dot (tree: reduce.cuh)
 template <int OP, bool Y_ALIGNED>
 __global__ void __launch_bounds__(kThreads, 4) reduce_kernel(const float *__restrict__ x, const float *__restrict__ y,
                                                           uint64_t n, float *__restrict__ partials,
@@ -264,9 +166,8 @@ __global__ void __launch_bounds__(kThreads, 4) reduce_kernel(const float *__rest
     }
 }
 
-wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, uint64_t n, float *result) {
-    if (((uintptr_t)x & 3u) != 0) WGB_FAIL(WGB_ERR_INVALID, "reduce: buffer is not 4-byte aligned");
-    wgb_ctx *ctx = p->ctx;
+// The grid launch_reduce uses for `n` elements (the fused Gemv -> Reduce tail reproduces exactly this launch).
+int reduce_grid_for(wgb_ctx *ctx, int op, uint64_t n) {
     const uint64_t nvec = n >> 2;
     int occ;
     switch (op) {
@@ -279,6 +180,13 @@ wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, ui
     }
     int grid = grid_for(ctx, (nvec + 7) / 8 + 1, occ);  // >= 8 vectors per thread before adding CTAs; one resident wave at most
     if ((size_t)grid > ctx->scratch.partials_floats) grid = (int)ctx->scratch.partials_floats;
+    return grid;
+}
+
+wgb_status launch_reduce(wgb_pass *p, int op, const float *x, const float *y, uint64_t n, float *result) {
+    if (((uintptr_t)x & 3u) != 0) WGB_FAIL(WGB_ERR_INVALID, "reduce: buffer is not 4-byte aligned");
+    wgb_ctx *ctx = p->ctx;
+    const int grid = reduce_grid_for(ctx, op, n);
     const uint32_t mis = (uint32_t)(((uintptr_t)x & 15u) >> 2);
     const uint64_t head = mis ? 4u - mis : 0u;
     const bool y_aligned = y && ((((uintptr_t)(y + head)) & 15u) == 0);

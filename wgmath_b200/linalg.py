@@ -172,6 +172,14 @@ class Gemv:
                                 1 if m.ordering.is_row_major() else 0, v.buffer()._h, ctypes.byref(sv), int(op), e.buffer()._h,
                                 ctypes.byref(se)))
 
+    def dispatch_reduce(self, device, shapes, pass_, result, m, v, reduce_op: "ReduceOp", variant=GemvVariant.Gemv):
+        """result = reduce_op(m * v) in one launch (wgb_gemv_reduce): Gemv::dispatch + Reduce::dispatch(out, result) with the product
+        vector never leaving the library; bit-identical to the two-dispatch chain through a 16-byte aligned `out`."""
+        m, v = as_view(m, 3), as_view(v, 3)
+        sm, sv = shapes.get(device, m.shape()).to_c(), shapes.get(device, v.shape()).to_c()
+        check(lib().wgb_gemv_reduce(pass_._h, int(variant), int(reduce_op), result.buffer()._h, m.buffer()._h, ctypes.byref(sm),
+                                    1 if m.ordering.is_row_major() else 0, v.buffer()._h, ctypes.byref(sv)))
+
 
 class OpAssign:
     """op_assign.rs:43-94: `OpAssign(pipeline, variant)` -> fields `.0` / `.1` are `pipeline` / `variant`."""
