@@ -578,9 +578,11 @@ def test_gemm_host_enqueue_sizes_change_while_products_are_in_flight(gpu, shapes
         assert rel_err(cm(out, M, N), ref) < F32_TOL, (M, N, K)
 
 
-def test_graph_refuses_to_replay_after_a_workspace_reallocation(gpu, shapes):
-    """A recorded 3xTF32 GEMM carries pointers into the context's operand-split workspace.  A larger eager product reallocates
-    it; replaying the old graph would read freed memory, so wgb_graph_launch must fail instead (and a fresh recording works)."""
+def test_graph_refuses_to_replay_after_a_workspace_reallocation(gpu, shapes, monkeypatch):
+    """A recorded 3xTF32 GEMM in its split-kernel form carries pointers into the context's operand-split workspace.  A larger
+    eager product reallocates it; replaying the old graph would read freed memory, so wgb_graph_launch must fail instead (and a
+    fresh recording works)."""
+    monkeypatch.setenv("WGB_TF32_FUSED_SPLIT", "0")      # (the in-kernel split needs no workspace)
     dev = w.GpuInstance.new().device()          # own context: its workspaces start empty
     sh = w.ViewShapeBuffers.new()
     gemm = w.Gemm.from_device(dev)

@@ -362,6 +362,28 @@ static void launch_sel(bool vec, int nv, const GemvArgs &a, dim3 grid, cudaStrea
     }
 }
 
+// Resident CTAs per SM of the gemv_tr instantiation a launch will use (cached: the occupancy query costs microseconds).
+static int gemv_t_resident(bool vec, int nv) {
+    static int cache[2][3] = {};
+    const int vi = vec ? 1 : 0, ni = nv == 1 ? 0 : (nv == 2 ? 1 : 2);
+    if (cache[vi][ni] == 0) {
+        int n = 0;
+        cudaError_t e;
+        if (vec) e = nv == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<true, 1>, kThreads, 0)
+                   : nv == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<true, 2>, kThreads, 0)
+                             : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<true, 4>, kThreads, 0);
+        else e = nv == 1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<false, 1>, kThreads, 0)
+                 : nv == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<false, 2>, kThreads, 0)
+                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gemv_t_kernel<false, 4>, kThreads, 0);
+        if (e != cudaSuccess || n < 1) {
+            (void)cudaGetLastError();
+            n = 4;
+        }
+        cache[vi][ni] = n;
+    }
+    return cache[vi][ni];
+}
+
 __global__ void gemv_empty_k_kernel(GemvArgs a, uint32_t nmats) {   // K == 0 with a fused op: out = 0 (op) operand
     const uint64_t total = (uint64_t)a.M * a.C * nmats;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -434,6 +456,24 @@ wgb_status launch_gemv(wgb_pass *p, bool tr, float *out, const wgb_view_shape &s
         const uint64_t max_split = (a.K + min_chunk - 1) / min_chunk;
         if (nsplit > max_split) nsplit = max_split;
         if (nsplit > 65535) nsplit = 65535;
+    }
+    if (tr && nsplit > 1) {
+        // gemv_tr CTAs all stream the same number of bytes, so the launch runs in waves of (SMs x resident CTAs): among the split
+        // counts up to twice the first guess, take the one whose last wave is fullest (65536 x 4096: 8 splits = 6.92 waves on 4
+        // resident CTAs per SM instead of 5 splits = 4.32)
+        const uint64_t resident = (uint64_t)ctx->prop.multiProcessorCount * (uint64_t)gemv_t_resident(vec, nv);
+        const uint64_t max_split = (a.K + min_chunk - 1) / min_chunk;
+        double best = 0.0;
+        uint64_t best_n = nsplit;
+        for (uint64_t n = nsplit; n <= 2 * nsplit + 1 && n <= max_split && n <= 65535; ++n) {
+            const double waves = (double)(tiles_x * zdim * n) / (double)resident;
+            const double eff = waves / (double)(uint64_t)(waves + 0.999999);
+            if (eff > best + 0.02) {
+                best = eff;
+                best_n = n;
+            }
+        }
+        nsplit = best_n;
     }
     uint32_t chunk = (uint32_t)(((uint64_t)a.K + nsplit - 1) / nsplit);
     chunk = (chunk + 31u) & ~31u;
