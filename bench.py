@@ -67,7 +67,9 @@ def traffic_from_profile(kernel_substr: str):
             if line.startswith("## "):
                 if rd is not None and wr is not None:
                     break
-                in_kernel = kernel_substr in line
+                # (the kernel template has trailing defaulted parameters: match the instantiation up to where the name given ends)
+                stem = kernel_substr.rstrip(">")
+                in_kernel = (stem + ">") in line or (stem + ",") in line
                 continue
             if not in_kernel:
                 continue
