@@ -8,7 +8,8 @@ pub trait CommandEncoderExt {
 }
 impl CommandEncoderExt for CommandEncoder {
     fn compute_pass<'encoder>(&'encoder mut self, label: &str, timestamps: Option<&mut GpuTimestamps>) -> ComputePass<'encoder> {
-        let (b, e) = timestamps.and_then(|ts| ts.next_compute_pass_timestamp_writes()).unwrap_or((std::ptr::null_mut(), std::ptr::null_mut()));
+        let (b, e) = timestamps.and_then(|ts| ts.next_compute_pass_timestamp_writes()).map(|w| (w.begin_event, w.end_event))
+            .unwrap_or((std::ptr::null_mut(), std::ptr::null_mut()));
         self.begin_compute_pass(label, b, e)
     }
 }

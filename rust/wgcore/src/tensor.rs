@@ -1,10 +1,14 @@
 //! crates/wgcore/src/tensor.rs (line numbers below refer to it): buffers, builders, views.  The view arithmetic is the
 //! reference's, verbatim in meaning; only buffer creation / copy / read go through the C ABI.
+use crate::gpu::GpuInstance;
 use crate::shapes::ViewShape;
 use bytemuck::Pod;
+use encase::internal::{CreateFrom, ReadFrom, WriteInto};
+use encase::{ShaderSize, ShaderType, StorageBuffer};
+use nalgebra::{Dim, IsContiguous, Matrix, Storage};
 use std::marker::PhantomData;
 use std::mem::size_of;
-use wgpu::{Buffer, BufferAddress, BufferDescriptor, BufferUsages, CommandEncoder, Device};
+use wgpu::{Buffer, BufferAddress, BufferDescriptor, BufferUsages, BufferView, CommandEncoder, Device};
 
 #[derive(Copy, Clone)] pub struct ColumnMajor;
 #[derive(Copy, Clone)] pub struct RowMajor;
@@ -34,6 +38,16 @@ impl<const DIM: usize> TensorBuilder<DIM> {
         let buffer = device.create_buffer(&BufferDescriptor { label: self.label.as_deref(), size: size_of::<T>() as u64 * self.len(), usage: self.usage, mapped_at_creation: false });
         GpuTensor { shape: self.shape, buffer, phantom: PhantomData }
     }
+    pub fn build_uninit_encased<T: ShaderType>(self, device: &Device) -> GpuTensor<T, DIM> {   // :132-146
+        let buffer = device.create_buffer(&BufferDescriptor { label: self.label.as_deref(), size: T::min_size().get() * self.len(), usage: self.usage, mapped_at_creation: false });
+        GpuTensor { shape: self.shape, buffer, phantom: PhantomData }
+    }
+    pub fn build_encase<T>(self, device: &Device, data: impl AsRef<[T]>) -> GpuTensor<T, DIM> where T: ShaderType + ShaderSize + WriteInto {   // :164-173
+        let mut bytes = vec![];
+        let mut buffer = StorageBuffer::new(&mut bytes);
+        buffer.write(data.as_ref()).unwrap();
+        self.build_bytes(device, &bytes)
+    }
     pub fn build_bytes<T>(self, device: &Device, data: &[u8]) -> GpuTensor<T, DIM> {          // :149-161
         GpuTensor { shape: self.shape, buffer: device.create_buffer_init(data, self.usage), phantom: PhantomData }
     }
@@ -50,6 +64,11 @@ impl<T, const DIM: usize> GpuTensor<T, DIM> {
     pub fn is_empty(&self) -> bool { self.len() == 0 }
     pub fn len(&self) -> u64 { self.shape.into_iter().map(|s| s as u64).product() }
     pub fn bytes_len(&self) -> u64 where T: Pod { size_of::<T>() as u64 * self.len() }
+    pub fn bytes_len_encased(&self) -> u64 where T: ShaderType { T::min_size().get() * self.len() }       // :217-222
+    pub fn copy_from_encased(&self, encoder: &mut CommandEncoder, source: &GpuTensor<T, DIM>) where T: ShaderType {   // :235-241
+        assert_eq!(self.len(), source.len());
+        encoder.copy_buffer_to_buffer(&source.buffer, 0, &self.buffer, 0, self.bytes_len_encased())
+    }
     pub fn copy_from(&self, encoder: &mut CommandEncoder, source: &GpuTensor<T, DIM>) where T: Pod {      // :227-233
         assert_eq!(self.len(), source.len());
         encoder.copy_buffer_to_buffer(&source.buffer, 0, &self.buffer, 0, self.bytes_len())
@@ -69,12 +88,27 @@ impl<T, const DIM: usize> GpuTensor<T, DIM> {
         embedded_shape[..DIM].copy_from_slice(&self.shape[..DIM]);
         self.reshape(embedded_shape, None, None)
     }
-    /// :375-384 — `async` kept for source compatibility; blocks like `poll(wait)`.
-    pub async fn read(&self, _device: &Device) -> anyhow::Result<Vec<T>> where T: Pod {
-        Ok(bytemuck::try_cast_slice(&self.buffer.read_bytes()).map_err(|e| anyhow::anyhow!("{e}"))?.to_vec())
+    /// :300-325 — the map_async + poll(wait) + get_mapped_range sequence is one blocking device-to-host copy here; the view owns
+    /// the bytes.  `async` kept for source compatibility.
+    pub async fn read_bytes<'a>(&'a self, _device: &'a Device) -> anyhow::Result<BufferView<'a>> {
+        Ok(BufferView::new(self.buffer.read_bytes()))
+    }
+    /// :375-384
+    pub async fn read(&self, device: &Device) -> anyhow::Result<Vec<T>> where T: Pod {
+        let data = self.read_bytes(device).await?;
+        Ok(bytemuck::try_cast_slice(&data).map_err(|e| anyhow::anyhow!("{e}"))?.to_vec())
+    }
+    /// :387-399
+    pub async fn read_encased(&self, device: &Device) -> anyhow::Result<Vec<T>> where T: ShaderType + ReadFrom + ShaderSize + CreateFrom {
+        let data = self.read_bytes(device).await?;
+        let mut result = vec![];
+        let bytes: &[u8] = data.as_ref();
+        StorageBuffer::new(&bytes).read(&mut result)?;
+        Ok(result)
     }
     pub async fn read_to(&self, device: &Device, out: &mut [T]) -> anyhow::Result<()> where T: Pod { out.copy_from_slice(&self.read(device).await?); Ok(()) }
-    pub async fn slow_read(&self, gpu: &crate::gpu::GpuInstance) -> Vec<T> where T: Pod { self.read(gpu.device()).await.unwrap() }   // :340-355: no staging copy needed
+    pub async fn slow_read(&self, gpu: &GpuInstance) -> Vec<T> where T: Pod { self.read(gpu.device()).await.unwrap() }   // :340-355: no staging copy needed
+    pub async fn slow_read_encased(&self, gpu: &GpuInstance) -> Vec<T> where T: ShaderType + ReadFrom + ShaderSize + CreateFrom { self.read_encased(gpu.device()).await.unwrap() }   // :357-372
     pub fn reshape<Ordering: MatrixOrdering, const DIM2: usize>(&self, shape: [u32; DIM2], stride: Option<u32>, stride_mat: Option<u32>) -> GpuTensorView<'_, T, Ordering, DIM2> {   // :514-541
         assert!(shape.iter().product::<u32>() <= self.shape.iter().product::<u32>());
         let mut size = [1; 3];
@@ -122,8 +156,13 @@ impl<T, Ordering> GpuMatrixView<'_, T, Ordering> {                              
 }
 impl<T> GpuMatrix<T> {                                                                                // :544-626
     pub fn uninit(device: &Device, nrows: u32, ncols: u32, usage: BufferUsages) -> Self where T: Pod { TensorBuilder::matrix(nrows, ncols, usage).build(device) }
-    /// `init` from a contiguous column-major slice (the reference takes a nalgebra matrix and uses `as_slice`, :561-571).
-    pub fn init(device: &Device, nrows: u32, ncols: u32, column_major: &[T], usage: BufferUsages) -> Self where T: Pod { TensorBuilder::matrix(nrows, ncols, usage).build_init(device, column_major) }
+    pub fn uninit_encased(device: &Device, nrows: u32, ncols: u32, usage: BufferUsages) -> Self where T: ShaderType { TensorBuilder::matrix(nrows, ncols, usage).build_uninit_encased(device) }   // :553-558
+    /// :561-571 — a contiguous (column-major) nalgebra matrix, uploaded as it lies in memory.
+    pub fn init<R: Dim, C: Dim, S: Storage<T, R, C> + IsContiguous>(device: &Device, matrix: &Matrix<T, R, C, S>, usage: BufferUsages) -> Self where T: Pod + nalgebra::Scalar {
+        TensorBuilder::matrix(matrix.nrows() as u32, matrix.ncols() as u32, usage).build_init(device, matrix.as_slice())
+    }
+    /// Extension: the same from a plain column-major slice.
+    pub fn init_slice(device: &Device, nrows: u32, ncols: u32, column_major: &[T], usage: BufferUsages) -> Self where T: Pod { TensorBuilder::matrix(nrows, ncols, usage).build_init(device, column_major) }
     pub fn column(&self, i: u32) -> GpuVectorView<'_, T> {
         GpuTensorView { view_shape: ViewShape { size: [self.shape[0], 1, 1], stride: 1, stride_mat: 1, offset: self.shape[0] * i }, buffer: &self.buffer, phantom: PhantomData }
     }
@@ -141,6 +180,8 @@ impl<T> GpuMatrix<T> {                                                          
     }
 }
 impl<T> GpuVector<T> {                                                                                // :629-682
+    pub fn encase(device: &Device, vector: impl AsRef<[T]>, usage: BufferUsages) -> Self where T: ShaderType + ShaderSize + WriteInto { let v = vector.as_ref(); TensorBuilder::vector(v.len() as u32, usage).build_encase(device, v) }   // :633-639
+    pub fn uninit_encased(device: &Device, len: u32, usage: BufferUsages) -> Self where T: ShaderType { TensorBuilder::vector(len, usage).build_uninit_encased(device) }   // :650-655
     pub fn uninit(device: &Device, len: u32, usage: BufferUsages) -> Self where T: Pod { TensorBuilder::vector(len, usage).build(device) }
     pub fn init(device: &Device, vector: impl AsRef<[T]>, usage: BufferUsages) -> Self where T: Pod { let v = vector.as_ref(); TensorBuilder::vector(v.len() as u32, usage).build_init(device, v) }
     pub fn rows(&self, first_row: u32, num_rows: u32) -> GpuVectorView<'_, T> {
@@ -148,6 +189,7 @@ impl<T> GpuVector<T> {                                                          
     }
 }
 impl<T> GpuScalar<T> {                                                                                // :684-705
+    pub fn uninit_encased(device: &Device, usage: BufferUsages) -> Self where T: ShaderType { TensorBuilder::scalar(usage).build_uninit_encased(device) }   // :692-697
     pub fn uninit(device: &Device, usage: BufferUsages) -> Self where T: Pod { TensorBuilder::scalar(usage).build(device) }
     pub fn init(device: &Device, value: T, usage: BufferUsages) -> Self where T: Pod { TensorBuilder::scalar(usage).build_init(device, &[value]) }
 }

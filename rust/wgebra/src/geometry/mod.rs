@@ -39,12 +39,16 @@ macro_rules! geometry_shader {
     ($(#[$doc:meta])* $name:ident, $op:expr, $dim:expr, $mat:ty, $out:ty) => {
         $(#[$doc])*
         pub struct $name;
+        // what `#[derive(Shader)]` generates in the reference (cholesky.rs:21-34 ...): the `wgcore::Shader` impl
+        wgcore::impl_shader!($name, concat!("wgebra/src/geometry/", stringify!($name), ".wgsl"), "wgmath_b200/csrc/geometry.cuh", |_device| {
+            debug_assert_eq!(unsafe { sys::wgb_geometry_in_bytes($dim) } as usize, core::mem::size_of::<$mat>());
+            debug_assert_eq!(unsafe { sys::wgb_geometry_out_bytes($op, $dim) } as usize, core::mem::size_of::<$out>());
+            $name
+        });
         impl $name {
-            pub const FILE_PATH: &'static str = "wgmath_b200/csrc/geometry.cuh";
-            pub fn from_device(_device: &Device) -> Result<Self, ComposerError> {
-                debug_assert_eq!(unsafe { sys::wgb_geometry_in_bytes($dim) } as usize, core::mem::size_of::<$mat>());
-                debug_assert_eq!(unsafe { sys::wgb_geometry_out_bytes($op, $dim) } as usize, core::mem::size_of::<$out>());
-                Ok($name)
+            /// Inherent twin of `Shader::from_device`, so the call compiles with or without the trait in scope.
+            pub fn from_device(device: &Device) -> Result<Self, ComposerError> {
+                <Self as wgcore::Shader>::from_device(device)
             }
             /// `outputs[i] = f(inputs[i])`: `KernelDispatch::new(device, pass, &pipeline).bind0([inputs.buffer(),
             /// outputs.buffer()]).dispatch(inputs.len())` of the reference's tests.
@@ -86,8 +90,10 @@ geometry_shader!(/// svd3.rs:24-27
 
 /// inv.rs:3-8: one shader holding inv2 / inv3 / inv4 (inv.wgsl:8-88).
 pub struct WgInv;
+wgcore::impl_shader!(WgInv, "wgebra/src/geometry/inv.wgsl", "wgmath_b200/csrc/geometry.cuh", |_device| WgInv);
 impl WgInv {
-    pub fn from_device(_device: &Device) -> Result<Self, ComposerError> { Ok(WgInv) }
+    /// Inherent twin of `Shader::from_device`.
+    pub fn from_device(device: &Device) -> Result<Self, ComposerError> { <Self as wgcore::Shader>::from_device(device) }
     pub fn dispatch2(&self, pass: &mut ComputePass, inputs: &GpuVector<Matrix2<f32>>, outputs: &GpuVector<Matrix2<f32>>) {
         sys::check(unsafe { sys::wgb_geometry_batch(pass.raw(), INV, 2, inputs.buffer().raw(), 0, outputs.buffer().raw(), 0, inputs.len()) });
     }

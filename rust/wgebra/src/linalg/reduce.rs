@@ -1,5 +1,7 @@
 //! crates/wgebra/src/linalg/reduce.rs:13-124
-use super::ComposerError;
+use super::{require_f32, ComposerError};
+use bytemuck::Pod;
+use nalgebra::DVector;
 use wgcore::shapes::ViewShapeBuffers;
 use wgcore::tensor::{GpuScalar, GpuVectorView};
 use wgpu::{sys, ComputePass, ComputePipeline, Device};
@@ -16,21 +18,23 @@ impl Reduce {
     pub const FILE_PATH: &'static str = "wgebra/src/reduce.wgsl";
     pub fn new(_device: &Device, op: ReduceOp) -> Result<Self, ComposerError> { Ok(Self(ComputePipeline("reduce"), op)) }
     /// `result = reduce(value)`; the whole machine instead of the reference's single 128-thread workgroup (reduce.rs:112).
-    pub fn dispatch<'a>(&self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass,
-        value: impl Into<GpuVectorView<'a, f32>>, result: &GpuScalar<f32>) {
+    pub fn dispatch<'a, T: Pod>(&self, device: &Device, shapes: &ViewShapeBuffers, pass: &mut ComputePass,
+        value: impl Into<GpuVectorView<'a, T>>, result: &GpuScalar<T>) {
+        require_f32::<T>("Reduce");
         let value = value.into();
-        let sv = shapes.get(device, value.shape());
+        let _ = shapes.get(device, value.shape());
+        let sv = value.shape().into();
         sys::check(unsafe { sys::wgb_reduce(pass.raw(), self.1 as i32, value.buffer().raw(), &sv, result.buffer().raw()) });
     }
-    /// reduce.rs:116-124 on a plain slice (the reference takes a nalgebra `DVector`).
+    /// reduce.rs:116-124
     #[doc(hidden)]
-    pub fn eval_cpu(&self, val: &[f32]) -> f32 {
+    pub fn eval_cpu(&self, val: &DVector<f32>) -> f32 {
         match self.1 {
-            ReduceOp::Min => val.iter().copied().fold(f32::INFINITY, f32::min),
-            ReduceOp::Max => val.iter().copied().fold(f32::NEG_INFINITY, f32::max),
-            ReduceOp::Prod => val.iter().product(),
-            ReduceOp::Sum => val.iter().sum(),
-            ReduceOp::SqNorm => val.iter().map(|x| x * x).sum(),
+            ReduceOp::Min => val.min(),
+            ReduceOp::Max => val.max(),
+            ReduceOp::Prod => val.product(),
+            ReduceOp::Sum => val.sum(),
+            ReduceOp::SqNorm => val.norm_squared(),
         }
     }
 }

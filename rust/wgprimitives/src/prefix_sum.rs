@@ -25,7 +25,7 @@ impl WgPrefixSum {
     /// the workspace only keeps the reference's capacity bookkeeping (its auxiliary levels live in the context).
     pub fn dispatch(&self, device: &Device, pass: &mut ComputePass, workspace: &mut PrefixSumWorkspace, data: &GpuVector<u32>) {
         workspace.reserve(device, data.len() as u32);
-        let shape = data.as_view::<wgcore::tensor::ColumnMajor>().shape();
+        let shape: sys::wgb_view_shape = data.as_view::<wgcore::tensor::ColumnMajor>().shape().into();
         sys::check(unsafe { sys::wgb_prefix_sum(pass.raw(), data.buffer().raw(), &shape) });
     }
 

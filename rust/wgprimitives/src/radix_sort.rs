@@ -26,8 +26,8 @@ impl RadixSort {
                     output_values: &GpuVector<u32>) {
         assert_eq!(input_keys.len(), input_values.len(), "Input keys and values must have the same number of elements");
         assert!(sorting_bits <= 32, "Can only sort up to 32 bits");
-        let (sk, sv) = (input_keys.as_view::<ColumnMajor>().shape(), input_values.as_view::<ColumnMajor>().shape());
-        let (so, sw) = (output_keys.as_view::<ColumnMajor>().shape(), output_values.as_view::<ColumnMajor>().shape());
+        let (sk, sv): (sys::wgb_view_shape, sys::wgb_view_shape) = (input_keys.as_view::<ColumnMajor>().shape().into(), input_values.as_view::<ColumnMajor>().shape().into());
+        let (so, sw): (sys::wgb_view_shape, sys::wgb_view_shape) = (output_keys.as_view::<ColumnMajor>().shape().into(), output_values.as_view::<ColumnMajor>().shape().into());
         sys::check(unsafe {
             sys::wgb_radix_sort(pass.raw(), input_keys.buffer().raw(), &sk, input_values.buffer().raw(), &sv, n_sort.buffer().raw(),
                                 sorting_bits, output_keys.buffer().raw(), &so, output_values.buffer().raw(), &sw)

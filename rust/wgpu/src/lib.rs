@@ -69,6 +69,9 @@ pub mod sys {
         pub fn wgb_event_create(ctx: *mut wgb_ctx, out: *mut *mut wgb_event) -> c_int;
         pub fn wgb_event_destroy(ev: *mut wgb_event) -> c_int;
         pub fn wgb_event_elapsed_ms(begin: *mut wgb_event, end: *mut wgb_event, ms: *mut f32) -> c_int;
+        pub fn wgb_event_record(ev: *mut wgb_event, pass: *mut wgb_pass) -> c_int;
+        pub fn wgb_gemv_reduce(pass: *mut wgb_pass, variant: c_int, reduce_op: c_int, result: *mut wgb_buffer, m: *const wgb_buffer,
+                               m_shape: *const wgb_view_shape, m_ord: c_int, v: *const wgb_buffer, v_shape: *const wgb_view_shape) -> c_int;
     }
 
     /// Non-zero status -> panic with the library's message ("Gemm: dimension mismatch. …" for status 2, as gemm.rs:91).
@@ -157,6 +160,35 @@ impl Buffer {
     }
 }
 impl Drop for Buffer { fn drop(&mut self) { unsafe { sys::wgb_buffer_destroy(self.raw); } } }
+
+/// wgpu::BufferView: the mapped bytes of a buffer; here an owned copy made by one blocking read (tensor.rs:300-325).
+pub struct BufferView<'a> { bytes: Vec<u8>, _buffer: PhantomData<&'a Buffer> }
+impl<'a> BufferView<'a> { pub fn new(bytes: Vec<u8>) -> Self { Self { bytes, _buffer: PhantomData } } }
+impl std::ops::Deref for BufferView<'_> { type Target = [u8]; fn deref(&self) -> &[u8] { &self.bytes } }
+impl AsRef<[u8]> for BufferView<'_> { fn as_ref(&self) -> &[u8] { &self.bytes } }
+
+bitflags::bitflags! {
+    /// wgpu::Backends (gpu.rs:20-29 `with_backends`): accepted and ignored, there is one backend.
+    #[derive(Copy, Clone, Debug, PartialEq, Eq, Hash)]
+    pub struct Backends: u32 { const VULKAN = 1; const GL = 2; const METAL = 4; const DX12 = 8; const BROWSER_WEBGPU = 16; }
+}
+/// wgpu::Adapter (gpu.rs:69-71): what `nvidia-smi -L` would say about the device.
+#[derive(Clone, Debug)]
+pub struct Adapter { pub name: String, pub ordinal: i32 }
+/// wgpu::QuerySet (timestamps.rs:44-46): the event slots live in `GpuTimestamps`; the set is a tag.
+#[derive(Debug, Default)]
+pub struct QuerySet;
+/// wgpu::ComputePassTimestampWrites (timestamps.rs:63-70): the begin / end slots of one pass.
+pub struct ComputePassTimestampWrites<'a> {
+    pub query_set: &'a QuerySet,
+    pub beginning_of_pass_write_index: Option<u32>,
+    pub end_of_pass_write_index: Option<u32>,
+    pub begin_event: *mut sys::wgb_event,
+    pub end_event: *mut sys::wgb_event,
+}
+/// wgpu::BufferAsyncError (timestamps.rs:196-224): never produced, a read is one blocking copy.
+#[derive(Debug, Clone, Copy)]
+pub struct BufferAsyncError;
 
 pub struct CommandBuffer;
 pub struct CommandEncoder { device: Device }
