@@ -337,6 +337,16 @@ wgb_status wgb_geometry_batch(wgb_pass *pass, wgb_geom_op op, int dim, const wgb
  *   [7] work units processed.  enable == 0 frees the trace buffer. */
 wgb_status wgb_debug_tc_trace(wgb_ctx *ctx, int enable, unsigned long long *out, size_t max_records, size_t *n_records);
 
+/* Gemm -> Reduce along one axis, fused: result[j] = reduce_op_i (m1 * m2)[i, j] (axis 1: one value per column,
+ * what one Reduce::dispatch per GpuMatrix::column(j) of the product gives, reduce.rs:100-113 + tensor.rs:574-585) or
+ * result[i] = reduce_op_j (m1 * m2)[i, j] (axis 2).  The product is never stored (no HBM round trip of C): the tensor-core epilogue
+ * leaves per-32-row / per-32-column partial results that a fold kernel combines in index order — deterministic, and equal to the
+ * two-dispatch chain up to f32 rounding (not bit-identical: the chain's reduction tree spans the whole column).  f32 results; f32 or
+ * bf16 operands; one matrix per operand.  Products the tensor-core path does not take are stored in a scratch matrix and reduced. */
+wgb_status wgb_gemm_reduce(wgb_pass *pass, wgb_gemm_variant variant, int axis, wgb_reduce_op reduce_op, wgb_buffer *result,
+                           const wgb_view_shape *result_shape, const wgb_buffer *m1, const wgb_view_shape *m1_shape,
+                           const wgb_buffer *m2, const wgb_view_shape *m2_shape, wgb_dtype in_dtype, wgb_f32_mode f32_mode);
+
 /* Gemv -> Reduce fused: result = reduce_op over the elements of m * v (or tr(m) * v), the reference's
  * Gemv::dispatch + Reduce::dispatch chain (gemv.rs:64-137, reduce.rs:100-113) in one launch.  The product vector is never written to
  * a caller buffer; the scalar is bit-identical to the two-dispatch chain through a 16-byte aligned `out`.  One matrix, one vector. */

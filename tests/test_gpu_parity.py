@@ -743,6 +743,49 @@ def test_gemv_fused_reduce_equals_the_two_dispatch_chain(gpu, shapes, rop, varia
         assert n2 - n1 == 1 and n1 - n0 == 2      # one launch instead of two
 
 
+@pytest.mark.parametrize("rop", list(w.ReduceOp))
+@pytest.mark.parametrize("axis", [1, 2])
+@pytest.mark.parametrize("M,N,K,tr,dtype,mode", [(256, 384, 192, False, "f32", None), (520, 200, 136, True, "f32", None),
+                                                 (1024, 1160, 264, False, "bf16", None), (100, 60, 52, False, "f32", w.F32Mode.Simt),
+                                                 (264, 136, 72, True, "f32", w.F32Mode.Tf32)])
+def test_gemm_fused_reduce_matches_the_two_dispatch_chain(gpu, shapes, rop, axis, M, N, K, tr, dtype, mode):
+    """wgb_gemm_reduce vs the chain Gemm::dispatch, then Reduce per column of the product (wgb_reduce_columns; for axis 2, per row):
+    the product is never stored, results agree to f32 rounding (1e-5 relative; the fused form folds 32-row partials in index order,
+    the chain reduces each whole column with its own tree) and a second run gives the same bits (deterministic)."""
+    dev = gpu.device()
+    ar, ac = (K, M) if tr else (M, K)
+    scale = np.float32(2.0 / K) if rop == w.ReduceOp.Prod else np.float32(1.0)     # Prod: factors near 1
+    A, B = O.uniform(SEED_A, ar, ac) * scale, O.uniform(SEED_B, K, N) + (np.float32(0.5) if rop == w.ReduceOp.Prod else np.float32(0.0))
+    if dtype == "bf16":
+        A, B = O.to_bf16_rne(A), O.to_bf16_rne(B)
+        ta, tb = upload(gpu, O.bf16_bits(A), (ar, ac), "bf16"), upload(gpu, O.bf16_bits(B), (K, N), "bf16")
+    else:
+        ta, tb = upload(gpu, A, (ar, ac)), upload(gpu, B, (K, N))
+    var = w.GemmVariant.GemmTr if tr else w.GemmVariant.Gemm
+    gemm = w.Gemm.from_device(dev)
+    n_out = N if axis == 1 else M
+    r1, r2 = w.TensorBuilder.vector(n_out, STORAGE).build(dev), w.TensorBuilder.vector(n_out, STORAGE).build(dev)
+    path = []
+    run_pass(gpu, lambda p: (gemm.dispatch_reduce(dev, shapes, p, r1, ta, tb, rop, axis, var, f32_mode=mode), path.append(p.last_gemm_path())))
+    run_pass(gpu, lambda p: gemm.dispatch_reduce(dev, shapes, p, r2, ta, tb, rop, axis, var, f32_mode=mode))
+    got = r1.read()
+    assert got.tobytes() == r2.read().tobytes()
+    assert path[0] == (1 if mode == w.F32Mode.Simt else 2 if dtype == "bf16" else 3 if mode == w.F32Mode.Tf32 else 4)
+    # the chain: the product stored (f32), then reduced along the axis in float64 for the expectation
+    c = w.TensorBuilder.matrix(M, N, STORAGE).build(dev)
+    run_pass(gpu, lambda p: gemm.dispatch_generic(dev, shapes, p, c, ta, tb, var, f32_mode=mode))
+    C = cm(c.read(), M, N).astype(np.float64)
+    red = {w.ReduceOp.Min: np.min, w.ReduceOp.Max: np.max, w.ReduceOp.Sum: np.sum, w.ReduceOp.Prod: np.prod,
+           w.ReduceOp.SqNorm: lambda x, axis: np.sum(x * x, axis=axis)}[rop]
+    want = red(C, axis=0 if axis == 1 else 1)
+    assert rel_err(got, want) < (1e-3 if rop == w.ReduceOp.Prod else 1e-5)
+    if axis == 1 and rop != w.ReduceOp.Prod:
+        # and against the library's own single-launch column reduce of the stored product
+        rc = w.TensorBuilder.vector(N, STORAGE).build(dev)
+        run_pass(gpu, lambda p: w.Reduce.new(dev, rop).dispatch_columns(dev, shapes, p, c, rc))
+        assert rel_err(got, rc.read().astype(np.float64)) < 1e-5
+
+
 def test_graph_capture_replays_a_dispatch_chain(gpu, shapes):
     """wgb_graph_*: record gemm -> op_assign -> reduce once, replay it, same result as the eager sequence."""
     dev = gpu.device()

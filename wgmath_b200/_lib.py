@@ -81,6 +81,7 @@ def lib() -> ctypes.CDLL:
         "wgb_gemv_ord": ([vp, ci, vp, sp, vp, sp, ci, vp, sp], ci),
         "wgb_gemv_op": ([vp, ci, vp, sp, vp, sp, ci, vp, sp, ci, vp, sp], ci),
         "wgb_gemv_reduce": ([vp, ci, ci, vp, vp, sp, ci, vp, sp], ci),
+        "wgb_gemm_reduce": ([vp, ci, ci, ci, vp, sp, vp, sp, vp, sp, ci, ci], ci),
         "wgb_debug_tc_trace": ([vp, ci, vp, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)], ci),
         "wgb_gemm_host": ([vp, ci, u32, u32, u32, vp, vp, vp, ci, ci, ci, ci], ci),
         "wgb_gemm_host_enqueue": ([vp, ci, u32, u32, u32, vp, vp, vp, ci, ci, ci, ci], ci),
@@ -138,7 +139,7 @@ EXPORTED = ["wgb_abi_version", "wgb_last_error_string", "wgb_ctx_create", "wgb_c
             "wgb_graph_destroy", "wgb_buffer_create", "wgb_buffer_create_init", "wgb_buffer_wrap",
             "wgb_buffer_destroy", "wgb_buffer_size", "wgb_buffer_device_ptr", "wgb_buffer_write", "wgb_buffer_copy",
             "wgb_buffer_read", "wgb_host_alloc", "wgb_host_free", "wgb_gemm", "wgb_gemm_ex", "wgb_gemm_op", "wgb_gemm_ord", "wgb_gemm_host", "wgb_gemm_host_enqueue", "wgb_gemm_host_flush", "wgb_gemv",
-            "wgb_gemv_ord", "wgb_gemv_op", "wgb_gemv_reduce", "wgb_debug_tc_trace",
+            "wgb_gemv_ord", "wgb_gemv_op", "wgb_gemv_reduce", "wgb_gemm_reduce", "wgb_debug_tc_trace",
             "wgb_op_assign", "wgb_reduce", "wgb_prefix_sum", "wgb_radix_sort", "wgb_geometry_in_bytes", "wgb_geometry_out_bytes", "wgb_geometry_batch", "wgb_dot", "wgb_reduce_columns", "wgb_fill_uniform", "wgb_event_create",
             "wgb_event_destroy", "wgb_event_record", "wgb_event_elapsed_ms", "wgb_comm_get_unique_id",
             "wgb_comm_init_rank", "wgb_comm_destroy", "wgb_gemm_row_sharded", "wgb_peer_gather_create",

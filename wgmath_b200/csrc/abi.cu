@@ -893,6 +893,40 @@ wgb_status wgb_gemm_op(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out
 }
 
 
+// Gemm -> Reduce along one axis in one pass over the operands: the product itself is never stored.
+wgb_status wgb_gemm_reduce(wgb_pass *pass, wgb_gemm_variant variant, int axis, wgb_reduce_op rop, wgb_buffer *result,
+                           const wgb_view_shape *rs, const wgb_buffer *m1, const wgb_view_shape *s1, const wgb_buffer *m2,
+                           const wgb_view_shape *s2, wgb_dtype in_dtype, wgb_f32_mode mode) {
+    if (!pass || !result || !rs || !m1 || !s1 || !m2 || !s2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_reduce: null argument");
+    if ((int)variant < 0 || (int)variant > WGB_GEMM_TR_FAST) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_reduce: unknown variant %d", (int)variant);
+    if (axis != 1 && axis != 2) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_reduce: axis must be 1 (one value per column) or 2 (one per row)");
+    if ((int)rop < 0 || (int)rop > WGB_RED_SQNORM) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_reduce: unknown reduce op %d", (int)rop);
+    if (in_dtype != WGB_F32 && in_dtype != WGB_BF16) WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_reduce: unsupported dtype");
+    if ((int)mode < 0 || (int)mode > WGB_F32_SIMT) WGB_FAIL(WGB_ERR_INVALID, "wgb_gemm_reduce: unknown f32 mode %d", (int)mode);
+    if (s1->size[2] != 1 || s2->size[2] != 1) WGB_FAIL(WGB_ERR_UNSUPPORTED, "wgb_gemm_reduce: one matrix per operand");
+    const bool tr = variant == WGB_GEMM_TR || variant == WGB_GEMM_TR_FAST;
+    const uint32_t M = tr ? s1->size[1] : s1->size[0], K = tr ? s1->size[0] : s1->size[1], N = s2->size[1];
+    if (K != s2->size[0]) WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm: dimension mismatch. (m1 cols %u vs m2 rows %u)", K, s2->size[0]);
+    const uint32_t n_out = axis == 1 ? N : M;
+    if (rs->size[0] != n_out)
+        WGB_FAIL(WGB_ERR_DIM_MISMATCH, "Gemm-reduce: dimension mismatch. (result has %u elements, the product has %u %s)", rs->size[0], n_out,
+                 axis == 1 ? "columns" : "rows");
+    pass->last_gemm_path = 0;
+    if (any_zero_buffer({result, m1, m2}) || M == 0 || N == 0) return WGB_OK;
+    WGB_TRY(check_view(result, *rs, 4, "gemm_reduce result", true));
+    WGB_TRY(check_view(m1, *s1, dtype_size(in_dtype), "gemm m1"));
+    WGB_TRY(check_view(m2, *s2, dtype_size(in_dtype), "gemm m2"));
+    GemmProblem g{};
+    g.tr = tr;
+    g.M = M; g.N = N; g.K = K; g.nmats = 1;
+    g.a = m1->ptr; g.a_off = s1->offset; g.lda = s1->stride; g.sa = s1->stride_mat;
+    g.b = m2->ptr; g.b_off = s2->offset; g.ldb = s2->stride; g.sb = s2->stride_mat;
+    g.in_dtype = in_dtype;
+    g.out_dtype = WGB_F32;
+    DeviceGuard dg(pass->ctx->device);
+    return gemm_reduce_dispatch(pass, g, mode, axis, (int)rop, (float *)result->ptr + rs->offset);
+}
+
 wgb_status wgb_gemm_ord(wgb_pass *pass, wgb_gemm_variant variant, wgb_buffer *out, const wgb_view_shape *so, wgb_ordering out_ord,
                         const wgb_buffer *m1, const wgb_view_shape *s1, wgb_ordering m1_ord, const wgb_buffer *m2,
                         const wgb_view_shape *s2, wgb_ordering m2_ord, wgb_dtype in_dtype, wgb_dtype out_dtype, wgb_f32_mode mode,

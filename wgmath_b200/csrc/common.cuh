@@ -206,6 +206,9 @@ struct GemmProblem {
     int ep_op = -1;
     const void *e = nullptr;
     uint64_t e_off = 0, lde = 0, se = 0;
+    // fused reduction of the product (wgb_gemm_reduce): c is not written; red_axis 1 = one value per column, 2 = one per row
+    int red_axis = 0, red_op = 0;
+    float *red_partials = nullptr;   // [ceil(M / 32)][N] (axis 1) or [ceil(N / 32)][M] (axis 2), filled by the epilogue
 };
 // out-of-line helper shared by both GEMM kernels
 template <typename T>
@@ -229,5 +232,8 @@ bool gemm_fused_eligible(const GemmProblem &g, wgb_f32_mode mode);
 
 // column-panel range restriction used by the sharded GEMM (compute only n in [n_begin, n_end))
 wgb_status gemm_dispatch(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode);
+// the product reduced along one axis without being stored (gemm.cu): axis 1 = one value per column, 2 = one per row
+wgb_status gemm_reduce_dispatch(wgb_pass *p, GemmProblem g, wgb_f32_mode mode, int axis, int op, float *result);
+bool gemm_tc_direct_f32_ok(const GemmProblem &g);
 
 }  // namespace wgb

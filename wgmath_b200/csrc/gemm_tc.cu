@@ -232,7 +232,7 @@ static void plan_tail(TcArgs &a, uint32_t clusters, int bn, int cg, int kind, bo
     a.total_units = a.total_tiles;
     const uint32_t tail = a.total_tiles % clusters;
     if (tail == 0) return;
-    if (env_int("WGB_TC_SPLITK", 0) != 0) {
+    if (env_int("WGB_TC_SPLITK", 0) != 0 && a.red_axis == 0) {   // (split partials are not final values: no fused reduction there)
         uint32_t split = clusters / tail;
         if (split > 8) split = 8;
         if (split > a.num_kb / 4) split = a.num_kb / 4;
@@ -424,6 +424,9 @@ wgb_status launch_gemm_tc(wgb_pass *p, const GemmProblem &g, wgb_f32_mode mode, 
         }
     }
     args.fused_split = fused_split ? 1u : 0u;
+    args.red_axis = (uint32_t)g.red_axis;
+    args.red_op = g.red_op;
+    args.red_partials = g.red_partials;
     args.ep_op = g.ep_op;
     args.ep = g.e ? (const char *)g.e + g.e_off * dtype_size(g.out_dtype) : nullptr;
     args.ep_ld = g.lde;

@@ -271,6 +271,12 @@ struct TcArgs {
     int ep_op;               // fused element-wise epilogue (-1: none): out = acc (op) e
     const void *ep;          // operand view base (element 0 of the view), element type = TOut
     uint64_t ep_ld, ep_sm;
+    // fused reduction of the product (wgb_gemm_reduce): the product is not stored; every 32-column block of a tile leaves as
+    // partial results instead — red_axis 1: per column over the 32 rows of each epilogue warp -> red_partials[row / 32][N];
+    // red_axis 2: per row over the block's 32 columns -> red_partials[col / 32][M].  A fold kernel combines them in index order.
+    uint32_t red_axis;       // 0: none
+    int red_op;              // wgb_reduce_op
+    float *red_partials;
     uint32_t fused_split;    // 3xTF32: the kernel splits the raw f32 tiles itself (FS instantiation) instead of reading hi / lo copies
     uint32_t debug_skip;     // diagnostics only (WGB_TC_DEBUG_SKIP): bit 0 = do not load A tiles, bit 1 = do not load B tiles
     unsigned long long *trace;   // diagnostics (wgb_debug_tc_trace): 8 words per cluster, null = off
@@ -735,6 +741,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     } else if (split_unit) {
 #pragma unroll
                         for (int i = 0; i < 32; ++i) __stcg(wsp + (uint64_t)(c * 32 + i) * kBlockM, __uint_as_float(cur[i]));
+                    } else if (args.red_axis != 0) {
+                        // fused reduction: neutral element outside the view, SqNorm squares first
+                        const int rop = args.red_op;
+                        const float init = rop == WGB_RED_MIN ? 3.4e38f : rop == WGB_RED_MAX ? -3.4e38f : rop == WGB_RED_PROD ? 1.0f : 0.0f;
+                        auto comb = [rop](float a, float b) {
+                            return rop == WGB_RED_MIN ? fminf(a, b) : rop == WGB_RED_MAX ? fmaxf(a, b) : rop == WGB_RED_PROD ? a * b : a + b;
+                        };
+                        float x[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const float val = __uint_as_float(cur[i]);
+                            x[i] = (row_ok && n0 + c * 32 + i < args.N) ? (rop == WGB_RED_SQNORM ? val * val : val) : init;
+                        }
+                        if (args.red_axis == 2) {
+                            // one value per row: fold the 32 columns of the block in column order
+                            float a = x[0];
+#pragma unroll
+                            for (int i = 1; i < 32; ++i) a = comb(a, x[i]);
+                            if (row_ok && n0 + c * 32 < args.N) args.red_partials[(uint64_t)((n0 + c * 32) / 32) * args.M + row] = a;
+                        } else {
+                            // one value per column: transpose-reduce across the warp's 32 rows (31 shuffles): after the step with
+                            // offset s, the lanes with bit s set keep the upper half of the remaining columns
+#pragma unroll
+                            for (int s = 16; s > 0; s >>= 1) {
+                                const bool upper = (lane & s) != 0;
+#pragma unroll
+                                for (int j = 0; j < s; ++j) {
+                                    const float mine = upper ? x[j + s] : x[j], send = upper ? x[j] : x[j + s];
+                                    x[j] = comb(mine, __shfl_xor_sync(0xFFFFFFFFu, send, s));
+                                }
+                            }
+                            const uint32_t col = n0 + c * 32 + lane;      // lane l now holds column l of the block
+                            if (col < args.N && row - lane < args.M) args.red_partials[(uint64_t)((row - lane) / 32) * args.N + col] = x[0];
+                        }
                     } else if (tma_epi) {
                         // TMEM -> registers -> shared memory block [32 columns][128 rows] -> one bulk tensor store per
                         // destination.  Whole 256 B (bf16) / 512 B (f32) column segments leave the SM instead of per-lane

@@ -91,6 +91,17 @@ class Gemm:
                                 m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], _DTYPE_CODE[out.dtype], int(mode)))
 
 
+    def dispatch_reduce(self, device, shapes, pass_, result, m1, m2, reduce_op: "ReduceOp", axis: int = 1, variant=GemmVariant.Gemm,
+                        f32_mode=None):
+        """result[j] = reduce_op over the column j of m1 * m2 (axis=1), or result[i] over the row i (axis=2), in one pass over the
+        operands (wgb_gemm_reduce): the reference's Gemm::dispatch followed by one Reduce::dispatch per GpuMatrix::column(j), with
+        the product never stored.  `result` is a vector (or vector view) of N (axis 1) or M (axis 2) f32."""
+        r, m1, m2 = as_view(result, 3), as_view(m1, 3), as_view(m2, 3)
+        rs, s1, s2 = (shapes.get(device, v.shape()).to_c() for v in (r, m1, m2))
+        mode = self.f32_mode if f32_mode is None else f32_mode
+        check(lib().wgb_gemm_reduce(pass_._h, int(variant), axis, int(reduce_op), r.buffer()._h, ctypes.byref(rs), m1.buffer()._h,
+                                    ctypes.byref(s1), m2.buffer()._h, ctypes.byref(s2), _DTYPE_CODE[m1.dtype], int(mode)))
+
     def dispatch_op(self, device, shapes, pass_, out, m1, m2, op: "OpAssignVariant", operand, variant=GemmVariant.Gemm, f32_mode=None):
         """out = (m1 * m2) (op) operand in one launch (wgb_gemm_op): Gemm::dispatch + OpAssign::dispatch(out, operand) fused
         into the GEMM epilogue.  `operand` may be `out` itself (accumulate into out)."""
