@@ -778,7 +778,11 @@ def test_gemm_fused_reduce_matches_the_two_dispatch_chain(gpu, shapes, rop, axis
     red = {w.ReduceOp.Min: np.min, w.ReduceOp.Max: np.max, w.ReduceOp.Sum: np.sum, w.ReduceOp.Prod: np.prod,
            w.ReduceOp.SqNorm: lambda x, axis: np.sum(x * x, axis=axis)}[rop]
     want = red(C, axis=0 if axis == 1 else 1)
-    assert rel_err(got, want) < (1e-3 if rop == w.ReduceOp.Prod else 1e-5)
+    if rop == w.ReduceOp.Prod:      # a product of ~1000 factors may leave the f32 range: compare where it stays inside
+        ok = np.isfinite(want) & (np.abs(want) > 1e-30) & (np.abs(want) < 1e30)
+        assert ok.sum() > 0 and rel_err(got[ok], want[ok]) < 1e-3
+    else:
+        assert rel_err(got, want) < 1e-5
     if axis == 1 and rop != w.ReduceOp.Prod:
         # and against the library's own single-launch column reduce of the stored product
         rc = w.TensorBuilder.vector(N, STORAGE).build(dev)
