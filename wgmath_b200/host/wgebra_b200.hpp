@@ -319,6 +319,16 @@ class Gemm {  // gemm.rs:9-127
         check(wgb_gemm_op(pass.raw(), (wgb_gemm_variant)variant, out.buffer()->raw, &so, m1.buffer()->raw, &s1, m2.buffer()->raw, &s2,
                           DType<T>::value, DType<T>::value, f32_mode, (wgb_op_assign_variant)op, operand.buffer()->raw, &se));
     }
+
+    // Extension (wgb_gemm_reduce): result[j] = reduce_op over column j of m1 * m2 (axis 1) or result[i] over row i (axis 2); the
+    // product is never stored — Gemm::dispatch + one Reduce::dispatch per GpuMatrix::column(j) in one pass over the operands.
+    template <typename T> void dispatch_reduce(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, GpuVectorView<float> result,
+                                               GpuCubeView<T> m1, GpuCubeView<T> m2, int reduce_op /* ReduceOp */, int axis = 1,
+                                               GemmVariant variant = GemmVariant::Gemm) const {
+        const ViewShape rs = shapes.get(d, result.shape()), s1 = shapes.get(d, m1.shape()), s2 = shapes.get(d, m2.shape());
+        check(wgb_gemm_reduce(pass.raw(), (wgb_gemm_variant)variant, axis, (wgb_reduce_op)reduce_op, result.buffer()->raw, &rs, m1.buffer()->raw,
+                              &s1, m2.buffer()->raw, &s2, DType<T>::value, f32_mode));
+    }
 };
 
 // Extension (wgb_graph_*): record a dispatch chain once, replay it with one launch.
@@ -355,6 +365,14 @@ class Gemv {  // gemv.rs:9-137
         const ViewShape so = shapes.get(d, out.shape()), sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape()), se = shapes.get(d, operand.shape());
         check(wgb_gemv_op(pass.raw(), (wgb_gemv_variant)variant, out.buffer()->raw, &so, m.buffer()->raw, &sm, m.ordering(), v.buffer()->raw, &sv,
                           (int)op, operand.buffer()->raw, &se));
+    }
+    // result = reduce_op(m * v): Gemv::dispatch + Reduce::dispatch(out, result) as one launch (wgb_gemv_reduce), bit-identical to the chain
+    template <typename T> void dispatch_reduce(const Device &d, const ViewShapeBuffers &shapes, ComputePass &pass, const GpuScalar<T> &result,
+                                               GpuCubeView<T> m, GpuCubeView<T> v, int reduce_op /* ReduceOp */,
+                                               GemvVariant variant = GemvVariant::Gemv) const {
+        const ViewShape sm = shapes.get(d, m.shape()), sv = shapes.get(d, v.shape());
+        check(wgb_gemv_reduce(pass.raw(), (wgb_gemv_variant)variant, (wgb_reduce_op)reduce_op, result.buffer()->raw, m.buffer()->raw, &sm,
+                              m.ordering(), v.buffer()->raw, &sv));
     }
 };
 
