@@ -503,7 +503,9 @@ wgb_status wgb_gemm_row_sharded_fused_ex(wgb_pass *pass, wgb_gemm_variant varian
 
 /* The same collective with HOST operands, enqueued (the N > 1 counterpart of wgb_gemm_host_enqueue): this rank's dense
  * column-major A block ([M_local x K], or [K x M_local] for the transposed variants) and B ([K x N]) are uploaded into one of two
- * alternating device slots, the fused GEMM + all-gather runs once they have landed, and the result is downloaded into out_host:
+ * alternating device slots (when the context also has a communicator of the same ranks, wgb_comm_init_rank, each rank uploads only
+ * its 1/P column slice of B and the slices are all-gathered over NVLink: B crosses the host links once per box; WGB_SHARD_B_UPLOAD=0
+ * restores the whole-B upload), the fused GEMM + all-gather runs once they have landed, and the result is downloaded into out_host:
  * this rank's [M_local x N] panel (download_all == 0; the ranks of a box assemble C in host memory) or the whole gathered cube
  * [M_local x N x nranks].  Returns once everything is queued: the upload of the next product overlaps the GEMM and the download
  * of this one.  out_host is complete after wgb_ctx_sync(), or after wgb_gemm_host_flush() for later work on the queue.  Pinned
