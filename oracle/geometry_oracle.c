@@ -40,7 +40,11 @@
  * PARITY PINNING: the reference holds no golden vectors for these functions; its tests (cholesky.rs:86-149, lu.rs:129-181,
  * qr2.rs:70-121, eig2.rs:69-114, eig3.rs:71-131, eig4.rs:72-131, svd2.rs:68-107, svd3.rs:70-111) compare with nalgebra on
  * unseeded random batches of 345.  tests/test_geometry_oracle.py replays them against this file with numpy float64 in
- * nalgebra's place.  Beyond that: parity unpinned.
+ * nalgebra's place.  Beyond that it is pinned to outputs of the reference's own shader text: the unmodified .wgsl libraries,
+ * composed with the test kernels embedded in those Rust tests, are executed by tests/golden/wgsl_interp.py
+ * (tests/golden/make_reference_vectors.py -> ref_wgsl_geometry.npz) and tests/test_reference_vectors.py requires this file to
+ * reproduce all 17 families word for word (factors, permutations, padding).  Not pinnable here: what WGSL leaves to the
+ * backend (contraction, accuracy of sin / cos / atan) — there is no wgpu runtime in this image.
  */
 #include <math.h>
 #include <stdint.h>

@@ -20,7 +20,10 @@
  * All arithmetic is u32 (wrapping).  PARITY PINNING: the reference's own tests compare with a sequential CPU scan
  * (prefix_sum.rs:101-117 eval_cpu; LEN = 15071, inputs all-ones / iota / random % 10000, prefix_sum.rs:243-288) and with a
  * stable CPU argsort (radix_sort/mod.rs:238-330: 15 keys x 128 variations, values = 2 * key + 5).  tests/test_oracle.py replays
- * both against this file; integer results are unique, so parity is bit-exact.
+ * both against this file; integer results are unique, so parity is bit-exact.  In addition the reference's own shaders
+ * (prefix_sum.wgsl; sorting.wgsl + the six sort_*.wgsl, with the host sequences of prefix_sum.rs:47-99 and mod.rs:204-322) are
+ * executed by tests/golden/wgsl_interp.py and their outputs (tests/golden/ref_wgsl_scan_sort.npz) must equal this file's
+ * (tests/test_reference_vectors.py).
  */
 #include <stdint.h>
 #include <stdlib.h>
