@@ -5,7 +5,8 @@ This is the generating script of those fixtures.  It runs in the build container
 not exist on the GPU box); tests read the committed .npz files.  The shader text is composed the way the reference's Rust
 side composes it — each step below cites the Rust lines it mirrors — and dispatched with the reference's grid rules.
 
-    python tests/golden/make_reference_vectors.py [linalg] [geometry] [scan_sort]     (default: all)
+    python tests/golden/make_reference_vectors.py [linalg] [geometry] [scan_sort] [check]    (default: all families; `check`
+    re-runs and compares with the committed files instead of writing them; about 12 minutes for everything)
 """
 import os
 import sys
@@ -29,6 +30,23 @@ def read(rel):
 
 def u8(a):
     return a.view(np.uint8)
+
+
+CHECK = False
+
+
+def save(name, out):
+    """writes the fixture, or with `check` on the command line compares a fresh run with the committed file"""
+    path = os.path.join(HERE, name)
+    if not CHECK:
+        np.savez_compressed(path, **out)
+        return
+    old = np.load(path)
+    assert sorted(old.files) == sorted(out), f"{name}: case lists differ"
+    bad = [k for k in out if not np.array_equal(np.asarray(out[k]).view(np.uint32), old[k].view(np.uint32))]
+    print(f"check {name}: {len(out) - len(bad)} of {len(out)} buffers reproduce bit for bit" + (f"; DIFFERENT: {bad}" if bad else ""), flush=True)
+    if bad:
+        raise SystemExit(1)
 
 
 # ------------------------------------------------------------------------------------------------ wgebra::linalg
@@ -108,7 +126,7 @@ def make_linalg():
         t = time.time()
         out[case["name"]] = run[case["kind"]](case)
         print(f"{case['kind']:10s} {case['name']:32s} {time.time() - t:7.1f} s", flush=True)
-    np.savez_compressed(os.path.join(HERE, "ref_wgsl_linalg.npz"), **out)
+    save("ref_wgsl_linalg.npz", out)
 
 
 # ------------------------------------------------------------------------------------------------ wgebra::geometry
@@ -196,7 +214,7 @@ def make_geometry():
         pr.dispatch("test", {(0, 0): u8(packed.reshape(-1)), (0, 1): u8(res.reshape(-1))}, (n, 1, 1))   # .dispatch(matrices.len()) cholesky.rs:119
         out[f"{op}{dim}"] = res
         print(f"geometry   {op}{dim:<28d} {time.time() - t:7.1f} s", flush=True)
-    np.savez_compressed(os.path.join(HERE, "ref_wgsl_geometry.npz"), **out)
+    save("ref_wgsl_geometry.npz", out)
 
 
 # ------------------------------------------------------------------------------------------------ prefix sum / radix sort
@@ -284,11 +302,12 @@ def make_scan_sort():
         k, v, oob = run_radix_sort(keys, values, case["n_sort"], case["bits"])
         out["sort/" + case["name"] + "/keys"], out["sort/" + case["name"] + "/values"] = k, v
         print(f"sort       {case['name']:32s} {time.time() - t:7.1f} s   ({oob} out-of-bounds reads served by robust buffer access)", flush=True)
-    np.savez_compressed(os.path.join(HERE, "ref_wgsl_scan_sort.npz"), **out)
+    save("ref_wgsl_scan_sort.npz", out)
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["linalg", "geometry", "scan_sort"]
+    CHECK = "check" in sys.argv[1:]
+    which = [a for a in sys.argv[1:] if a != "check"] or ["linalg", "geometry", "scan_sort"]
     if "linalg" in which:
         make_linalg()
     if "geometry" in which:
