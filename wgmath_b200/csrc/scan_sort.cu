@@ -43,7 +43,9 @@ namespace {
 // waits on hundreds of predecessors: 2.4 TB/s (one-warp window), 2.4 TB/s (whole-CTA window), 2.9 TB/s (two-level group
 // descriptors) against 4.4-5.1 TB/s for the same kernels with the look-back switched off.  A fourth variant (16384-element
 // tiles, 64-descriptor window, ticketed tiles) was validated bit-exact in round 2 and measured 159 us vs 131 us for the three-step
-// form at n = 2^26 (3.4 vs 4.1 TB/s of algorithmic bytes): also retired (profiles/README.md).
+// form at n = 2^26 (3.4 vs 4.1 TB/s of algorithmic bytes): also retired (profiles/README.md).  A fifth, without any look-back chain
+// (one persistent kernel, chunks re-read from L2 between a reduce and a scan pass, chunk-level counters only), was correct and
+// took 175 us: profiles/r2_scan_stream_experiment/.
 constexpr int kScanRounds = 8;                         // 128-bit accesses per lane and warp tile
 constexpr int kScanWarpTile = kScanRounds * 128;       // 1024 elements per warp tile
 constexpr int kScanThreads = 256;
