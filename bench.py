@@ -95,6 +95,7 @@ class ClockSampler:
         self.samples, self.power, self.reasons, self.max_mhz, self.ok = [], [], set(), None, False
         self._active = threading.Event()
         self._stop = threading.Event()
+        self._lock = threading.Lock()
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -107,20 +108,31 @@ class ClockSampler:
         except Exception as e:  # NVML missing: report it, do not guess
             self.err = repr(e)
 
-    def _run(self):
+    def sample_now(self):
+        """One sample, taken by the caller's thread.  The timing loops call it between queueing the timed steps and waiting for
+        them, so that a window has at least one sample under load even when the polling thread is starved (seen once at 8
+        ranks: NVML answered none of the thread's calls inside a 141 ms window)."""
+        if not self.ok:
+            return
         nv = self._nv
+        try:
+            mhz = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+            watts = nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        except Exception:
+            return
+        with self._lock:
+            self.samples.append(mhz)
+            self.power.append(watts)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+
+    def _run(self):
         while not self._stop.is_set():
             if self._active.is_set():
-                try:
-                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-                    self.power.append(nv.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                        else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-                    for bit, name in self.REASONS.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
+                self.sample_now()
                 time.sleep(0.002)
             else:
                 time.sleep(0.0005)
@@ -285,6 +297,7 @@ def main_gpu(args):
             check(L.wgb_event_record(e1, p._h))
             p.end()
             gpu.queue().submit(enc.finish())
+            sampler.sample_now()          # the device is still working through the queued steps here
             barrier_sync()
         ms = ctypes.c_float()
         check(L.wgb_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
