@@ -228,6 +228,64 @@ def test_interp_arithmetic_model():
     assert u.tolist() == [0xFFFFFFFE, 1, 12, 9, 32] and c[0] == 6
 
 
+def test_interp_control_flow_swizzles_bitcasts_and_struct_pointers():
+    src = """
+    struct Pair { lo: vec2<f32>, n: u32 }
+    @group(0) @binding(0) var<storage, read_write> o: array<f32>;
+    @group(0) @binding(1) var<storage, read_write> u: array<u32>;
+    fn grow(p: ptr<function, Pair>) { (*p).lo.y += 1.0; (*p).n++; }
+    fn classify(k: u32) -> u32 {
+      switch k { case 0u, 1u: { return 10u; } case 2u: { return 20u; } default: { return 30u; } }
+    }
+    fn fast_rsqrt(val: f32) -> f32 {           // the bit trick svd3.wgsl uses: i32 arithmetic shift, wrapping subtraction
+      var i = bitcast<i32>(val);
+      i = 0x5f375a82 - (i >> 1);
+      return bitcast<f32>(i);
+    }
+    @compute @workgroup_size(1)
+    fn main() {
+      var i = 0u;
+      var acc = 0u;
+      loop {
+        if i == 2u { i++; continue; }
+        acc += i;
+        continuing { i++; break if i >= 6u; }
+      }
+      u[0] = acc;                              // 0 + 1 + 4 + 5: at i = 2 the body bumps i and `continue` still runs `continuing`
+      u[1] = classify(1u) + classify(2u) + classify(7u);
+      var p = Pair(vec2(1.0, 2.0), 5u);
+      grow(&p);
+      let q = &p;
+      (*q).lo.x = 9.0;
+      o[0] = p.lo.x + p.lo.y;
+      u[2] = p.n;
+      let v = vec4(1.0, 2.0, 3.0, 4.0);
+      let w = v.zyx;
+      o[1] = w.x * 100.0 + w.y * 10.0 + w.z;
+      var m = mat3x3<f32>();
+      m[1] = vec3(1.0, 2.0, 3.0);
+      m[2][0] = 7.0;
+      o[2] = (m * vec3(0.0, 1.0, 1.0)).x;
+      o[3] = select(vec2(1.0, 2.0), vec2(3.0, 4.0), vec2(true, false)).x + select(vec2(1.0, 2.0), vec2(3.0, 4.0), vec2(true, false)).y;
+      o[4] = fast_rsqrt(4.0);
+      u[3] = bitcast<u32>(-0.0);
+      var k = -7i;
+      u[4] = u32(k >> 1u) & 0xffu;             // arithmetic shift: -4 -> 0xfc
+      u[5] = u32(k / 2i + 10i) * 10u + u32(k % 3i + 5i);   // truncating division and remainder: -3, -1
+      while k < 0i { k += 3i; }
+      u[6] = u32(k);
+      o[5] = max(o[6] - o[6], 1.5);            // inf - inf = nan: min / max return the other operand
+    }"""
+    o = np.zeros(7, np.float32)
+    o[6] = np.inf
+    u = np.zeros(7, np.uint32)
+    run(src, "main", {(0, 0): o.view(np.uint8), (0, 1): u.view(np.uint8)}, (1, 1, 1))
+    assert u.tolist() == [10, 60, 6, 0x80000000, 0xFC, 74, 2]
+    i = np.array([4.0], np.float32).view(np.int32)[0]
+    want = np.array([0x5f375a82 - (int(i) >> 1)], np.int32).view(np.float32)[0]
+    assert o[:6].tolist() == [12.0, 321.0, 8.0, 5.0, want, 1.5]
+
+
 def test_interp_rejects_what_it_cannot_run_faithfully():
     oob = """
     @group(0) @binding(0) var<storage, read_write> d: array<f32>;
