@@ -77,6 +77,9 @@ def lib():
         L.orc_geom_in_words.argtypes = [ctypes.c_int]
         L.orc_geom_in_words.restype = ctypes.c_uint32
         L.orc_num_threads.restype = ctypes.c_int
+        L.orc_shape_index.restype = ctypes.c_uint32
+        L.orc_shape_index.argtypes = [ctypes.POINTER(Shape), ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                      ctypes.POINTER(ctypes.c_uint32)]
         L.orc_set_num_threads.argtypes = [ctypes.c_int]
         L.orc_set_num_threads.restype = None
         _lib = L
@@ -109,6 +112,13 @@ def gemm_ord(variant, out, so, out_rm, m1, s1, m1_rm, m2, s2, m2_rm) -> int:
 def gemv_ord(variant, out, so, m, sm, m_rm, v, sv) -> int:
     return lib().orc_gemv_ord(variant, _fp(out), ctypes.byref(so), _fp(m), ctypes.byref(sm), int(m_rm), _fp(v),
                               ctypes.byref(sv))
+
+
+def shape_index(s: Shape, row_major: bool, fn: int, i: int, j: int = 0, t: int = 0):
+    """shape.wgsl's iv (fn 0) / im (1) / it (2) and with_vec4_elts for a column- or row-major view: (index, 6 u32 of the vec4 shape)"""
+    v4 = (ctypes.c_uint32 * 6)()
+    idx = lib().orc_shape_index(ctypes.byref(s), int(row_major), fn, i, j, t, v4)
+    return idx, tuple(v4)
 
 
 def op_assign(op, a, sa, b, sb) -> int:

@@ -5,7 +5,7 @@ This is the generating script of those fixtures.  It runs in the build container
 not exist on the GPU box); tests read the committed .npz files.  The shader text is composed the way the reference's Rust
 side composes it — each step below cites the Rust lines it mirrors — and dispatched with the reference's grid rules.
 
-    python tests/golden/make_reference_vectors.py [linalg] [geometry] [scan_sort] [check]    (default: all families; `check`
+    python tests/golden/make_reference_vectors.py [shape] [linalg] [geometry] [scan_sort] [check]    (default: all families; `check`
     re-runs and compares with the committed files instead of writing them; about 12 minutes for everything)
 """
 import os
@@ -305,9 +305,35 @@ def make_scan_sort():
     save("ref_wgsl_scan_sort.npz", out)
 
 
+# ------------------------------------------------------------------------------------------------ shape.wgsl by itself
+def make_shape():
+    """iv / im / it / with_vec4_elts of shape.wgsl, called directly, for the column-major build and for the ROW_MAJOR build
+    (row_major_shader_defs(), shape.rs:11-15)"""
+    out = {"views": np.array(C.SHAPE_VIEWS, np.uint32), "queries": np.array(C.SHAPE_QUERIES, np.uint32)}
+    for tag, defs in (("col", ()), ("row", ("ROW_MAJOR",))):
+        pr = W.Program()
+        mod = pr.set_main(read("wgebra/src/linalg/shape.wgsl"), defs)
+        ty = mod.resolve_type(("ty", "Shape", [], 0))
+        names = [n for n, _ in ty.members]
+        res = np.zeros((len(C.SHAPE_VIEWS), len(C.SHAPE_QUERIES), 3), np.uint32)
+        v4 = np.zeros((len(C.SHAPE_VIEWS), 6), np.uint32)
+        for a, view in enumerate(C.SHAPE_VIEWS):
+            sv = W.StructVal(ty, {n: np.uint32(x) for n, x in zip(names, view)})
+            r = pr.call_function("with_vec4_elts", [sv])
+            v4[a] = [r.f[n] for n in names]
+            for q, (i, j, t) in enumerate(C.SHAPE_QUERIES):
+                i, j, t = np.uint32(i), np.uint32(j), np.uint32(t)
+                res[a, q] = [pr.call_function("iv", [sv, i]), pr.call_function("im", [sv, i, j]), pr.call_function("it", [sv, i, j, t])]
+        out[tag + "/index"], out[tag + "/vec4"] = res, v4
+    save("ref_wgsl_shape.npz", out)
+    print("shape      iv / im / it / with_vec4_elts, both builds", flush=True)
+
+
 if __name__ == "__main__":
     CHECK = "check" in sys.argv[1:]
-    which = [a for a in sys.argv[1:] if a != "check"] or ["linalg", "geometry", "scan_sort"]
+    which = [a for a in sys.argv[1:] if a != "check"] or ["shape", "linalg", "geometry", "scan_sort"]
+    if "shape" in which:
+        make_shape()
     if "linalg" in which:
         make_linalg()
     if "geometry" in which:

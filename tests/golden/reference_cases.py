@@ -224,3 +224,9 @@ def sort_input(case):
         keys = keys % np.uint32(7) + (keys & np.uint32(0xFFFF0000))      # few distinct low digits, noise above the sorted bits
     values = keys * np.uint32(2) + np.uint32(5)                           # mod.rs:267
     return keys, values
+
+
+# ------------------------------------------------------------------------------------------------ shape.wgsl index functions
+SHAPE_VIEWS = [(10, 7, 3, 12, 100, 5), (64, 64, 1, 64, 4096, 0), (30, 18, 2, 32, 640, 8), (1, 1, 1, 1, 1, 3), (7, 5, 4, 9, 63, 2),
+               (4096, 4096, 1, 4096, 1 << 24, 0)]
+SHAPE_QUERIES = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (3, 4, 2), (6, 4, 3), (9, 6, 1), (29, 17, 1), (4095, 4095, 0)]   # (i, j, t)

@@ -61,6 +61,29 @@ def test_every_stored_vector_has_a_case(linalg_vectors):
     assert sorted(linalg_vectors.files) == sorted(c["name"] for c in C.all_linalg_cases())
 
 
+def test_shape_index_functions_match_shape_wgsl_in_both_builds():
+    """shape.wgsl's iv / im / it / with_vec4_elts executed by the interpreter in the column-major build and in the ROW_MAJOR build
+    (shape.rs:11-15): the oracle's index functions — what orc_gemm / orc_gemm_ord address memory with — and the element
+    addressing of the host mirror's views agree with both tables."""
+    import wgmath_b200 as w
+    g = np.load(os.path.join(GOLD, "ref_wgsl_shape.npz"))
+    assert g["views"].tolist() == [list(v) for v in C.SHAPE_VIEWS] and g["queries"].tolist() == [list(q) for q in C.SHAPE_QUERIES]
+    for tag, rm in (("col", False), ("row", True)):
+        for a, view in enumerate(C.SHAPE_VIEWS):
+            s = O.Shape(*view)
+            for q, (i, j, t) in enumerate(C.SHAPE_QUERIES):
+                want = g[tag + "/index"][a, q]
+                got = [O.shape_index(s, rm, fn, i, j, t)[0] for fn in (0, 1, 2)]
+                assert got == want.tolist(), (tag, view, (i, j, t))
+            assert list(O.shape_index(s, rm, 0, 0)[1]) == g[tag + "/vec4"][a].tolist()
+            # host mirror: a view's sub-view constructors move `offset` by the same element strides
+            vs = w.ViewShape((view[0], view[1], view[2]), view[3], view[4], view[5])
+            tv = w.GpuTensorView(vs, None, "f32", 3, w.RowMajor if rm else w.ColumnMajor)
+            if view[0] > 3 and view[1] > 4 and view[2] > 2:
+                sub = tv.matrix(2).columns(4, 1).rows(3, 1)
+                assert sub.shape().offset == int(g[tag + "/index"][a, 3][2])          # query (3, 4, 2)
+
+
 # ------------------------------------------------------------------------------------------------ factorizations, scan, sort
 @pytest.fixture(scope="module")
 def geometry_vectors():
