@@ -81,6 +81,10 @@ def gemv_cases():
                             4 + 12 * C * T, 4 + 16 * K * T, 4 + (K + 4) * C * T))
     cases.append(_gemv_case("fast_views", "gemv_tr_fast", (M, C, T, 12, 12 * C, 4), (K, M, T, K + 4, (K + 4) * M, 4), (K, C, T, K + 4, (K + 4) * C, 4),
                             4 + 12 * C * T, 4 + (K + 4) * M * T, 4 + (K + 4) * C * T))
+    # dimensions that are not multiples of 4 (buffers padded to whole vec4 blocks, K padding zero, as for the ragged gemm cases)
+    M, K = 30, 46
+    cases.append(_gemv_case("ragged", "gemv", (M, 1, 1, 32, 32, 0), (M, K, 1, 32, 32 * 48, 0), (K, 1, 1, 48, 48, 0), 32, 32 * 48, 48) | dict(zero_k_padding=("cols", "rows")))
+    cases.append(_gemv_case("ragged", "gemv_tr", (M, 1, 1, 32, 32, 0), (K, M, 1, 48, 48 * 32, 0), (K, 1, 1, 48, 48, 0), 32, 48 * 32, 48) | dict(zero_k_padding=("rows", "rows")))
     return cases
 
 
@@ -139,7 +143,12 @@ def inputs(case):
             _zero_k(m2, case["s2"], case["zero_k_padding"][1], K)
         return dict(out=np.full(case["len_out"], -7.0, np.float32), m1=m1, m2=m2)
     if k == "gemv":
-        return dict(out=_uniform(h + 4, case["len_out"]), m=_uniform(h + 1, case["len_m"]), v=_uniform(h + 3, case["len_v"]))
+        m, v = _uniform(h + 1, case["len_m"]), _uniform(h + 3, case["len_v"])
+        if case.get("zero_k_padding"):
+            K = case["sv"][0]
+            _zero_k(m, case["sm"], case["zero_k_padding"][0], K)
+            _zero_k(v, case["sv"], case["zero_k_padding"][1], K)
+        return dict(out=_uniform(h + 4, case["len_out"]), m=m, v=v)
     if k == "op_assign":
         if case["fixture"]:
             i = np.arange(case["len_a"], dtype=np.float32)
