@@ -197,7 +197,8 @@ def cpu_gemm_sample(target_s: float, n: int = 4096, repeat: int = 1):
         times.append(time.perf_counter() - t0)
     dt = float(np.median(times))
     desc = (f"rows 0..{rows} of the {n}^3 product ({rows}x{n}x{n}), f32, oracle port of gemm.wgsl:81-113 "
-            f"(wgpu fallback adapter unavailable: no Rust/Vulkan in the image), OpenMP over invocations")
+            f"(reproduces the shader's output bit for bit: tests/test_reference_vectors.py; the reference's own wgpu fallback "
+            f"adapter cannot run here: no Rust/Vulkan in the image), OpenMP over invocations")
     return 2.0 * rows * n * n / dt / 1e12, cores, desc, dt, rows
 
 
