@@ -59,6 +59,11 @@ def test_oracle_reproduces_the_reference_shaders_bit_for_bit(linalg_vectors, cas
 
 def test_every_stored_vector_has_a_case(linalg_vectors):
     assert sorted(linalg_vectors.files) == sorted(c["name"] for c in C.all_linalg_cases())
+    geo = np.load(os.path.join(GOLD, "ref_wgsl_geometry.npz"))
+    assert sorted(geo.files) == sorted(f"{op}{dim}" for op, dim in C.geometry_cases())
+    ss = np.load(os.path.join(GOLD, "ref_wgsl_scan_sort.npz"))
+    want = ["scan/" + c["name"] for c in C.scan_cases()] + [f"sort/{c['name']}/{w}" for c in C.sort_cases() for w in ("keys", "values")]
+    assert sorted(ss.files) == sorted(want)
 
 
 def test_shape_index_functions_match_shape_wgsl_in_both_builds():
