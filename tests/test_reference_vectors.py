@@ -314,6 +314,38 @@ def test_interp_control_flow_swizzles_bitcasts_and_struct_pointers():
     assert o[:6].tolist() == [12.0, 321.0, 8.0, 5.0, want, 1.5]
 
 
+def test_interp_matrix_conventions_and_precedence():
+    """WGSL matrices are column-major: matCxR has C columns of R rows, m[c][r]; M * v combines columns, v * M dots with columns."""
+    src = """
+    @group(0) @binding(0) var<storage, read_write> o: array<f32>;
+    @group(0) @binding(1) var<storage, read_write> m_io: mat2x3<f32>;
+    @compute @workgroup_size(1)
+    fn main() {
+      let m = mat2x3<f32>(1.0, 2.0, 3.0, 4.0, 5.0, 6.0);       // columns (1,2,3) and (4,5,6)
+      let a = m * vec2(10.0, 100.0);                             // 10 * col0 + 100 * col1
+      o[0] = a.x; o[1] = a.y; o[2] = a.z;
+      let b = vec3(1.0, 10.0, 100.0) * m;                        // (dot(v, col0), dot(v, col1))
+      o[3] = b.x; o[4] = b.y;
+      let t = transpose(m);                                      // mat3x2: t[r][c] = m[c][r]
+      o[5] = t[2][1];
+      let p = t * m;                                             // (2 rows x 3 columns) * (3 rows x 2 columns) = mat2x2
+      o[6] = p[1][0];                                            // column 1, row 0
+      o[7] = 2.0 + 3.0 * 4.0 - 6.0 / 3.0;                        // 12
+      o[8] = f32((7u & 3u) | (8u >> 2u)) + f32(1u << 3u);        // (3 | 2) + 8 = 11
+      o[9] = f32(-3i * -3i % 5i);                                // 9 % 5 = 4
+      o[10] = select(1.0, 2.0, 1.0 < 2.0 && !(3.0 <= 2.0) || false);
+      m_io[1][2] = m_io[0][1] + 0.5;                             // storage layout: column stride 16 bytes for 3 rows
+    }"""
+    o = np.zeros(11, np.float32)
+    mio = np.arange(8, dtype=np.float32)                          # col0 = (0,1,2), pad, col1 = (4,5,6), pad
+    run(src, "main", {(0, 0): o.view(np.uint8), (0, 1): mio.view(np.uint8)}, (1, 1, 1))
+    assert o[:6].tolist() == [410.0, 520.0, 630.0, 321.0, 654.0, 6.0]
+    # t is 3 columns of 2 rows: t[c][r] = m[r][c]; (t * m)[1][0] = sum_k t[k][0] * m[1][k] = 1*4 + 2*5 + 3*6
+    assert o[6] == 32.0
+    assert o[7:].tolist() == [12.0, 11.0, 4.0, 2.0]
+    assert mio.tolist() == [0, 1, 2, 3, 4, 5, 1.5, 7]
+
+
 def test_interp_rejects_what_it_cannot_run_faithfully():
     oob = """
     @group(0) @binding(0) var<storage, read_write> d: array<f32>;
